@@ -1,0 +1,196 @@
+/*
+ * segland_b200.h -- C ABI of libsegland_b200.so
+ *
+ * The drop-in boundary for SegLand's POP-head + dense post-processing hot path
+ * (SURVEY.md section 8).  The reference has no FFI layer of its own: its "operator
+ * surface" is a set of Python functions.  Each entry point below names the
+ * reference function (file:line under the SegLand tree) whose arithmetic it
+ * replaces; segland_b200/ops.py binds them with ctypes and keeps the reference's
+ * Python signatures (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - the library never allocates, frees or synchronises: the caller owns every
+ *     buffer and passes the CUDA stream (a cudaStream_t cast to void*, NULL = the
+ *     legacy default stream) the work is queued on;
+ *   - the device is the caller's current CUDA device; entry points are re-entrant
+ *     and may be called concurrently on different streams / devices;
+ *   - return value: 0 on success, a negative SL_E* code for argument errors
+ *     (nothing was launched), or a positive cudaError_t from the launch;
+ *   - tensors are dense, row-major, in the reference's own layout (NCHW);
+ *   - "bf16" buffers are raw uint16_t bit patterns of __nv_bfloat16.
+ *   - accumulating outputs (confusion matrices, inter/union meters) are ADDED to:
+ *     zero them once per sweep, not per call.
+ */
+#ifndef SEGLAND_B200_H
+#define SEGLAND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SL_ABI_VERSION 1
+
+#define SL_OK 0
+#define SL_EINVAL (-1)      /* a size/shape argument is out of the supported range   */
+#define SL_ENULL (-2)       /* a required pointer is NULL                             */
+#define SL_EALIGN (-3)      /* a pointer/extent violates the stated alignment         */
+#define SL_EUNSUPPORTED (-4)/* the device is not sm_100 (this library is B200-only)  */
+
+#define SL_MAX_CLASSES 32   /* 1 + Kb + Kn must be <= 32 (OEM: 12)                    */
+#define SL_MAX_FUSE 16      /* fusemat model count M <= 16                            */
+
+int sl_abi_version(void);
+/* Static string for any code an entry point can return (SL_E* or cudaError_t). */
+const char *sl_error_string(int code);
+/* 0 iff the current device is compute capability 10.x; SL_EUNSUPPORTED otherwise. */
+int sl_check_device(void);
+
+/* ---------------------------------------------------------------------------
+ * (a1/a2) POP head -- GFSS_Model.orthogonal_decompose + classifier/classifier_n
+ *   networks/pspnet_pop.py:95-121 (decompose), :46-52,57-63 (3-layer 1x1 MLP),
+ *   :143-159 (forward_all), :171-182 (forward_base).  Identical bodies in
+ *   networks/{pspplus,deeplab,vggunet,seghr,swin,convnext,lsk}_pop.py.
+ *
+ * sl_pop_prepare: everything that depends only on weights/prototypes.
+ *   protos  [K,C] fp32 raw prototypes, base classes first then novel
+ *           (cat[base_emb, novel_emb]); K = Kb + Kn >= 1; C % 8 == 0, 8 <= C <= 1024.
+ *   W1_fg/W2_fg [C,C], w3_fg [C]: the MLP applied to classes [0,Kb)  (self.classifier)
+ *   W1_bg/W2_bg/w3_bg: the MLP applied to the background vector and to classes
+ *           [Kb,K) (self.classifier_n in ft mode; pass the same pointers as *_fg in
+ *           base mode, pspnet_pop.py:178-182).
+ * outputs
+ *   s_hat   [K,C]  F.normalize(protos, p=2, dim=-1), eps 1e-12 (pspnet_pop.py:106,113)
+ *   alpha,beta [K] alpha_k = MLP(+s_hat_k), beta_k = MLP(-s_hat_k): the MLP is
+ *           bias-free with ReLUs, hence positively homogeneous, so the logit of the
+ *           rank-1 foreground vector p*s_hat_k is p>=0 ? p*alpha_k : -p*beta_k.
+ *   W1p_t   [C_in][C_out] fp32, transposed W1' = W1_bg (I - S_hat^T S_hat): folds
+ *           "bg = q - sum_k p_k s_hat_k" (pspnet_pop.py:112,118) into layer 1.
+ *   W2_t    [C_in][C_out] fp32, transposed W2_bg.
+ *   W1p_hi/lo, W2_hi/lo  [C_out][C_in] bf16 split (hi = bf16(W), lo = bf16(W - hi)) for
+ *           the tensor-core path; may all be NULL when only the SIMT path is used.
+ */
+int sl_pop_prepare(const float *protos, int K, int Kb, int C,
+                   const float *W1_fg, const float *W2_fg, const float *w3_fg,
+                   const float *W1_bg, const float *W2_bg, const float *w3_bg,
+                   float *s_hat, float *alpha, float *beta,
+                   float *W1p_t, float *W2_t,
+                   uint16_t *W1p_hi, uint16_t *W1p_lo, uint16_t *W2_hi, uint16_t *W2_lo,
+                   void *stream);
+
+/* K foreground logits at feature resolution (HBM-bound, CUDA cores).
+ *   feat   [B,C,N] bf16 (features.flatten(2), pspnet_pop.py:148); N % 8 == 0,
+ *          16-byte aligned.
+ *   logits [B,Ktot,N] fp32; channel ch_map[k] (host array of K ints) receives class
+ *          k's logit -- forward_all's order [bg, base.., novel..] (pspnet_pop.py:159)
+ *          is ch_map[k] = 1 + k.
+ */
+int sl_pop_fg_lowres(const uint16_t *feat, int B, int C, int N,
+                     const float *s_hat, const float *alpha, const float *beta, int K,
+                     float *logits, int Ktot, const int *ch_map_host, void *stream);
+
+/* Background logit (class 0), exact fp32 CUDA-core path:
+ *   logit_0 = w3 . relu(W2 relu(W1' q))   written to channel `ch` of logits.
+ */
+int sl_pop_bg_simt(const uint16_t *feat, int B, int C, int N,
+                   const float *W1p_t, const float *W2_t, const float *w3_bg,
+                   float *logits, int Ktot, int ch, void *stream);
+
+/* Background logit on tcgen05 tensor cores with split-bf16 operands (2 + 3 MMA
+ * passes, fp32 accumulation in TMEM).  C % 64 == 0, 64 <= C <= 512, N % 128 == 0.
+ * Returns SL_EINVAL for shapes outside that range (callers fall back to _simt).
+ */
+int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
+                 const uint16_t *W1p_hi, const uint16_t *W1p_lo,
+                 const uint16_t *W2_hi, const uint16_t *W2_lo, const float *w3_bg,
+                 float *logits, int Ktot, int ch, void *stream);
+
+/* Test-time view aggregation at feature resolution (spec: this repo -- the reference
+ * has no flip/sliding-window inference): out = scale * sum_v unflip(view_v).
+ *   views [V,B,K,h,w] fp32; flip_host[v] bit0 = horizontal flip, bit1 = vertical flip.
+ */
+int sl_views_reduce(const float *views, int V, int B, int K, int h, int w,
+                    const int *flip_host, float scale, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * (a4/a5) F.interpolate(bilinear, align_corners=True) -> argmax -> confusion
+ *   eval_base.py:168-178, eval_ft.py:168-183, ft_pop.py:327-331.
+ *   logits_lr [B,K,h,w] fp32; output size H x W; 2 <= K <= SL_MAX_CLASSES.
+ *   label   [B,H,W] u8 or NULL; pixels == ignore_label are excluded from cm.
+ *   pred    [B,H,W] u8 or NULL: first-maximum argmax (np.argmax semantics).
+ *   conf    [B,H,W] fp32 or NULL: max softmax probability (spec: this repo).
+ *   probs   [B,K,H,W] fp32 or NULL: softmax over channels (spec: this repo).
+ *   logits_hr [B,K,H,W] fp32 or NULL: the upsampled logits themselves
+ *           (what eval_base.py:190-191 dumps to .mat for fusemat.py).
+ *   cm      [K,K] int64 or NULL, row = gt, col = pred, ACCUMULATED
+ *           (get_confusion_matrix, utils/pyt_utils.py:182-200); requires label.
+ */
+int sl_upsample_argmax(const float *logits_lr, int B, int K, int h, int w, int H, int W,
+                       const uint8_t *label, int ignore_label,
+                       uint8_t *pred, float *conf, float *probs, float *logits_hr,
+                       long long *cm, void *stream);
+
+/* (a10) pseudo-labelling of base-image background, pspnet_pop.py:221-231:
+ *   idx = argmax(upsample(preds2[b])); idx[idx>0] += n_base; mask[b][mask[b]==0] = idx.
+ *   preds2 [B,K2,h,w] fp32 (K2 = 1+Kn); mask [B,H,W] int64, updated IN PLACE.
+ */
+int sl_pseudo_label(const float *preds2, int B, int K2, int h, int w, int H, int W,
+                    int n_base, long long *mask, void *stream);
+
+/* (a5) get_confusion_matrix(gt, pred, K), utils/pyt_utils.py:182-200, on label maps:
+ *   cm[gt*K+pred] += 1 for every i < n with gt[i] != ignore_label.  Labels >= K that
+ *   are not ignore_label are skipped and counted in *n_bad (int64, may be NULL).
+ */
+int sl_confusion(const uint8_t *gt, const uint8_t *pred, long long n, int K,
+                 int ignore_label, long long *cm, long long *n_bad, void *stream);
+
+/* (a7) intersectionAndUnionGPU(output, target, K, ignore), utils/pyt_utils.py:293-305.
+ *   output,target [n] int64.  Mirrors the reference's in-place side effect:
+ *   output[target == ignore] = ignore.  inter/uni/tgt [K] fp32 are OVERWRITTEN with the
+ *   per-call areas (the caller accumulates, ft_pop.py:333-334); cm_ws [K*K] int64 is
+ *   scratch the call zeroes itself.
+ */
+int sl_inter_union(long long *output, const long long *target, long long n, int K,
+                   int ignore_label, float *inter, float *uni, float *tgt,
+                   long long *cm_ws, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * (a9) masked_average_pooling(feature, mask), networks/pspnet.py:7-15
+ *   feat [B,C,h,w] bf16; mask [B,1,H,W] fp32.
+ *   mask_lr_ws [B,h*w] fp32 scratch (the align_corners bilinear down-sample of mask);
+ *   per_image [B,C] fp32 = sum_hw(f*m)/(sum_hw m + 1e-5); proto [C] fp32 = mean_B.
+ *   h*w % 8 == 0.
+ */
+int sl_map_proto(const uint16_t *feat, const float *mask, int B, int C, int h, int w,
+                 int H, int W, float *mask_lr_ws, float *per_image, float *proto,
+                 void *stream);
+
+/* (a8) OrthLoss.get_orth_loss, loss/criterion.py:37-43, with proto_sim built as in
+ *   pspnet_pop.py:185-186 (base: Kb_other = 0, rows = base_emb) and :234-239
+ *   (ft: rows = novel_emb, others = base_emb):
+ *   r_hat = normalize(rows), sim = r_hat @ cat[r_hat, normalize(others)]^T  [Kr, Kr+Ko]
+ *   loss = mean |sim[i][j]| over j > i.
+ *   proto_sim [Kr,Kr+Ko] fp32 (may be NULL), loss [1] fp32,
+ *   grad_rows [Kr,C] fp32 or NULL = d loss / d rows (others are frozen in ft mode).
+ */
+int sl_orth_loss(const float *rows, int Kr, const float *others, int Ko, int C,
+                 float *proto_sim, float *loss, float *grad_rows, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * (a11) fusemat.py:37-48: mats[0] + mats[1] + ... (sequential fp32 adds, in order),
+ *   / divisor (fp32 IEEE division by len(fusion_list)), argmax over K (first max).
+ *   mats_host: HOST array of M device pointers, each [K,HW] fp32; HW % 4 == 0.
+ *   pred [HW] u8; fused [K,HW] fp32 or NULL (the divided sum);
+ *   label/cm as in sl_upsample_argmax (optional mIoU of the fused map).
+ */
+int sl_fuse_argmax(const float *const *mats_host, int M, int K, long long HW, int divisor,
+                   uint8_t *pred, float *fused,
+                   const uint8_t *label, int ignore_label, long long *cm, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGLAND_B200_H */

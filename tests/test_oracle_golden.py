@@ -1,0 +1,97 @@
+"""Pins oracle/ref_ops.py against outputs of the reference's own functions
+(tests/golden/*.npz, written by oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops
+from helpers import bf16_from_bits, state_from_npz
+
+HEAD_CASES = ['head_base_c64', 'head_ft_c64', 'head_base_c512', 'head_ft_c192_s4', 'head_ft_c96_rand']
+
+
+@pytest.mark.parametrize('name', HEAD_CASES)
+def test_head_matches_reference(golden, name):
+    z = golden(name)
+    st = state_from_npz(z)
+    feats = bf16_from_bits(z['feats_bf16_bits']).float()
+    logits = ref_ops.ref_head(feats, st.base_emb, st.novel_emb, st.cls, st.cls_n)
+    assert logits.shape == z['logits'].shape
+    # same ops in the same order on the same CPU -> bit-exact
+    assert np.array_equal(logits.numpy(), z['logits'])
+    H, W = z['labels'].shape[-2:]
+    pred = ref_ops.ref_upsample_argmax(logits, (H, W))
+    assert np.array_equal(pred, z['pred'])
+    cm = sum(ref_ops.ref_confusion(z['labels'][t], pred[t], st.n_classes) for t in range(pred.shape[0]))
+    assert np.array_equal(cm, z['cm'])
+    assert cm.dtype == np.float64 and cm.sum() == (z['labels'] != 255).sum()
+    if 'upsampled' in z.files:
+        assert np.array_equal(ref_ops.ref_upsample(logits, (H, W)).numpy(), z['upsampled'])
+
+
+def test_upsample_cases(golden):
+    z = golden('upsample_cases')
+    i = 0
+    while f'in{i}' in z.files:
+        lg = torch.from_numpy(z[f'in{i}'])
+        H, W = z[f'out{i}'].shape[-2:]
+        assert np.array_equal(ref_ops.ref_upsample(lg, (H, W)).numpy(), z[f'out{i}'])
+        assert np.array_equal(ref_ops.ref_upsample_argmax(lg, (H, W)), z[f'pred{i}'])
+        i += 1
+    assert i >= 6
+
+
+def test_metrics(golden):
+    z = golden('metrics')
+    K = 12
+    cm = ref_ops.ref_confusion(z['gt'], z['pred'], K)
+    assert np.array_equal(cm, z['cm'])
+    out = torch.from_numpy(z['pred'].astype(np.int64))
+    tgt = torch.from_numpy(z['gt'].astype(np.int64))
+    inter, union, target = ref_ops.ref_inter_union(out, tgt, K, 255)
+    for mine, key in ((inter, 'inter'), (union, 'union'), (target, 'target')):
+        assert np.array_equal(mine.numpy(), z[key + '_t'])
+        assert np.array_equal(mine.numpy().astype(np.int64), z[key + '_np'])
+    assert np.array_equal(out.numpy(), z['output_after'])          # in-place side effect
+    # inter/union are the diagonal / row+col-diag of the confusion matrix
+    assert np.array_equal(np.diag(cm), z['inter_np'])
+    assert np.array_equal(cm.sum(0) + cm.sum(1) - np.diag(cm), z['union_np'])
+    base, novel, total, arr = ref_ops.ref_miou(cm, 7)
+    assert 0 < base < 1 and 0 < novel < 1 and abs(total - np.nanmean(arr)) < 1e-15
+
+
+def test_map(golden):
+    z = golden('map')
+    p = ref_ops.ref_masked_average_pooling(bf16_from_bits(z['feats_bf16_bits']).float(), torch.from_numpy(z['masks']))
+    assert np.array_equal(p.numpy(), z['proto'])
+    p2 = ref_ops.ref_masked_average_pooling(bf16_from_bits(z['feats2_bf16_bits']).float(), torch.from_numpy(z['masks2']))
+    assert np.array_equal(p2.numpy(), z['proto2'])
+
+
+def test_orth_and_pseudo(golden):
+    z = golden('orth_pseudo')
+    stb, stf = state_from_npz(z, 'b_'), state_from_npz(z, 'f_')
+    sim_b = ref_ops.ref_proto_sim_base(stb.base_emb)
+    assert np.allclose(sim_b.numpy(), z['sim_b'], rtol=0, atol=1e-7)
+    assert abs(ref_ops.ref_orth_loss(sim_b).item() - float(z['orth_b'])) < 1e-7
+    sim_f = ref_ops.ref_proto_sim_ft(stf.novel_emb, stf.base_emb)
+    assert np.array_equal(sim_f.numpy(), z['sim_f'])
+    assert ref_ops.ref_orth_loss(sim_f).item() == float(z['orth_f'])
+    assert sim_f.shape == (4, 11) and int(torch.triu(torch.ones_like(sim_f), 1).sum()) == 34
+    # pseudo-labelling of the base images (second half of the batch in forward_novel)
+    preds_all = torch.from_numpy(z['preds_all'])                   # eval-mode forward_all == train-mode preds
+    B = preds_all.shape[0]
+    preds2_base = torch.cat([preds_all[B // 2:, :1], preds_all[B // 2:, 1 + 7:]], dim=1)
+    mask_b = torch.from_numpy(z['mask_b_before'].copy())
+    new = ref_ops.ref_pseudo_label(preds2_base, mask_b, 7)
+    assert np.array_equal(new.numpy(), z['mask_b_after'])
+    assert np.array_equal(mask_b.numpy(), z['mask_b_after'])       # in place, like the reference
+
+
+def test_fuse(golden):
+    z = golden('fuse')
+    for tile in ('tile_a', 'tile_b'):
+        mats = [z[f'{tile}_m{m}'] for m in range(3)]
+        pred, fused = ref_ops.ref_fuse(mats)
+        assert fused.dtype == np.float32
+        assert np.array_equal(pred, z[f'{tile}_pred'])
