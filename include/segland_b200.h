@@ -34,6 +34,12 @@ extern "C" {
 
 #define SL_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define SL_API __attribute__((visibility("default")))
+#else
+#define SL_API
+#endif
+
 #define SL_OK 0
 #define SL_EINVAL (-1)      /* a size/shape argument is out of the supported range   */
 #define SL_ENULL (-2)       /* a required pointer is NULL                             */
@@ -43,11 +49,11 @@ extern "C" {
 #define SL_MAX_CLASSES 32   /* 1 + Kb + Kn must be <= 32 (OEM: 12)                    */
 #define SL_MAX_FUSE 16      /* fusemat model count M <= 16                            */
 
-int sl_abi_version(void);
+SL_API int sl_abi_version(void);
 /* Static string for any code an entry point can return (SL_E* or cudaError_t). */
-const char *sl_error_string(int code);
+SL_API const char *sl_error_string(int code);
 /* 0 iff the current device is compute capability 10.x; SL_EUNSUPPORTED otherwise. */
-int sl_check_device(void);
+SL_API int sl_check_device(void);
 
 /* ---------------------------------------------------------------------------
  * (a1/a2) POP head -- GFSS_Model.orthogonal_decompose + classifier/classifier_n
@@ -73,7 +79,7 @@ int sl_check_device(void);
  *   W1p_hi/lo, W2_hi/lo  [C_out][C_in] bf16 split (hi = bf16(W), lo = bf16(W - hi)) for
  *           the tensor-core path; may all be NULL when only the SIMT path is used.
  */
-int sl_pop_prepare(const float *protos, int K, int Kb, int C,
+SL_API int sl_pop_prepare(const float *protos, int K, int Kb, int C,
                    const float *W1_fg, const float *W2_fg, const float *w3_fg,
                    const float *W1_bg, const float *W2_bg, const float *w3_bg,
                    float *s_hat, float *alpha, float *beta,
@@ -88,14 +94,14 @@ int sl_pop_prepare(const float *protos, int K, int Kb, int C,
  *          k's logit -- forward_all's order [bg, base.., novel..] (pspnet_pop.py:159)
  *          is ch_map[k] = 1 + k.
  */
-int sl_pop_fg_lowres(const uint16_t *feat, int B, int C, int N,
+SL_API int sl_pop_fg_lowres(const uint16_t *feat, int B, int C, int N,
                      const float *s_hat, const float *alpha, const float *beta, int K,
                      float *logits, int Ktot, const int *ch_map_host, void *stream);
 
 /* Background logit (class 0), exact fp32 CUDA-core path:
  *   logit_0 = w3 . relu(W2 relu(W1' q))   written to channel `ch` of logits.
  */
-int sl_pop_bg_simt(const uint16_t *feat, int B, int C, int N,
+SL_API int sl_pop_bg_simt(const uint16_t *feat, int B, int C, int N,
                    const float *W1p_t, const float *W2_t, const float *w3_bg,
                    float *logits, int Ktot, int ch, void *stream);
 
@@ -103,7 +109,7 @@ int sl_pop_bg_simt(const uint16_t *feat, int B, int C, int N,
  * passes, fp32 accumulation in TMEM).  C % 64 == 0, 64 <= C <= 512, N % 128 == 0.
  * Returns SL_EINVAL for shapes outside that range (callers fall back to _simt).
  */
-int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
+SL_API int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
                  const uint16_t *W1p_hi, const uint16_t *W1p_lo,
                  const uint16_t *W2_hi, const uint16_t *W2_lo, const float *w3_bg,
                  float *logits, int Ktot, int ch, void *stream);
@@ -112,7 +118,7 @@ int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
  * has no flip/sliding-window inference): out = scale * sum_v unflip(view_v).
  *   views [V,B,K,h,w] fp32; flip_host[v] bit0 = horizontal flip, bit1 = vertical flip.
  */
-int sl_views_reduce(const float *views, int V, int B, int K, int h, int w,
+SL_API int sl_views_reduce(const float *views, int V, int B, int K, int h, int w,
                     const int *flip_host, float scale, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------
@@ -128,7 +134,7 @@ int sl_views_reduce(const float *views, int V, int B, int K, int h, int w,
  *   cm      [K,K] int64 or NULL, row = gt, col = pred, ACCUMULATED
  *           (get_confusion_matrix, utils/pyt_utils.py:182-200); requires label.
  */
-int sl_upsample_argmax(const float *logits_lr, int B, int K, int h, int w, int H, int W,
+SL_API int sl_upsample_argmax(const float *logits_lr, int B, int K, int h, int w, int H, int W,
                        const uint8_t *label, int ignore_label,
                        uint8_t *pred, float *conf, float *probs, float *logits_hr,
                        long long *cm, void *stream);
@@ -137,34 +143,35 @@ int sl_upsample_argmax(const float *logits_lr, int B, int K, int h, int w, int H
  *   idx = argmax(upsample(preds2[b])); idx[idx>0] += n_base; mask[b][mask[b]==0] = idx.
  *   preds2 [B,K2,h,w] fp32 (K2 = 1+Kn); mask [B,H,W] int64, updated IN PLACE.
  */
-int sl_pseudo_label(const float *preds2, int B, int K2, int h, int w, int H, int W,
+SL_API int sl_pseudo_label(const float *preds2, int B, int K2, int h, int w, int H, int W,
                     int n_base, long long *mask, void *stream);
 
 /* (a5) get_confusion_matrix(gt, pred, K), utils/pyt_utils.py:182-200, on label maps:
  *   cm[gt*K+pred] += 1 for every i < n with gt[i] != ignore_label.  Labels >= K that
  *   are not ignore_label are skipped and counted in *n_bad (int64, may be NULL).
  */
-int sl_confusion(const uint8_t *gt, const uint8_t *pred, long long n, int K,
+SL_API int sl_confusion(const uint8_t *gt, const uint8_t *pred, long long n, int K,
                  int ignore_label, long long *cm, long long *n_bad, void *stream);
 
 /* (a7) intersectionAndUnionGPU(output, target, K, ignore), utils/pyt_utils.py:293-305.
  *   output,target [n] int64.  Mirrors the reference's in-place side effect:
  *   output[target == ignore] = ignore.  inter/uni/tgt [K] fp32 are OVERWRITTEN with the
- *   per-call areas (the caller accumulates, ft_pop.py:333-334); cm_ws [K*K] int64 is
- *   scratch the call zeroes itself.
+ *   per-call areas (the caller accumulates, ft_pop.py:333-334); ws [3*K] int64 is scratch
+ *   the call zeroes itself (exact integer areas before the fp32 conversion histc implies).
  */
-int sl_inter_union(long long *output, const long long *target, long long n, int K,
+SL_API int sl_inter_union(long long *output, const long long *target, long long n, int K,
                    int ignore_label, float *inter, float *uni, float *tgt,
-                   long long *cm_ws, void *stream);
+                   long long *ws, void *stream);
 
 /* ---------------------------------------------------------------------------
  * (a9) masked_average_pooling(feature, mask), networks/pspnet.py:7-15
  *   feat [B,C,h,w] bf16; mask [B,1,H,W] fp32.
- *   mask_lr_ws [B,h*w] fp32 scratch (the align_corners bilinear down-sample of mask);
+ *   mask_lr_ws [B*h*w + B] fp32 scratch: the align_corners bilinear down-sample of mask
+ *           followed by the B per-image mask sums;
  *   per_image [B,C] fp32 = sum_hw(f*m)/(sum_hw m + 1e-5); proto [C] fp32 = mean_B.
  *   h*w % 8 == 0.
  */
-int sl_map_proto(const uint16_t *feat, const float *mask, int B, int C, int h, int w,
+SL_API int sl_map_proto(const uint16_t *feat, const float *mask, int B, int C, int h, int w,
                  int H, int W, float *mask_lr_ws, float *per_image, float *proto,
                  void *stream);
 
@@ -176,7 +183,7 @@ int sl_map_proto(const uint16_t *feat, const float *mask, int B, int C, int h, i
  *   proto_sim [Kr,Kr+Ko] fp32 (may be NULL), loss [1] fp32,
  *   grad_rows [Kr,C] fp32 or NULL = d loss / d rows (others are frozen in ft mode).
  */
-int sl_orth_loss(const float *rows, int Kr, const float *others, int Ko, int C,
+SL_API int sl_orth_loss(const float *rows, int Kr, const float *others, int Ko, int C,
                  float *proto_sim, float *loss, float *grad_rows, void *stream);
 
 /* ---------------------------------------------------------------------------
@@ -186,7 +193,7 @@ int sl_orth_loss(const float *rows, int Kr, const float *others, int Ko, int C,
  *   pred [HW] u8; fused [K,HW] fp32 or NULL (the divided sum);
  *   label/cm as in sl_upsample_argmax (optional mIoU of the fused map).
  */
-int sl_fuse_argmax(const float *const *mats_host, int M, int K, long long HW, int divisor,
+SL_API int sl_fuse_argmax(const float *const *mats_host, int M, int K, long long HW, int divisor,
                    uint8_t *pred, float *fused,
                    const uint8_t *label, int ignore_label, long long *cm, void *stream);
 

@@ -1,0 +1,130 @@
+// sl_pop_prepare: everything in the POP head that depends only on weights and prototypes.
+//   reference: networks/pspnet_pop.py:106,113 (F.normalize of the prototypes),
+//              :46-52,57-63 (classifier / classifier_n), :112,118 (bg = q - sum_k p_k s_k).
+// Three tiny kernels (K <= 31, C <= 1024): total work ~ K*C^2 FMA, negligible next to one tile.
+#include "common.cuh"
+
+namespace sl {
+
+// s_hat[k] = protos[k] / max(||protos[k]||_2, 1e-12)
+__global__ void __launch_bounds__(128) normalize_protos_kernel(const float* __restrict__ protos, int C,
+                                                               float* __restrict__ s_hat) {
+  __shared__ float red[4];
+  const float* row = protos + static_cast<size_t>(blockIdx.x) * C;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < C; i += 128) { const float v = row[i]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  const float nrm = fmaxf(sqrtf(red[0] + red[1] + red[2] + red[3]), 1e-12f);
+  for (int i = threadIdx.x; i < C; i += 128) s_hat[static_cast<size_t>(blockIdx.x) * C + i] = row[i] / nrm;
+}
+
+// alpha_k = MLP(+s_hat_k), beta_k = MLP(-s_hat_k).  grid (K, 2), 256 threads.
+__global__ void __launch_bounds__(256) alpha_beta_kernel(const float* __restrict__ s_hat, int Kb, int C,
+                                                         const float* __restrict__ W1f, const float* __restrict__ W2f,
+                                                         const float* __restrict__ w3f, const float* __restrict__ W1g,
+                                                         const float* __restrict__ W2g, const float* __restrict__ w3g,
+                                                         float* __restrict__ alpha, float* __restrict__ beta) {
+  extern __shared__ float sm[];
+  float* x = sm;          // [C] input (+-s_hat_k)
+  float* h1 = sm + C;     // [C]
+  float* h2 = sm + 2 * C; // [C]
+  __shared__ float red[8];
+  const int k = blockIdx.x;
+  const float sign = blockIdx.y == 0 ? 1.f : -1.f;
+  const bool fg = k < Kb;
+  const float* W1 = fg ? W1f : W1g;
+  const float* W2 = fg ? W2f : W2g;
+  const float* w3 = fg ? w3f : w3g;
+  for (int i = threadIdx.x; i < C; i += 256) x[i] = sign * s_hat[static_cast<size_t>(k) * C + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < C; o += 8) {
+    const float* w = W1 + static_cast<size_t>(o) * C;
+    float acc = 0.f;
+    for (int i = lane; i < C; i += 32) acc = fmaf(w[i], x[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) h1[o] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  for (int o = warp; o < C; o += 8) {
+    const float* w = W2 + static_cast<size_t>(o) * C;
+    float acc = 0.f;
+    for (int i = lane; i < C; i += 32) acc = fmaf(w[i], h1[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) h2[o] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < C; i += 256) acc = fmaf(w3[i], h2[i], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    (blockIdx.y == 0 ? alpha : beta)[k] = t;
+  }
+}
+
+// W1' = W1 (I - S^T S):  row o of W1' = W1[o] - sum_k (W1[o] . s_k) s_k.   grid C, 128 threads.
+// Also emits the layouts both background paths want: transposed fp32 and split bf16.
+__global__ void __launch_bounds__(128) fold_weights_kernel(const float* __restrict__ s_hat, int K, int C,
+                                                           const float* __restrict__ W1, const float* __restrict__ W2,
+                                                           float* __restrict__ W1p_t, float* __restrict__ W2_t,
+                                                           uint16_t* __restrict__ W1p_hi, uint16_t* __restrict__ W1p_lo,
+                                                           uint16_t* __restrict__ W2_hi, uint16_t* __restrict__ W2_lo) {
+  __shared__ float u[SL_MAX_CLASSES];
+  const int o = blockIdx.x;
+  const float* w1 = W1 + static_cast<size_t>(o) * C;
+  const float* w2 = W2 + static_cast<size_t>(o) * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < K; k += 4) {
+    const float* s = s_hat + static_cast<size_t>(k) * C;
+    float acc = 0.f;
+    for (int i = lane; i < C; i += 32) acc = fmaf(w1[i], s[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) u[k] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 128) {
+    float corr = 0.f;
+    for (int k = 0; k < K; ++k) corr = fmaf(u[k], s_hat[static_cast<size_t>(k) * C + i], corr);
+    const float a = w1[i] - corr;
+    const float b = w2[i];
+    if (W1p_t) W1p_t[static_cast<size_t>(i) * C + o] = a;
+    if (W2_t) W2_t[static_cast<size_t>(i) * C + o] = b;
+    if (W1p_hi) {
+      const uint16_t ah = f32_to_bf16_rn(a), bh = f32_to_bf16_rn(b);
+      const size_t idx = static_cast<size_t>(o) * C + i;
+      W1p_hi[idx] = ah;
+      W1p_lo[idx] = f32_to_bf16_rn(a - bf16_bits_to_f32(ah));
+      W2_hi[idx] = bh;
+      W2_lo[idx] = f32_to_bf16_rn(b - bf16_bits_to_f32(bh));
+    }
+  }
+}
+
+}  // namespace sl
+
+extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const float* W1_fg, const float* W2_fg,
+                              const float* w3_fg, const float* W1_bg, const float* W2_bg, const float* w3_bg,
+                              float* s_hat, float* alpha, float* beta, float* W1p_t, float* W2_t, uint16_t* W1p_hi,
+                              uint16_t* W1p_lo, uint16_t* W2_hi, uint16_t* W2_lo, void* stream) {
+  SL_CHECK_ARG(K >= 1 && K < SL_MAX_CLASSES && Kb >= 0 && Kb <= K);
+  SL_CHECK_ARG(C >= 8 && C <= 1024 && C % 8 == 0);
+  SL_CHECK_PTR(protos); SL_CHECK_PTR(W1_fg); SL_CHECK_PTR(W2_fg); SL_CHECK_PTR(w3_fg);
+  SL_CHECK_PTR(W1_bg); SL_CHECK_PTR(W2_bg); SL_CHECK_PTR(w3_bg);
+  SL_CHECK_PTR(s_hat); SL_CHECK_PTR(alpha); SL_CHECK_PTR(beta);
+  const int n_split = (W1p_hi != nullptr) + (W1p_lo != nullptr) + (W2_hi != nullptr) + (W2_lo != nullptr);
+  SL_CHECK_ARG(n_split == 0 || n_split == 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  sl::normalize_protos_kernel<<<K, 128, 0, st>>>(protos, C, s_hat);
+  sl::alpha_beta_kernel<<<dim3(K, 2), 256, 3 * C * sizeof(float), st>>>(s_hat, Kb, C, W1_fg, W2_fg, w3_fg, W1_bg,
+                                                                        W2_bg, w3_bg, alpha, beta);
+  if (W1p_t || W2_t || n_split)
+    sl::fold_weights_kernel<<<C, 128, 0, st>>>(s_hat, K, C, W1_bg, W2_bg, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo);
+  return SL_LAUNCH_RESULT();
+}

@@ -1,0 +1,389 @@
+// Dense post-processing behind the POP head:
+//   sl_upsample_argmax  F.interpolate(bilinear, align_corners=True) -> argmax -> confusion matrix
+//                       (eval_base.py:168-178, eval_ft.py:168-183, ft_pop.py:327-331)
+//   sl_pseudo_label     pspnet_pop.py:221-231
+//   sl_confusion        utils/pyt_utils.py:182-200 (get_confusion_matrix)
+//   sl_inter_union      utils/pyt_utils.py:293-305 (intersectionAndUnionGPU)
+//   sl_views_reduce     flip/multi-view aggregation at feature resolution (spec: this repo)
+// The full-resolution logits are never written unless the caller asks for them (probs / logits_hr).
+#include "common.cuh"
+
+namespace sl {
+
+// Interpolated value of channel plane `src` [h][w] at output pixel given by (cy, cx), in ATen's
+// association: l0y*(l0x*a + l1x*b) + l1y*(l0x*c + l1x*d).
+__device__ __forceinline__ float bilerp(const float* __restrict__ src, int w, const SrcCoord& cy, const SrcCoord& cx) {
+  const float* r0 = src + cy.i0 * w + cx.i0;
+  const float* r1 = r0 + cy.step * w;
+  const float a = __ldg(r0), b = __ldg(r0 + cx.step), c = __ldg(r1), d = __ldg(r1 + cx.step);
+  return cy.l0 * (cx.l0 * a + cx.l1 * b) + cy.l1 * (cx.l0 * c + cx.l1 * d);
+}
+
+// np.argmax / torch.argmax semantics: first maximum; NaN counts as maximal (first NaN wins).
+__device__ __forceinline__ void argmax_step(float v, int k, float& best, int& idx) {
+  if (v > best || (v != v && best == best)) { best = v; idx = k; }
+}
+
+constexpr int UP_PX = 4;  // consecutive x pixels per thread (uchar4 label/pred accesses)
+
+// KP: compile-time bound on K so the per-pixel channel values stay in registers when the
+// softmax outputs need them (KP == 0: values are not kept).
+template <int KP>
+__global__ void __launch_bounds__(256) upsample_argmax_kernel(
+    const float* __restrict__ logits_lr, int B, int K, int h, int w, int H, int W, float sy, float sx,
+    const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred, float* __restrict__ conf,
+    float* __restrict__ probs, float* __restrict__ logits_hr, unsigned long long* __restrict__ cm) {
+  __shared__ unsigned int hist[SL_MAX_CLASSES * SL_MAX_CLASSES];
+  const bool do_cm = cm != nullptr;
+  if (do_cm) {
+    for (int i = threadIdx.x; i < K * K; i += 256) hist[i] = 0u;
+    __syncthreads();
+  }
+  const int groups_x = (W + UP_PX - 1) / UP_PX;
+  const long long total = static_cast<long long>(B) * H * groups_x;
+  const bool vec_ok = (W % UP_PX) == 0;
+  const long long start = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  // every lane runs the same number of iterations so the warp-collective histogram stays converged
+  const long long iters = (total + stride - 1) / stride;
+  for (long long it = 0; it < iters; ++it) {
+    const long long g = start + it * stride;
+    const bool active = g < total;
+    int idx[UP_PX];
+    int lab[UP_PX];
+#pragma unroll
+    for (int j = 0; j < UP_PX; ++j) { idx[j] = 0; lab[j] = -1; }
+    if (active) {
+      const int gx = static_cast<int>(g % groups_x);
+      const long long rowid = g / groups_x;
+      const int y = static_cast<int>(rowid % H);
+      const int b = static_cast<int>(rowid / H);
+      const int x0 = gx * UP_PX;
+      const SrcCoord cy = src_coord(sy, y, h);
+      SrcCoord cx[UP_PX];
+#pragma unroll
+      for (int j = 0; j < UP_PX; ++j) cx[j] = src_coord(sx, min(x0 + j, W - 1), w);
+      float best[UP_PX];
+#pragma unroll
+      for (int j = 0; j < UP_PX; ++j) best[j] = -INFINITY;
+      float vals[UP_PX][KP > 0 ? KP : 1];
+      const float* plane = logits_lr + static_cast<size_t>(b) * K * h * w;
+      const size_t pix = (static_cast<size_t>(b) * H + y) * W + x0;           // index into [B,H,W]
+      const size_t HW = static_cast<size_t>(H) * W;
+      auto channel = [&](int k, float (&v)[UP_PX]) {
+#pragma unroll
+        for (int j = 0; j < UP_PX; ++j) {
+          v[j] = bilerp(plane + static_cast<size_t>(k) * h * w, w, cy, cx[j]);
+          argmax_step(v[j], k, best[j], idx[j]);
+        }
+        if (logits_hr) {
+          float* dst = logits_hr + (static_cast<size_t>(b) * K + k) * HW + static_cast<size_t>(y) * W + x0;
+          if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          else
+#pragma unroll
+            for (int j = 0; j < UP_PX; ++j) if (x0 + j < W) dst[j] = v[j];
+        }
+      };
+      if constexpr (KP > 0) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          if (k < K) {
+            float v[UP_PX];
+            channel(k, v);
+#pragma unroll
+            for (int j = 0; j < UP_PX; ++j) vals[j][k] = v[j];
+          }
+        }
+      } else {
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+          float v[UP_PX];
+          channel(k, v);
+        }
+      }
+      if (KP > 0 && (conf || probs)) {
+        float inv[UP_PX];
+#pragma unroll
+        for (int j = 0; j < UP_PX; ++j) {
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < KP; ++k) if (k < K) { vals[j][k] = __expf(vals[j][k] - best[j]); s += vals[j][k]; }
+          inv[j] = 1.f / s;
+        }
+        if (conf) {
+          float* dst = conf + pix;
+          if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(inv[0], inv[1], inv[2], inv[3]);
+          else
+#pragma unroll
+            for (int j = 0; j < UP_PX; ++j) if (x0 + j < W) dst[j] = inv[j];
+        }
+        if (probs) {
+#pragma unroll
+          for (int k = 0; k < KP; ++k) if (k < K) {
+            float* dst = probs + (static_cast<size_t>(b) * K + k) * HW + static_cast<size_t>(y) * W + x0;
+            if (vec_ok)
+              *reinterpret_cast<float4*>(dst) = make_float4(vals[0][k] * inv[0], vals[1][k] * inv[1],
+                                                            vals[2][k] * inv[2], vals[3][k] * inv[3]);
+            else
+#pragma unroll
+              for (int j = 0; j < UP_PX; ++j) if (x0 + j < W) dst[j] = vals[j][k] * inv[j];
+          }
+        }
+      }
+      if (pred) {
+        if (vec_ok) *reinterpret_cast<uchar4*>(pred + pix) = make_uchar4(idx[0], idx[1], idx[2], idx[3]);
+        else
+#pragma unroll
+          for (int j = 0; j < UP_PX; ++j) if (x0 + j < W) pred[pix + j] = static_cast<uint8_t>(idx[j]);
+      }
+      if (do_cm) {
+        if (vec_ok) {
+          const uchar4 l4 = *reinterpret_cast<const uchar4*>(label + pix);
+          lab[0] = l4.x; lab[1] = l4.y; lab[2] = l4.z; lab[3] = l4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < UP_PX; ++j) if (x0 + j < W) lab[j] = label[pix + j];
+        }
+      }
+    }
+    if (do_cm) {
+#pragma unroll
+      for (int j = 0; j < UP_PX; ++j) {
+        const bool valid = lab[j] >= 0 && lab[j] != ignore_label && lab[j] < K;
+        hist_add_warp(hist, valid ? lab[j] * K + idx[j] : 0, valid);
+      }
+    }
+  }
+  if (do_cm) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K; i += 256)
+      if (hist[i]) atomicAdd(&cm[i], static_cast<unsigned long long>(hist[i]));
+  }
+}
+
+// ------------------------------------------------------------------ pseudo-labelling
+__global__ void __launch_bounds__(256) pseudo_label_kernel(const float* __restrict__ preds2, int B, int K2, int h, int w,
+                                                           int H, int W, float sy, float sx, int n_base,
+                                                           long long* __restrict__ mask) {
+  const long long total = static_cast<long long>(B) * H * W;
+  for (long long g = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; g < total;
+       g += static_cast<long long>(gridDim.x) * 256) {
+    if (mask[g] != 0) continue;
+    const int x = static_cast<int>(g % W);
+    const long long rowid = g / W;
+    const int y = static_cast<int>(rowid % H);
+    const int b = static_cast<int>(rowid / H);
+    const SrcCoord cy = src_coord(sy, y, h), cx = src_coord(sx, x, w);
+    const float* plane = preds2 + static_cast<size_t>(b) * K2 * h * w;
+    float best = -INFINITY;
+    int idx = 0;
+    for (int k = 0; k < K2; ++k) argmax_step(bilerp(plane + static_cast<size_t>(k) * h * w, w, cy, cx), k, best, idx);
+    mask[g] = idx > 0 ? idx + n_base : 0;
+  }
+}
+
+// ------------------------------------------------------------------ confusion on label maps
+__global__ void __launch_bounds__(256) confusion_kernel(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pr,
+                                                        long long n, int K, int ignore_label,
+                                                        unsigned long long* __restrict__ cm,
+                                                        unsigned long long* __restrict__ n_bad) {
+  __shared__ unsigned int hist[SL_MAX_CLASSES * SL_MAX_CLASSES];
+  __shared__ unsigned int bad;
+  for (int i = threadIdx.x; i < K * K; i += 256) hist[i] = 0u;
+  if (threadIdx.x == 0) bad = 0u;
+  __syncthreads();
+  const bool vec = ((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pr)) & 15) == 0;
+  const long long nvec = vec ? n / 16 : 0;
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  const long long start = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const long long iters = (nvec + stride - 1) / stride;
+  unsigned int my_bad = 0;
+  for (long long it = 0; it < iters; ++it) {
+    const long long v = start + it * stride;
+    const bool active = v < nvec;
+    uint4 g4 = make_uint4(0, 0, 0, 0), p4 = g4;
+    if (active) {
+      g4 = ld_stream_u4(gt + v * 16);
+      p4 = ld_stream_u4(pr + v * 16);
+    }
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+    const uint32_t pw[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (gw[q] >> (8 * j)) & 0xff, p = (pw[q] >> (8 * j)) & 0xff;
+        const bool keep = active && g != ignore_label;
+        const bool valid = keep && g < K && p < K;
+        my_bad += (keep && !valid);
+        hist_add_warp(hist, valid ? g * K + p : 0, valid);
+      }
+  }
+  // scalar tail (and the whole array when the pointers are not 16-byte aligned)
+  const long long tail0 = nvec * 16;
+  const long long titers = (n - tail0 + stride - 1) / stride;
+  for (long long it = 0; it < titers; ++it) {
+    const long long i = tail0 + start + it * stride;
+    const bool active = i < n;
+    const int g = active ? gt[i] : 0, p = active ? pr[i] : 0;
+    const bool keep = active && g != ignore_label;
+    const bool valid = keep && g < K && p < K;
+    my_bad += (keep && !valid);
+    hist_add_warp(hist, valid ? g * K + p : 0, valid);
+  }
+  if (my_bad) atomicAdd(&bad, my_bad);
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K; i += 256)
+    if (hist[i]) atomicAdd(&cm[i], static_cast<unsigned long long>(hist[i]));
+  if (threadIdx.x == 0 && bad && n_bad) atomicAdd(n_bad, static_cast<unsigned long long>(bad));
+}
+
+// ------------------------------------------------------------------ intersection / union
+// ws: [3][K] int64 = {intersection, area_output, area_target}
+__global__ void __launch_bounds__(256) inter_union_kernel(long long* __restrict__ output,
+                                                          const long long* __restrict__ target, long long n, int K,
+                                                          long long ignore, unsigned long long* __restrict__ ws) {
+  __shared__ unsigned int hist[3 * SL_MAX_CLASSES];
+  for (int i = threadIdx.x; i < 3 * K; i += 256) hist[i] = 0u;
+  __syncthreads();
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  const long long start = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const long long iters = (n + stride - 1) / stride;
+  for (long long it = 0; it < iters; ++it) {
+    const long long i = start + it * stride;
+    const bool active = i < n;
+    long long o = active ? output[i] : -1, t = active ? target[i] : -1;
+    if (active && t == ignore) { o = ignore; output[i] = ignore; }   // utils/pyt_utils.py:299
+    const bool o_in = active && o >= 0 && o < K;
+    const bool t_in = active && t >= 0 && t < K;
+    hist_add_warp(hist, o_in ? static_cast<int>(o) : 0, o_in && o == t);          // intersection
+    hist_add_warp(hist, o_in ? K + static_cast<int>(o) : 0, o_in);                // area_output
+    hist_add_warp(hist, t_in ? 2 * K + static_cast<int>(t) : 0, t_in);            // area_target
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * K; i += 256)
+    if (hist[i]) atomicAdd(&ws[i], static_cast<unsigned long long>(hist[i]));
+}
+
+__global__ void inter_union_finish_kernel(const unsigned long long* __restrict__ ws, int K, float* __restrict__ inter,
+                                          float* __restrict__ uni, float* __restrict__ tgt) {
+  const int k = threadIdx.x;
+  if (k >= K) return;
+  // torch.histc returns fp32 counts; union = area_output + area_target - intersection in fp32
+  const float fi = static_cast<float>(ws[k]), fo = static_cast<float>(ws[K + k]), ft = static_cast<float>(ws[2 * K + k]);
+  inter[k] = fi;
+  uni[k] = fo + ft - fi;
+  tgt[k] = ft;
+}
+
+// ------------------------------------------------------------------ view aggregation
+struct FlipFlags { int f[16]; };
+__global__ void __launch_bounds__(256) views_reduce_kernel(const float* __restrict__ views, int V, long long planes,
+                                                           int h, int w, FlipFlags flips, float scale,
+                                                           float* __restrict__ out) {
+  const long long total = planes * h * w;
+  for (long long g = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; g < total;
+       g += static_cast<long long>(gridDim.x) * 256) {
+    const int x = static_cast<int>(g % w);
+    const long long r = g / w;
+    const int y = static_cast<int>(r % h);
+    const long long plane = r / h;
+    float acc = 0.f;
+    for (int v = 0; v < V; ++v) {
+      const int xs = (flips.f[v] & 1) ? w - 1 - x : x;
+      const int ys = (flips.f[v] & 2) ? h - 1 - y : y;
+      acc += views[((static_cast<size_t>(v) * planes + plane) * h + ys) * w + xs];
+    }
+    out[g] = acc * scale;
+  }
+}
+
+static inline int grid_for(long long work_items, int per_sm) {
+  long long blocks = (work_items + 255) / 256;
+  const long long cap = static_cast<long long>(kNumSMs) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace sl
+
+extern "C" int sl_upsample_argmax(const float* logits_lr, int B, int K, int h, int w, int H, int W,
+                                  const uint8_t* label, int ignore_label, uint8_t* pred, float* conf, float* probs,
+                                  float* logits_hr, long long* cm, void* stream) {
+  SL_CHECK_PTR(logits_lr);
+  SL_CHECK_ARG(B >= 1 && K >= 1 && K <= SL_MAX_CLASSES && h >= 1 && w >= 1 && H >= 1 && W >= 1);
+  SL_CHECK_ARG(static_cast<long long>(h) * w * K < (1ll << 31));
+  if (cm) SL_CHECK_PTR(label);
+  SL_CHECK_ARG(pred || conf || probs || logits_hr || cm);
+  if (W % 4 == 0) {
+    if (label) SL_CHECK_ALIGN(label, 4);
+    if (pred) SL_CHECK_ALIGN(pred, 4);
+    if (conf) SL_CHECK_ALIGN(conf, 16);
+    if (probs) SL_CHECK_ALIGN(probs, 16);
+    if (logits_hr) SL_CHECK_ALIGN(logits_hr, 16);
+  }
+  const float sy = sl::ac_scale(h, H), sx = sl::ac_scale(w, W);
+  const long long items = static_cast<long long>(B) * H * ((W + sl::UP_PX - 1) / sl::UP_PX);
+  const int grid = sl::grid_for(items, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto* cmu = reinterpret_cast<unsigned long long*>(cm);
+#define SL_UP_LAUNCH(KP) sl::upsample_argmax_kernel<KP><<<grid, 256, 0, st>>>( \
+      logits_lr, B, K, h, w, H, W, sy, sx, label, ignore_label, pred, conf, probs, logits_hr, cmu)
+  if (!(conf || probs)) SL_UP_LAUNCH(0);
+  else if (K <= 8) SL_UP_LAUNCH(8);
+  else if (K <= 12) SL_UP_LAUNCH(12);
+  else if (K <= 16) SL_UP_LAUNCH(16);
+  else SL_UP_LAUNCH(32);
+#undef SL_UP_LAUNCH
+  return SL_LAUNCH_RESULT();
+}
+
+extern "C" int sl_pseudo_label(const float* preds2, int B, int K2, int h, int w, int H, int W, int n_base,
+                               long long* mask, void* stream) {
+  SL_CHECK_PTR(preds2); SL_CHECK_PTR(mask);
+  SL_CHECK_ARG(B >= 1 && K2 >= 1 && K2 <= SL_MAX_CLASSES && h >= 1 && w >= 1 && H >= 1 && W >= 1 && n_base >= 0);
+  const long long items = static_cast<long long>(B) * H * W;
+  sl::pseudo_label_kernel<<<sl::grid_for(items, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      preds2, B, K2, h, w, H, W, sl::ac_scale(h, H), sl::ac_scale(w, W), n_base, mask);
+  return SL_LAUNCH_RESULT();
+}
+
+extern "C" int sl_confusion(const uint8_t* gt, const uint8_t* pred, long long n, int K, int ignore_label,
+                            long long* cm, long long* n_bad, void* stream) {
+  SL_CHECK_ARG(n >= 0 && K >= 1 && K <= SL_MAX_CLASSES);
+  SL_CHECK_PTR(cm);
+  if (n == 0) return SL_OK;   // empty maps are legal (and may come with NULL data pointers)
+  SL_CHECK_PTR(gt); SL_CHECK_PTR(pred);
+  sl::confusion_kernel<<<sl::grid_for((n + 15) / 16, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      gt, pred, n, K, ignore_label, reinterpret_cast<unsigned long long*>(cm),
+      reinterpret_cast<unsigned long long*>(n_bad));
+  return SL_LAUNCH_RESULT();
+}
+
+extern "C" int sl_inter_union(long long* output, const long long* target, long long n, int K, int ignore_label,
+                              float* inter, float* uni, float* tgt, long long* ws, void* stream) {
+  SL_CHECK_PTR(inter); SL_CHECK_PTR(uni); SL_CHECK_PTR(tgt); SL_CHECK_PTR(ws);
+  SL_CHECK_ARG(n >= 0 && K >= 1 && K <= SL_MAX_CLASSES);
+  if (n > 0) { SL_CHECK_PTR(output); SL_CHECK_PTR(target); }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(long long) * 3 * K, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (n > 0)
+    sl::inter_union_kernel<<<sl::grid_for(n, 8), 256, 0, st>>>(output, target, n, K, ignore_label,
+                                                              reinterpret_cast<unsigned long long*>(ws));
+  sl::inter_union_finish_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long*>(ws), K, inter, uni, tgt);
+  return SL_LAUNCH_RESULT();
+}
+
+extern "C" int sl_views_reduce(const float* views, int V, int B, int K, int h, int w, const int* flip_host,
+                               float scale, float* out, void* stream) {
+  SL_CHECK_PTR(views); SL_CHECK_PTR(out); SL_CHECK_PTR(flip_host);
+  SL_CHECK_ARG(V >= 1 && V <= 16 && B >= 1 && K >= 1 && h >= 1 && w >= 1);
+  sl::FlipFlags ff;
+  for (int v = 0; v < 16; ++v) ff.f[v] = v < V ? flip_host[v] : 0;
+  const long long planes = static_cast<long long>(B) * K;
+  sl::views_reduce_kernel<<<sl::grid_for(planes * h * w, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      views, V, planes, h, w, ff, scale, out);
+  return SL_LAUNCH_RESULT();
+}

@@ -1,0 +1,182 @@
+// Prototype-side operators:
+//   sl_map_proto   masked_average_pooling, networks/pspnet.py:7-15
+//   sl_orth_loss   proto_sim (networks/pspnet_pop.py:185-186, :234-239) + OrthLoss.get_orth_loss
+//                  (loss/criterion.py:37-43), forward and gradient w.r.t. the trainable rows.
+#include "common.cuh"
+
+namespace sl {
+
+// ---- MAP step 1: bilinear align_corners=True resample of the mask to feature resolution, plus the
+// per-image mask sum (one CTA per image -> fixed summation order).
+__global__ void __launch_bounds__(256) map_mask_kernel(const float* __restrict__ mask, int h, int w, int H, int W,
+                                                       float sy, float sx, float* __restrict__ mask_lr,
+                                                       float* __restrict__ msum) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const float* src = mask + static_cast<size_t>(b) * H * W;
+  float* dst = mask_lr + static_cast<size_t>(b) * h * w;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < h * w; i += 256) {
+    const int y = i / w, x = i - y * w;
+    const SrcCoord cy = src_coord(sy, y, H), cx = src_coord(sx, x, W);
+    const float* r0 = src + static_cast<size_t>(cy.i0) * W + cx.i0;
+    const float* r1 = r0 + static_cast<size_t>(cy.step) * W;
+    const float v = cy.l0 * (cx.l0 * __ldg(r0) + cx.l1 * __ldg(r0 + cx.step)) +
+                    cy.l1 * (cx.l0 * __ldg(r1) + cx.l1 * __ldg(r1 + cx.step));
+    dst[i] = v;
+    acc += v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    msum[b] = t;
+  }
+}
+
+// ---- MAP step 2: per (image, channel) masked sum.  A warp owns MAP_CH channels at a time so each
+// mask value loaded from L1 is reused MAP_CH times; features stream once with 128-bit loads.
+constexpr int MAP_CH = 4;
+__global__ void __launch_bounds__(256) map_reduce_kernel(const uint16_t* __restrict__ feat, int C, int N,
+                                                         const float* __restrict__ mask_lr,
+                                                         const float* __restrict__ msum,
+                                                         float* __restrict__ per_image) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = (blockIdx.x * 8 + warp) * MAP_CH;
+  if (c0 >= C) return;
+  const float* m = mask_lr + static_cast<size_t>(b) * N;
+  const uint16_t* f = feat + (static_cast<size_t>(b) * C + c0) * N;
+  float acc[MAP_CH];
+#pragma unroll
+  for (int j = 0; j < MAP_CH; ++j) acc[j] = 0.f;
+  for (int n = lane * 8; n < N; n += 32 * 8) {
+    const float4 ma = __ldg(reinterpret_cast<const float4*>(m + n));
+    const float4 mb = __ldg(reinterpret_cast<const float4*>(m + n + 4));
+    uint4 v[MAP_CH];
+#pragma unroll
+    for (int j = 0; j < MAP_CH; ++j)
+      v[j] = (c0 + j < C) ? ld_stream_u4(f + static_cast<size_t>(j) * N + n) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < MAP_CH; ++j) {
+      float a = acc[j];
+      a = fmaf(bf16lo(v[j].x), ma.x, a); a = fmaf(bf16hi(v[j].x), ma.y, a);
+      a = fmaf(bf16lo(v[j].y), ma.z, a); a = fmaf(bf16hi(v[j].y), ma.w, a);
+      a = fmaf(bf16lo(v[j].z), mb.x, a); a = fmaf(bf16hi(v[j].z), mb.y, a);
+      a = fmaf(bf16lo(v[j].w), mb.z, a); a = fmaf(bf16hi(v[j].w), mb.w, a);
+      acc[j] = a;
+    }
+  }
+  const float denom = msum[b] + 1e-5f;
+#pragma unroll
+  for (int j = 0; j < MAP_CH; ++j) {
+    const float t = warp_sum(acc[j]);
+    if (lane == 0 && c0 + j < C) per_image[static_cast<size_t>(b) * C + c0 + j] = t / denom;
+  }
+}
+
+__global__ void map_mean_kernel(const float* __restrict__ per_image, int B, int C, float* __restrict__ proto) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int b = 0; b < B; ++b) t += per_image[static_cast<size_t>(b) * C + c];
+  proto[c] = t / static_cast<float>(B);
+}
+
+// ---- orthogonal-prototype loss, one CTA.  e = [normalize(rows); normalize(others)]  [Kr+Ko, C]
+//   sim[i][j] = e_i . e_j  (i < Kr),  loss = mean_{j>i} |sim[i][j]|,
+//   d loss / d rows[i] = (I - e_i e_i^T) g_i / max(||rows[i]||, eps),
+//   g_i = (1/M) ( sum_{j>i} sgn(sim[i][j]) e_j + sum_{j<i} sgn(sim[j][i]) e_j ).
+__global__ void __launch_bounds__(256) orth_loss_kernel(const float* __restrict__ rows, int Kr,
+                                                        const float* __restrict__ others, int Ko, int C,
+                                                        float* __restrict__ proto_sim, float* __restrict__ loss,
+                                                        float* __restrict__ grad_rows) {
+  extern __shared__ float sm[];
+  const int Kt = Kr + Ko;
+  float* e = sm;                 // [Kt][C]
+  float* nrm = sm + Kt * C;      // [Kt]
+  float* sim = nrm + Kt;         // [Kr][Kt]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < Kt; r += 8) {
+    const float* src = r < Kr ? rows + static_cast<size_t>(r) * C : others + static_cast<size_t>(r - Kr) * C;
+    float ss = 0.f;
+    for (int i = lane; i < C; i += 32) { const float v = src[i]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float n = fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) nrm[r] = n;
+    for (int i = lane; i < C; i += 32) e[r * C + i] = src[i] / n;
+  }
+  __syncthreads();
+  for (int p = warp; p < Kr * Kt; p += 8) {
+    const int i = p / Kt, j = p - i * Kt;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(e[i * C + c], e[j * C + c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) { sim[p] = acc; if (proto_sim) proto_sim[p] = acc; }
+  }
+  __syncthreads();
+  int M = 0;
+  for (int i = 0; i < Kr; ++i) M += Kt - 1 - i;
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < Kr; ++i)
+      for (int j = i + 1; j < Kt; ++j) t += fabsf(sim[i * Kt + j]);
+    loss[0] = M > 0 ? t / static_cast<float>(M) : nanf("");
+  }
+  if (grad_rows == nullptr) return;
+  const float invM = M > 0 ? 1.f / static_cast<float>(M) : 0.f;
+  auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+  for (int i = warp; i < Kr; i += 8) {
+    // g . e_i first (projection term), then the projected gradient
+    float dotp = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float g = 0.f;
+      for (int j = i + 1; j < Kt; ++j) g = fmaf(sgn(sim[i * Kt + j]), e[j * C + c], g);
+      for (int j = 0; j < i; ++j) g = fmaf(sgn(sim[j * Kt + i]), e[j * C + c], g);
+      dotp = fmaf(g, e[i * C + c], dotp);
+    }
+    dotp = warp_sum(dotp);
+    for (int c = lane; c < C; c += 32) {
+      float g = 0.f;
+      for (int j = i + 1; j < Kt; ++j) g = fmaf(sgn(sim[i * Kt + j]), e[j * C + c], g);
+      for (int j = 0; j < i; ++j) g = fmaf(sgn(sim[j * Kt + i]), e[j * C + c], g);
+      grad_rows[static_cast<size_t>(i) * C + c] = invM * (g - dotp * e[i * C + c]) / nrm[i];
+    }
+  }
+}
+
+}  // namespace sl
+
+extern "C" int sl_map_proto(const uint16_t* feat, const float* mask, int B, int C, int h, int w, int H, int W,
+                            float* mask_lr_ws, float* per_image, float* proto, void* stream) {
+  SL_CHECK_PTR(feat); SL_CHECK_PTR(mask); SL_CHECK_PTR(mask_lr_ws); SL_CHECK_PTR(per_image); SL_CHECK_PTR(proto);
+  SL_CHECK_ARG(B >= 1 && B <= 65535 && C >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1);
+  const long long N = static_cast<long long>(h) * w;
+  SL_CHECK_ARG(N % 8 == 0 && N < (1ll << 30));
+  SL_CHECK_ALIGN(feat, 16); SL_CHECK_ALIGN(mask_lr_ws, 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* msum = mask_lr_ws + static_cast<size_t>(B) * N;   // the B mask sums follow the [B,N] map
+  sl::map_mask_kernel<<<B, 256, 0, st>>>(mask, h, w, H, W, sl::ac_scale(H, h), sl::ac_scale(W, w), mask_lr_ws, msum);
+  dim3 grid((C + 8 * sl::MAP_CH - 1) / (8 * sl::MAP_CH), B);
+  sl::map_reduce_kernel<<<grid, 256, 0, st>>>(feat, C, static_cast<int>(N), mask_lr_ws, msum, per_image);
+  sl::map_mean_kernel<<<(C + 127) / 128, 128, 0, st>>>(per_image, B, C, proto);
+  return SL_LAUNCH_RESULT();
+}
+
+extern "C" int sl_orth_loss(const float* rows, int Kr, const float* others, int Ko, int C, float* proto_sim,
+                            float* loss, float* grad_rows, void* stream) {
+  SL_CHECK_PTR(rows); SL_CHECK_PTR(loss);
+  SL_CHECK_ARG(Kr >= 1 && Ko >= 0 && Kr + Ko <= SL_MAX_CLASSES && C >= 1 && C <= 1024);
+  if (Ko > 0) SL_CHECK_PTR(others);
+  const int Kt = Kr + Ko;
+  const size_t smem = (static_cast<size_t>(Kt) * C + Kt + static_cast<size_t>(Kr) * Kt) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(sl::orth_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  sl::orth_loss_kernel<<<1, 256, smem, static_cast<cudaStream_t>(stream)>>>(rows, Kr, others, Ko, C, proto_sim, loss,
+                                                                           grad_rows);
+  return SL_LAUNCH_RESULT();
+}

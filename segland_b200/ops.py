@@ -1,0 +1,377 @@
+"""Host-side mirror of the reference's operator surface for the POP head + post-processing path.
+
+Every function keeps the name, argument meaning and side effects of the SegLand function it
+replaces (cited per function; paths are relative to the SegLand tree) and does its arithmetic
+in libsegland_b200.so through the C ABI.  PyTorch is used for device memory and streams only.
+There is no CPU path: CPU tensors are moved to the current CUDA device (counted as H2D by the
+callers that time it) and a missing library / non-B200 device raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import call, int_array, ptr, ptr_array
+
+IGNORE_LABEL = 255           # dataset/oem.py:15
+MAX_CLASSES = 32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(t, dtype=None):
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(t)
+    if not t.is_cuda:
+        t = t.cuda(non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def check_device():
+    """Raise unless the current CUDA device is a B200-class (sm_100) part."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('segland_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    call('sl_check_device')
+
+
+# =============================================================================== POP head
+@dataclass
+class _Plan:
+    s_hat: torch.Tensor
+    alpha: torch.Tensor
+    beta: torch.Tensor
+    W1p_t: torch.Tensor
+    W2_t: torch.Tensor
+    w3_bg: torch.Tensor
+    split: tuple | None      # (W1p_hi, W1p_lo, W2_hi, W2_lo) uint16 views of bf16
+
+
+class PopHead:
+    """The POP head of GFSS_Model after the decoder (networks/*_pop.py; pspnet_pop.py:136-182).
+
+    Holds the state-dict entries the head reads -- base_emb [Kb,C], novel_emb [Kn,C] (ft mode),
+    classifier.{0,2,4}.weight, classifier_n.{0,2,4}.weight -- and maps features [B,C,h,w]
+    (bf16) to logits [B,1+Kb(+Kn),h,w] fp32 in the reference's channel order
+    [bg, base_1..Kb, novel_1..Kn] (pspnet_pop.py:159).  In ft mode the background and novel
+    channels use classifier_n, base channels use classifier (pspnet_pop.py:150-157).
+
+    bg_mode: 'tc'   tcgen05 split-bf16 tensor-core MLP (C % 64 == 0, C <= 512, N % 128 == 0)
+             'simt' exact fp32 CUDA-core MLP (any C % 8 == 0, C <= 768)
+             'auto' tc when the shape allows, else simt
+    """
+
+    def __init__(self, base_emb, classifier, novel_emb=None, classifier_n=None, device=None, bg_mode='auto'):
+        check_device()
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        self.device = dev
+        self.base_emb = f32(base_emb)
+        self.novel_emb = None if novel_emb is None or novel_emb.shape[0] == 0 else f32(novel_emb)
+        self.Kb, self.C = self.base_emb.shape
+        self.Kn = 0 if self.novel_emb is None else self.novel_emb.shape[0]
+        self.K = self.Kb + self.Kn
+        if not (1 <= self.K < MAX_CLASSES):
+            raise ValueError(f'1 + Kb + Kn must be <= {MAX_CLASSES}')
+        self.cls = self._mlp(classifier, f32)
+        if self.Kn:
+            if classifier_n is None:
+                raise ValueError('ft mode (novel_emb given) needs classifier_n')
+            self.cls_n = self._mlp(classifier_n, f32)
+        else:
+            self.cls_n = None
+        if bg_mode not in ('auto', 'tc', 'simt'):
+            raise ValueError(bg_mode)
+        self.bg_mode = bg_mode
+        self._plan = None
+        self.refresh()
+
+    # -- construction helpers ------------------------------------------------------------
+    def _mlp(self, ws, f32):
+        W1, W2, w3 = ws
+        C = self.C
+        W1, W2, w3 = f32(W1).reshape(C, C), f32(W2).reshape(C, C), f32(w3).reshape(C)
+        return (W1, W2, w3)
+
+    @classmethod
+    def from_state_dict(cls, sd, **kw):
+        """Build from a GFSS_Model state dict; checkpoints saved from DDP/DataParallel carry a
+        'module.' prefix (utils/pyt_utils.py:101-106) which is stripped."""
+        sd = {(k[7:] if k.startswith('module.') else k): v for k, v in sd.items()}
+        get = lambda p: (sd[p + '.0.weight'], sd[p + '.2.weight'], sd[p + '.4.weight'])
+        novel = sd.get('novel_emb')
+        return cls(sd['base_emb'], get('classifier'), novel,
+                   get('classifier_n') if 'classifier_n.0.weight' in sd else None, **kw)
+
+    @classmethod
+    def from_model(cls, model, **kw):
+        """Build from a (possibly DDP-wrapped) reference GFSS_Model instance."""
+        m = model.module if hasattr(model, 'module') else model
+        get = lambda seq: (seq[0].weight, seq[2].weight, seq[4].weight)
+        is_ft = getattr(m, 'is_ft', False) and getattr(m, 'novel_emb', None) is not None
+        return cls(m.base_emb, get(m.classifier), m.novel_emb if is_ft else None,
+                   get(m.classifier_n) if is_ft else None, **kw)
+
+    @property
+    def n_classes(self):
+        return 1 + self.K
+
+    # -- weight-dependent precompute (sl_pop_prepare) -------------------------------------
+    def refresh(self):
+        """Recompute s_hat / alpha / beta / folded weights; call after any weight update."""
+        dev, C, K = self.device, self.C, self.K
+        protos = self.base_emb if self.novel_emb is None else torch.cat([self.base_emb, self.novel_emb], 0)
+        fg = self.cls
+        bg = self.cls_n if self.cls_n is not None else self.cls
+        new = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
+        want_split = self.bg_mode != 'simt' and C % 64 == 0 and 64 <= C <= 512
+        split = tuple(new(C, C, dtype=torch.int16) for _ in range(4)) if want_split else None
+        plan = _Plan(new(K, C), new(K), new(K), new(C, C), new(C, C), bg[2], split)
+        sp = split if split else (None,) * 4
+        with torch.cuda.device(dev):
+            call('sl_pop_prepare', ptr(protos.contiguous()), K, self.Kb, C, ptr(fg[0]), ptr(fg[1]), ptr(fg[2]),
+                 ptr(bg[0]), ptr(bg[1]), ptr(bg[2]), ptr(plan.s_hat), ptr(plan.alpha), ptr(plan.beta),
+                 ptr(plan.W1p_t), ptr(plan.W2_t), ptr(sp[0]), ptr(sp[1]), ptr(sp[2]), ptr(sp[3]), _stream())
+        self._plan = plan
+        self._ch_map = int_array([1 + k for k in range(K)])
+        return self
+
+    def _use_tc(self, N):
+        if self.bg_mode == 'simt':
+            return False
+        ok = self._plan.split is not None and N % 128 == 0
+        if self.bg_mode == 'tc' and not ok:
+            raise ValueError(f'bg_mode="tc" needs C % 64 == 0, C <= 512, N % 128 == 0 (C={self.C}, N={N})')
+        return ok
+
+    # -- forward ---------------------------------------------------------------------------
+    def __call__(self, features, out=None, fg_only=False):
+        """features [B,C,h,w] bf16 CUDA (other float dtypes are cast to bf16, as north_star
+        specifies bf16 features) -> logits [B,1+K,h,w] fp32.
+        fg_only skips the background MLP and leaves channel 0 untouched (stage-S timing)."""
+        if features.dim() != 4 or features.shape[1] != self.C:
+            raise ValueError(f'features must be [B,{self.C},h,w], got {tuple(features.shape)}')
+        feats = _cuda(features, torch.bfloat16)
+        B, C, h, w = feats.shape
+        N = h * w
+        if N % 8:
+            raise ValueError('h*w must be a multiple of 8')
+        Ktot = 1 + self.K
+        if out is None:
+            out = torch.empty(B, Ktot, h, w, dtype=torch.float32, device=feats.device)
+        p = self._plan
+        st = _stream()
+        call('sl_pop_fg_lowres', ptr(feats), B, C, N, ptr(p.s_hat), ptr(p.alpha), ptr(p.beta), self.K,
+             ptr(out), Ktot, self._ch_map, st)
+        if not fg_only:
+            if self._use_tc(N):
+                call('sl_pop_bg_tc', ptr(feats), B, C, N, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
+                     ptr(p.split[3]), ptr(p.w3_bg), ptr(out), Ktot, 0, st)
+            else:
+                call('sl_pop_bg_simt', ptr(feats), B, C, N, ptr(p.W1p_t), ptr(p.W2_t), ptr(p.w3_bg),
+                     ptr(out), Ktot, 0, st)
+        return out
+
+    forward = __call__
+
+
+def aggregate_views(views, flips, scale=None):
+    """Test-time view aggregation (spec: this repo; the reference has none).
+    views [V,B,K,h,w] fp32 logits of V views of the same tiles; flips[v] in {0,1,2,3}
+    (bit0 = horizontally flipped input, bit1 = vertically flipped).  Returns the un-flipped
+    mean [B,K,h,w] (scale defaults to 1/V)."""
+    views = _cuda(views, torch.float32)
+    V, B, K, h, w = views.shape
+    out = torch.empty(B, K, h, w, dtype=torch.float32, device=views.device)
+    call('sl_views_reduce', ptr(views), V, B, K, h, w, int_array(flips), float(1.0 / V if scale is None else scale),
+         ptr(out), _stream())
+    return out
+
+
+# ================================================================== dense post-processing
+def upsample_argmax(logits, size, label=None, cm=None, ignore_label=IGNORE_LABEL, want_pred=True,
+                    want_conf=False, want_probs=False, want_logits=False):
+    """F.interpolate(logits, size, mode='bilinear', align_corners=True) -> argmax(dim=1) -> uint8
+    (eval_base.py:168-170, eval_ft.py:168-172), optionally fused with the confusion-matrix update
+    (eval_base.py:172-178).  logits [B,K,h,w] fp32 CUDA.
+
+    cm: int64 [K,K] CUDA accumulator (row = gt, col = pred), updated in place; needs label
+        [B,H,W] uint8.  Returns a dict with the requested outputs: 'pred' uint8 [B,H,W],
+        'conf' fp32 [B,H,W] and 'probs' fp32 [B,K,H,W] (softmax; spec: this repo), 'logits'
+        fp32 [B,K,H,W] (the up-sampled logits eval_base.py:190-191 dumps for fusemat)."""
+    logits = _cuda(logits, torch.float32)
+    B, K, h, w = logits.shape
+    H, W = int(size[0]), int(size[1])
+    dev = logits.device
+    out = {}
+    pred = torch.empty(B, H, W, dtype=torch.uint8, device=dev) if want_pred else None
+    conf = torch.empty(B, H, W, dtype=torch.float32, device=dev) if want_conf else None
+    probs = torch.empty(B, K, H, W, dtype=torch.float32, device=dev) if want_probs else None
+    hr = torch.empty(B, K, H, W, dtype=torch.float32, device=dev) if want_logits else None
+    if cm is not None:
+        if label is None:
+            raise ValueError('cm needs label')
+        if cm.dtype != torch.int64 or tuple(cm.shape) != (K, K) or not cm.is_cuda or not cm.is_contiguous():
+            raise ValueError('cm must be a contiguous CUDA int64 [K,K] tensor')
+        label = _cuda(label, torch.uint8)
+        if tuple(label.shape) != (B, H, W):
+            raise ValueError(f'label must be [B,H,W]={B, H, W}, got {tuple(label.shape)}')
+    call('sl_upsample_argmax', ptr(logits), B, K, h, w, H, W, ptr(label) if cm is not None else None,
+         int(ignore_label), ptr(pred), ptr(conf), ptr(probs), ptr(hr), ptr(cm), _stream())
+    for k, v in (('pred', pred), ('conf', conf), ('probs', probs), ('logits', hr)):
+        if v is not None:
+            out[k] = v
+    return out
+
+
+def confusion_update(cm, gt, pred, ignore_label=IGNORE_LABEL):
+    """cm[gt, pred] += 1 over all pixels with gt != ignore_label (device-resident accumulation).
+    gt/pred: uint8 tensors of equal shape.  Returns the number of out-of-range labels skipped
+    as a 1-element CUDA int64 tensor (no host sync)."""
+    gt, pred = _cuda(gt, torch.uint8), _cuda(pred, torch.uint8)
+    if gt.shape != pred.shape:
+        raise ValueError('gt and pred shapes differ')
+    K = cm.shape[0]
+    n_bad = torch.zeros(1, dtype=torch.int64, device=cm.device)
+    call('sl_confusion', ptr(gt), ptr(pred), gt.numel(), K, int(ignore_label), ptr(cm), ptr(n_bad), _stream())
+    return n_bad
+
+
+def get_confusion_matrix(gt_label, pred_label, class_num):
+    """utils/pyt_utils.py:182-200 with the reference's signature and return type: 1-D (or any
+    shape) label arrays already filtered by gt != ignore (eval_base.py:175-178) -> float64
+    numpy [class_num, class_num], row = gt, col = pred.  Labels equal to 255 are still
+    skipped, so unfiltered maps give the same matrix as the reference's filtered call."""
+    dev = torch.device('cuda', torch.cuda.current_device())
+    cm = torch.zeros(class_num, class_num, dtype=torch.int64, device=dev)
+    to_u8 = lambda a: _cuda(torch.as_tensor(np.asarray(a).astype(np.uint8, copy=False)) if not torch.is_tensor(a) else a,
+                            torch.uint8)
+    confusion_update(cm, to_u8(gt_label), to_u8(pred_label))
+    return cm.cpu().numpy().astype(np.float64)
+
+
+def miou_from_confusion(confusion_matrix, base_classes):
+    """eval_base.py:193-199 / eval_ft.py:196-202 on a host copy of the (tiny) matrix:
+    returns (base_miou, novel_miou, total_miou, miou_array) in float64."""
+    cm = confusion_matrix.detach().cpu().numpy() if torch.is_tensor(confusion_matrix) else np.asarray(confusion_matrix)
+    cm = cm.astype(np.float64)
+    pos, res, tp = cm.sum(1), cm.sum(0), np.diag(cm)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        miou_array = tp / (pos + res - tp)
+        base = np.nanmean(miou_array[:base_classes + 1])
+        novel = np.nanmean(miou_array[base_classes + 1:]) if base_classes + 1 < len(miou_array) else float('nan')
+        total = np.nanmean(miou_array)
+    return base, novel, total, miou_array
+
+
+def intersectionAndUnionGPU(output, target, K, ignore_index=IGNORE_LABEL):
+    """utils/pyt_utils.py:293-305, same signature, return values and side effect:
+    output/target int64 CUDA tensors of equal shape; output[target == ignore] = ignore IN PLACE;
+    returns (area_intersection, area_union, area_target) as fp32 [K] CUDA tensors."""
+    assert output.dim() in [1, 2, 3]
+    assert output.shape == target.shape
+    if not (output.is_cuda and target.is_cuda and output.dtype == torch.int64 and target.dtype == torch.int64):
+        raise ValueError('intersectionAndUnionGPU takes int64 CUDA tensors (as .max(1)[1] and the label loader give)')
+    if not output.is_contiguous():
+        raise ValueError('output must be contiguous (it is modified in place)')
+    target = target.contiguous()
+    dev = output.device
+    inter, uni, tgt = (torch.empty(K, dtype=torch.float32, device=dev) for _ in range(3))
+    ws = torch.empty(3 * K, dtype=torch.int64, device=dev)
+    call('sl_inter_union', ptr(output), ptr(target), output.numel(), K, int(ignore_index), ptr(inter), ptr(uni),
+         ptr(tgt), ptr(ws), _stream())
+    return inter, uni, tgt
+
+
+def pseudo_label(preds2_base, mask_b, n_base):
+    """pspnet_pop.py:221-231: label the background (== 0) pixels of the base images' masks with
+    argmax(upsample(classifier_n outputs)), shifting novel indices by n_base.  preds2_base
+    [Bb,1+Kn,h,w] fp32; mask_b [Bb,H,W] int64 CUDA, modified IN PLACE and returned."""
+    preds2_base = _cuda(preds2_base, torch.float32)
+    if not (mask_b.is_cuda and mask_b.dtype == torch.int64 and mask_b.is_contiguous()):
+        raise ValueError('mask_b must be a contiguous int64 CUDA tensor')
+    B, K2, h, w = preds2_base.shape
+    H, W = mask_b.shape[-2:]
+    call('sl_pseudo_label', ptr(preds2_base), B, K2, h, w, H, W, int(n_base), ptr(mask_b), _stream())
+    return mask_b
+
+
+# ======================================================================== prototypes / loss
+def masked_average_pooling(feature, mask, return_per_image=False):
+    """networks/pspnet.py:7-15: feature [B,C,h,w] (cast to bf16), mask [B,1,H,W] float ->
+    [1,1,C] fp32: mean over images of sum(f * m_lr) / (sum(m_lr) + 1e-5), m_lr = bilinear
+    align_corners=True resample of mask to [h,w]."""
+    feature = _cuda(feature, torch.bfloat16)
+    mask = _cuda(mask, torch.float32)
+    B, C, h, w = feature.shape
+    H, W = mask.shape[-2:]
+    if mask.shape[0] != B or mask.numel() != B * H * W:
+        raise ValueError('mask must be [B,1,H,W]')
+    dev = feature.device
+    ws = torch.empty(B * h * w + B, dtype=torch.float32, device=dev)
+    per_image = torch.empty(B, C, dtype=torch.float32, device=dev)
+    proto = torch.empty(C, dtype=torch.float32, device=dev)
+    call('sl_map_proto', ptr(feature), ptr(mask), B, C, h, w, H, W, ptr(ws), ptr(per_image), ptr(proto), _stream())
+    out = proto.view(1, 1, C)
+    return (out, per_image) if return_per_image else out
+
+
+class _OrthLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, others):
+        rows_c = rows.detach().to(torch.float32).contiguous()
+        Kr, C = rows_c.shape
+        Ko = 0 if others is None else others.shape[0]
+        oth = None if Ko == 0 else others.detach().to(torch.float32).contiguous()
+        dev = rows_c.device
+        sim = torch.empty(Kr, Kr + Ko, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(rows_c)
+        call('sl_orth_loss', ptr(rows_c), Kr, ptr(oth), Ko, C, ptr(sim), ptr(loss), ptr(grad), _stream())
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(sim)
+        return loss.reshape(()), sim
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_sim):
+        (grad,) = ctx.saved_tensors
+        return grad * g_loss, None
+
+
+def orth_loss(rows, others=None):
+    """proto_sim + OrthLoss.get_orth_loss (loss/criterion.py:37-43) in one kernel.
+    Base training (pspnet_pop.py:185-186): orth_loss(base_emb) -> sim [Kb,Kb].
+    Fine-tuning (pspnet_pop.py:234-239): orth_loss(novel_emb, base_emb) -> sim [Kn,Kn+Kb]
+    (base_emb is frozen in ft mode, so only `rows` receives a gradient).
+    Returns (loss scalar, proto_sim); differentiable w.r.t. rows."""
+    if not rows.is_cuda:
+        raise ValueError('orth_loss needs CUDA tensors')
+    return _OrthLossFn.apply(rows, others)
+
+
+# =================================================================================== fusion
+def fuse_logits(mats, n_lists=None, label=None, cm=None, ignore_label=IGNORE_LABEL, want_fused=False):
+    """fusemat.py:42-48 for one tile (or a batch laid out as one long pixel axis): mats is the
+    list of per-model logit stacks [K,H,W] (or [K,...]) fp32, summed in list order, divided by
+    n_lists (= len(fusion_list); defaults to len(mats)), argmax over K -> uint8 [H,W]."""
+    mats = [_cuda(m, torch.float32) for m in mats]
+    K = mats[0].shape[0]
+    shape = tuple(mats[0].shape[1:])
+    HW = int(np.prod(shape))
+    for m in mats:
+        if tuple(m.shape) != (K,) + shape:
+            raise ValueError('all stacks must share one shape')
+    dev = mats[0].device
+    pred = torch.empty(shape, dtype=torch.uint8, device=dev)
+    fused = torch.empty((K,) + shape, dtype=torch.float32, device=dev) if want_fused else None
+    if cm is not None:
+        label = _cuda(label, torch.uint8)
+    call('sl_fuse_argmax', ptr_array(mats), len(mats), K, HW, int(len(mats) if n_lists is None else n_lists),
+         ptr(pred), ptr(fused), ptr(label) if cm is not None else None, int(ignore_label), ptr(cm), _stream())
+    return (pred, fused) if want_fused else pred

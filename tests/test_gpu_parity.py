@@ -1,0 +1,368 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (via segland_b200.ops),
+against the CPU oracle and the reference-generated golden fixtures.
+
+Tolerances (north_star): logits / probabilities / prototypes within 1e-3 relative (helpers.RTOL,
+tested both relative-to-max and element-wise); argmax maps agree on >= 99.99% of pixels with
+every disagreement a near-tie; confusion matrices, label maps from integer paths and fused
+argmax maps bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import RTOL, argmax_agreement, assert_close_rel, bf16_from_bits, rel_err, state_from_npz
+from oracle import ref_ops
+from segland_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+HEAD_CASES = ['head_base_c64', 'head_ft_c64', 'head_base_c512', 'head_ft_c192_s4', 'head_ft_c96_rand']
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from segland_b200 import ops as _ops
+    _ops.check_device()
+    return _ops
+
+
+def make_head(ops, st, bg_mode):
+    return ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n, bg_mode=bg_mode)
+
+
+def tc_ok(C, N):
+    return C % 64 == 0 and 64 <= C <= 512 and N % 128 == 0
+
+
+# ------------------------------------------------------------------------------------ head
+@pytest.mark.parametrize('name', HEAD_CASES)
+@pytest.mark.parametrize('bg_mode', ['simt', 'tc'])
+def test_head_vs_golden(ops, golden, name, bg_mode):
+    z = golden(name)
+    st = state_from_npz(z)
+    feats = bf16_from_bits(z['feats_bf16_bits'])
+    B, C, h, w = feats.shape
+    if bg_mode == 'tc' and not tc_ok(C, h * w):
+        pytest.skip('shape outside the tensor-core kernel range')
+    head = make_head(ops, st, bg_mode)
+    logits = head(feats.cuda())
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(z['logits'])
+    assert_close_rel(logits.cpu(), ref, RTOL, f'{name}/{bg_mode} logits')
+    # prepare outputs: normalised prototypes
+    protos = st.base_emb if st.novel_emb is None else torch.cat([st.base_emb, st.novel_emb])
+    assert_close_rel(head._plan.s_hat.cpu(), F.normalize(protos, dim=-1), 1e-5, 's_hat')
+    # downstream: argmax + confusion through the fused kernel
+    H, W = z['labels'].shape[-2:]
+    K = st.n_classes
+    cm = torch.zeros(K, K, dtype=torch.int64, device='cuda')
+    labels = torch.from_numpy(z['labels'])
+    out = ops.upsample_argmax(logits, (H, W), label=labels, cm=cm, want_logits=True)
+    pred = out['pred'].cpu().numpy()
+    agree = argmax_agreement(pred, z['pred'], out['logits'].cpu().numpy(), tie_tol=5e-3)
+    assert agree >= 0.999, agree                       # tiny maps: one near-tie pixel is > 1e-4
+    # the confusion matrix is bit-exact for the prediction the kernel itself made
+    cm_ref = sum(ref_ops.ref_confusion(z['labels'][t], pred[t], K) for t in range(B))
+    assert np.array_equal(cm.cpu().numpy().astype(np.float64), cm_ref)
+    if agree == 1.0:
+        assert np.array_equal(cm.cpu().numpy().astype(np.float64), z['cm'])
+
+
+@pytest.mark.parametrize('mode,C,Kn,hw,bg_mode', [
+    ('base', 512, 0, 64, 'simt'), ('ft', 512, 4, 64, 'simt'), ('base', 512, 0, 64, 'tc'), ('ft', 512, 4, 64, 'tc'),
+    ('ft', 192, 4, 64, 'tc'), ('ft', 96, 4, 32, 'simt'), ('ft', 480, 4, 16, 'simt'), ('ft', 256, 4, 32, 'tc'),
+    ('ft', 128, 4, 32, 'tc')])
+def test_head_vs_oracle_seeded(ops, mode, C, Kn, hw, bg_mode):
+    """Seeded synthetic tiles at model geometries the golden files do not cover."""
+    if bg_mode == 'tc' and not tc_ok(C, hw * hw):
+        pytest.skip('shape outside the tensor-core kernel range')
+    st = synth.make_head_state(C, 7, Kn, seed=100 + C)
+    stride = 8
+    labels = synth.make_labels(1, hw * stride, hw * stride, st.n_classes, seed=C, coarse=8)
+    feats = synth.make_features(labels, st, stride, seed=C)
+    ref = ref_ops.ref_head(feats.float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
+    logits = make_head(ops, st, bg_mode)(feats.cuda())
+    assert_close_rel(logits.cpu(), ref, RTOL, f'{mode} C={C} {bg_mode}')
+    # per-channel check too: the background channel must hold the bound on its own
+    assert_close_rel(logits[:, 0].cpu(), ref[:, 0], RTOL, 'bg channel')
+    assert_close_rel(logits[:, 1:].cpu(), ref[:, 1:], RTOL, 'fg channels')
+
+
+def test_head_random_features_and_ragged_batch(ops):
+    """Pure-noise features (worst case for ties), B=3, N not a multiple of the CTA tile."""
+    st = synth.make_head_state(64, 7, 4, seed=9)
+    feats = synth.make_random_features(3, 64, 5, 8, seed=9)          # N = 40: 8 | N, 64 does not
+    ref = ref_ops.ref_head(feats.float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
+    logits = make_head(ops, st, 'simt')(feats.cuda())
+    assert_close_rel(logits.cpu(), ref, RTOL, 'ragged')
+
+
+def test_head_fg_only_and_refresh(ops):
+    st = synth.make_head_state(64, 7, 0, seed=10)
+    feats = synth.make_random_features(1, 64, 8, 8, seed=10).cuda()
+    head = make_head(ops, st, 'simt')
+    full = head(feats).clone()
+    out = torch.full_like(full, 7.0)
+    head(feats, out=out, fg_only=True)
+    assert torch.equal(out[:, 1:], full[:, 1:]) and bool((out[:, 0] == 7.0).all())
+    # weights change -> refresh() picks them up
+    head.base_emb.mul_(-1.0)
+    head.refresh()
+    st.base_emb = -st.base_emb
+    ref = ref_ops.ref_head(feats.cpu().float(), st.base_emb, None, st.cls, None)
+    assert_close_rel(head(feats).cpu(), ref, RTOL, 'after refresh')
+
+
+def test_head_tc_matches_simt_on_device(ops):
+    """The tensor-core background path against the exact fp32 path, same inputs, on the device."""
+    st = synth.make_head_state(512, 7, 4, seed=77)
+    feats = synth.make_random_features(2, 512, 32, 32, seed=77).cuda()
+    a = make_head(ops, st, 'simt')(feats)
+    b = make_head(ops, st, 'tc')(feats)
+    assert torch.equal(a[:, 1:], b[:, 1:])
+    assert_close_rel(b[:, 0].cpu(), a[:, 0].cpu(), 2e-4, 'tc vs simt bg')
+
+
+def test_head_argument_errors(ops):
+    st = synth.make_head_state(64, 7, 0, seed=1)
+    head = make_head(ops, st, 'simt')
+    with pytest.raises(ValueError):
+        head(torch.zeros(1, 32, 8, 8, dtype=torch.bfloat16, device='cuda'))
+    with pytest.raises(ValueError):
+        head(torch.zeros(1, 64, 3, 3, dtype=torch.bfloat16, device='cuda'))     # N % 8 != 0
+    from segland_b200 import _cabi
+    with pytest.raises(_cabi.SeglandError):                                       # NULL pointer -> SL_ENULL
+        _cabi.call('sl_pop_fg_lowres', None, 1, 64, 64, None, None, None, 7, None, 8, _cabi.int_array([1] * 7), None)
+
+
+# ---------------------------------------------------------------------- upsample / argmax
+def test_upsample_cases_vs_golden(ops, golden):
+    z = golden('upsample_cases')
+    i, total, agree_px = 0, 0, 0
+    while f'in{i}' in z.files:
+        lg = torch.from_numpy(z[f'in{i}']).cuda()
+        H, W = z[f'out{i}'].shape[-2:]
+        out = ops.upsample_argmax(lg, (H, W), want_logits=True, want_probs=True, want_conf=True)
+        up = out['logits'].cpu()
+        assert_close_rel(up, torch.from_numpy(z[f'out{i}']), 1e-5, f'upsample case {i}')
+        a = argmax_agreement(out['pred'].cpu().numpy(), z[f'pred{i}'], z[f'out{i}'], tie_tol=1e-5)
+        total += H * W
+        agree_px += a * H * W
+        # bit-exact against torch's own CUDA kernel (the reference's live GPU path)
+        up_t = F.interpolate(lg, size=(H, W), mode='bilinear', align_corners=True)
+        assert torch.equal(out['logits'], up_t), f'case {i}: differs from ATen CUDA upsample'
+        assert torch.equal(out['pred'].long(), up_t.argmax(1))
+        # softmax outputs (spec: this repo) against torch
+        sm = torch.softmax(up_t, dim=1)
+        assert_close_rel(out['probs'].cpu(), sm.cpu(), 1e-5, 'probs')
+        assert_close_rel(out['conf'].cpu(), sm.max(1)[0].cpu(), 1e-5, 'conf')
+        i += 1
+    assert agree_px / total >= 0.9999
+
+
+def test_argmax_first_max_and_nan(ops):
+    lg = torch.zeros(1, 4, 2, 2, device='cuda')
+    assert int(ops.upsample_argmax(lg, (4, 4))['pred'].max()) == 0          # all ties -> index 0
+    lg[0, 2] = 1.0
+    lg[0, 3] = 1.0
+    assert bool((ops.upsample_argmax(lg, (4, 4))['pred'] == 2).all())       # first maximum
+    lg[0, 1, 0, 0] = float('nan')
+    pred = ops.upsample_argmax(lg, (2, 2))['pred'].cpu().numpy()
+    ref = np.argmax(lg.cpu().numpy(), axis=1).astype(np.uint8)              # NaN wins, like np.argmax
+    assert np.array_equal(pred, ref)
+
+
+def test_pseudo_label_vs_golden(ops, golden):
+    z = golden('orth_pseudo')
+    preds_all = torch.from_numpy(z['preds_all'])
+    B = preds_all.shape[0]
+    preds2_base = torch.cat([preds_all[B // 2:, :1], preds_all[B // 2:, 1 + 7:]], dim=1).contiguous()
+    mask = torch.from_numpy(z['mask_b_before'].copy()).cuda()
+    ret = ops.pseudo_label(preds2_base.cuda(), mask, 7)
+    assert ret.data_ptr() == mask.data_ptr()                               # in place
+    got, want = mask.cpu().numpy(), z['mask_b_after']
+    assert (got == want).mean() >= 0.999
+    changed = z['mask_b_before'] == 0
+    assert np.array_equal(got[~changed], z['mask_b_before'][~changed])       # only background is touched
+    # bit-exact against the same computation with torch CUDA ops
+    m2 = torch.from_numpy(z['mask_b_before'].copy()).cuda()
+    up = F.interpolate(preds2_base.cuda(), size=m2.shape[-2:], mode='bilinear', align_corners=True)
+    idx = up.argmax(1)
+    idx[idx > 0] += 7
+    m2[m2 == 0] = idx[m2 == 0]
+    assert torch.equal(mask, m2)
+
+
+def test_views_reduce(ops):
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(2, 12, 8, 8, generator=g).cuda()
+    views = torch.stack([base, base.flip(-1), base.flip(-2), base.flip(-1, -2)])
+    out = ops.aggregate_views(views, [0, 1, 2, 3])
+    assert torch.allclose(out, base, atol=1e-6)
+    # flip commutes with align-corners upsampling: pred(view) flipped back == pred(orig)
+    p0 = ops.upsample_argmax(base, (64, 64))['pred']
+    p1 = ops.upsample_argmax(base.flip(-1).contiguous(), (64, 64))['pred'].flip(-1)
+    assert (p0 == p1).float().mean() >= 0.9999
+
+
+# --------------------------------------------------------------------------------- metrics
+def test_confusion_vs_golden(ops, golden):
+    z = golden('metrics')
+    cm = ops.get_confusion_matrix(z['gt'], z['pred'], 12)
+    assert cm.dtype == np.float64 and np.array_equal(cm, z['cm'])
+    keep = z['gt'] != 255                                                   # the reference's filtered call
+    assert np.array_equal(ops.get_confusion_matrix(z['gt'][keep], z['pred'][keep], 12), z['cm'])
+
+
+@pytest.mark.parametrize('n', [0, 1, 15, 16, 17, 1000, 1 << 20, (1 << 20) + 5])
+def test_confusion_sizes_and_alignment(ops, n):
+    rng = np.random.default_rng(n)
+    gt = rng.integers(0, 12, size=n + 3).astype(np.uint8)
+    gt[rng.random(n + 3) < 0.1] = 255
+    pr = rng.integers(0, 12, size=n + 3).astype(np.uint8)
+    for off in (0, 3):                                                       # aligned and unaligned views
+        g, p = torch.from_numpy(gt).cuda()[off:off + n], torch.from_numpy(pr).cuda()[off:off + n]
+        cm = torch.zeros(12, 12, dtype=torch.int64, device='cuda')
+        from segland_b200 import _cabi
+        _cabi.call('sl_confusion', _cabi.ptr(g), _cabi.ptr(p), n, 12, 255, _cabi.ptr(cm), None, None)
+        ref = ref_ops.ref_confusion(gt[off:off + n], pr[off:off + n], 12)
+        assert np.array_equal(cm.cpu().numpy().astype(np.float64), ref)
+
+
+def test_confusion_out_of_range_labels(ops):
+    gt = torch.tensor([0, 1, 200, 255, 3], dtype=torch.uint8)
+    pr = torch.tensor([0, 2, 1, 1, 99], dtype=torch.uint8)
+    cm = torch.zeros(4, 4, dtype=torch.int64, device='cuda')
+    bad = ops.confusion_update(cm, gt, pr)
+    assert int(cm.sum()) == 2 and int(cm[0, 0]) == 1 and int(cm[1, 2]) == 1 and int(bad) == 2
+
+
+def test_inter_union_vs_golden(ops, golden):
+    z = golden('metrics')
+    out = torch.from_numpy(z['pred'].astype(np.int64)).cuda()
+    tgt = torch.from_numpy(z['gt'].astype(np.int64)).cuda()
+    inter, union, target = ops.intersectionAndUnionGPU(out, tgt, 12, 255)
+    assert inter.dtype == torch.float32
+    assert np.array_equal(inter.cpu().numpy(), z['inter_t'])
+    assert np.array_equal(union.cpu().numpy(), z['union_t'])
+    assert np.array_equal(target.cpu().numpy(), z['target_t'])
+    assert np.array_equal(out.cpu().numpy(), z['output_after'])             # in-place side effect
+
+
+# ------------------------------------------------------------------------ prototypes / loss
+def test_map_vs_golden(ops, golden):
+    z = golden('map')
+    p = ops.masked_average_pooling(bf16_from_bits(z['feats_bf16_bits']).cuda(), torch.from_numpy(z['masks']).cuda())
+    assert p.shape == (1, 1, 64)
+    assert_close_rel(p.cpu(), torch.from_numpy(z['proto']), RTOL, 'map')
+    p2 = ops.masked_average_pooling(bf16_from_bits(z['feats2_bf16_bits']).cuda(), torch.from_numpy(z['masks2']).cuda())
+    assert_close_rel(p2.cpu(), torch.from_numpy(z['proto2']), RTOL, 'map soft mask, 10x12 -> N=120')
+
+
+def test_map_empty_mask(ops):
+    feats = synth.make_random_features(2, 32, 8, 8, seed=1).cuda()
+    p = ops.masked_average_pooling(feats, torch.zeros(2, 1, 64, 64, device='cuda'))
+    assert bool((p == 0).all())                                             # 0 / (0 + 1e-5)
+
+
+def test_orth_loss_vs_golden(ops, golden):
+    z = golden('orth_pseudo')
+    stb, stf = state_from_npz(z, 'b_'), state_from_npz(z, 'f_')
+    rows = stb.base_emb.cuda().requires_grad_(True)
+    loss, sim = ops.orth_loss(rows)
+    assert_close_rel(sim.cpu(), torch.from_numpy(z['sim_b']), 1e-5, 'sim base')
+    assert abs(loss.item() - float(z['orth_b'])) <= 1e-5 * abs(float(z['orth_b']))
+    loss.backward()
+    assert_close_rel(rows.grad.cpu(), torch.from_numpy(z['orth_grad_b']), RTOL, 'orth grad base')
+    rows = stf.novel_emb.cuda().requires_grad_(True)
+    loss, sim = ops.orth_loss(rows, stf.base_emb.cuda())
+    assert sim.shape == (4, 11)
+    assert_close_rel(sim.cpu(), torch.from_numpy(z['sim_f']), 1e-5, 'sim ft')
+    assert abs(loss.item() - float(z['orth_f'])) <= 1e-5 * abs(float(z['orth_f']))
+    (10.0 * loss).backward()                                                 # OrthLoss.w = 10
+    assert_close_rel(rows.grad.cpu(), 10.0 * torch.from_numpy(z['orth_grad_f']), RTOL, 'orth grad ft')
+
+
+# ---------------------------------------------------------------------------------- fusion
+def test_fuse_vs_golden(ops, golden):
+    z = golden('fuse')
+    for tile in ('tile_a', 'tile_b'):
+        mats = [torch.from_numpy(z[f'{tile}_m{m}']).cuda() for m in range(3)]
+        pred, fused = ops.fuse_logits(mats, want_fused=True)
+        ref_pred, ref_fused = ref_ops.ref_fuse([z[f'{tile}_m{m}'] for m in range(3)])
+        assert np.array_equal(fused.cpu().numpy(), ref_fused)               # same IEEE ops, same order
+        assert np.array_equal(pred.cpu().numpy(), z[f'{tile}_pred'])        # bit-exact vs fusemat.py itself
+
+
+@pytest.mark.parametrize('M', [1, 2, 5])
+def test_fuse_model_counts_and_divisor(ops, M):
+    mats = synth.make_logit_stacks(M, 12, 32, 32, seed=M)
+    ref_pred, ref_fused = ref_ops.ref_fuse([m.numpy() for m in mats], n_lists=M + 1)
+    labels = synth.make_labels(1, 32, 32, 12, seed=M, coarse=4)[0]
+    cm = torch.zeros(12, 12, dtype=torch.int64, device='cuda')
+    pred, fused = ops.fuse_logits([m.cuda() for m in mats], n_lists=M + 1, label=labels, cm=cm, want_fused=True)
+    assert np.array_equal(pred.cpu().numpy(), ref_pred) and np.array_equal(fused.cpu().numpy(), ref_fused)
+    assert np.array_equal(cm.cpu().numpy().astype(np.float64), ref_ops.ref_confusion(labels.numpy(), ref_pred, 12))
+
+
+# ------------------------------------------------------- whole path, configs[0] and full size
+def test_eval_two_512_tiles_vs_oracle(ops):
+    """BASELINE configs[0]: PSPNet-POP base eval on 2 synthetic 512x512 OEM-shaped tiles."""
+    from segland_b200 import sweep
+    st = synth.make_head_state(512, 7, 0, seed=1234)
+    labels = synth.make_labels(2, 512, 512, 8, seed=1234)
+    feats = synth.make_features(labels, st, 8, seed=1234)
+    K = st.n_classes
+    ev = sweep.TileEvaluator(make_head(ops, st, 'auto'), (512, 512))
+    out = ev.step(feats.cuda(), labels.cuda(), want_logits=True)
+    cm, (base, novel, total, arr) = ev.finalize(base_classes=7)
+    pred = out['pred'].cpu().numpy()
+    cm_ref = np.zeros((K, K))
+    logits_ref = []
+    for t in range(2):
+        p, c, lg = ref_ops.ref_eval_tile(feats[t:t + 1].float(), labels[t:t + 1].numpy(), st.base_emb, None, st.cls,
+                                         None, (512, 512), K)
+        agree = argmax_agreement(pred[t:t + 1], p, out['logits'][t:t + 1].cpu().numpy(), tie_tol=5e-3)
+        assert agree >= 0.9999, agree
+        cm_ref += c
+        logits_ref.append(lg)
+    assert_close_rel(ev._logits.cpu(), torch.cat(logits_ref), RTOL, 'configs[0] logits')
+    mine = cm.cpu().numpy().astype(np.float64)
+    assert mine.sum() == cm_ref.sum() == (labels != 255).sum().item()
+    assert np.abs(mine - cm_ref).sum() <= 2 * 1e-4 * cm_ref.sum()           # only near-tie pixels may move
+    ref_total = ref_ops.ref_miou(cm_ref, 7)[2]
+    assert abs(total - ref_total) < 1e-3
+
+
+def test_full_size_properties(ops):
+    """BASELINE configs[1] size (1024^2 tiles, C=512, 128x128 features): size-independent
+    properties instead of the (slow) oracle."""
+    from segland_b200 import sweep
+    T = 4
+    st = synth.make_head_state(512, 7, 0, seed=4321)
+    labels = synth.make_labels(T, 1024, 1024, 8, seed=4321)
+    feats = synth.make_features(labels, st, 8, seed=4321).cuda()
+    labels_d = labels.cuda()
+    ev = sweep.TileEvaluator(make_head(ops, st, 'auto'), (1024, 1024))
+    out = ev.step(feats, labels_d)
+    pred = out['pred']
+    # 1. the fused confusion matrix equals a separate pass over (label, pred): checksum of checksums
+    cm2 = torch.zeros_like(ev.cm)
+    ops.confusion_update(cm2, labels_d, pred)
+    assert torch.equal(ev.cm, cm2)
+    assert int(ev.cm.sum()) == int((labels != 255).sum())
+    assert torch.equal(ev.cm.sum(1).cpu(), torch.bincount(labels[labels != 255].long().flatten(), minlength=8))
+    # 2. batch independence: tile t alone gives the same prediction as inside the batch
+    ev1 = sweep.TileEvaluator(ev.head, (1024, 1024))
+    p1 = ev1.step(feats[2:3], labels_d[2:3])['pred']
+    assert torch.equal(p1[0], pred[2])
+    # 3. accumulation is additive across steps
+    ev.step(feats, labels_d)
+    assert torch.equal(ev.cm, 2 * cm2)
+    # 4. the synthetic signal is recoverable: mIoU well above chance
+    assert ops.miou_from_confusion(cm2, 7)[2] > 0.5
+    # 5. homogeneity of the head: logits(2q) == 2 logits(q) exactly (power-of-two scaling)
+    lg1 = ev.head(feats[:1]).clone()
+    lg2 = ev.head((feats[:1].float() * 2).to(torch.bfloat16))
+    assert torch.equal(lg2, 2 * lg1)
