@@ -177,7 +177,6 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from segland_b200 import ops, sweep, synth
-    from segland_b200._cabi import call, ptr
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -214,13 +213,10 @@ def run_ours(args, rank, world, local_rank):
             ev._logits = lg = torch.empty(T, K, HW_LR, HW_LR, dtype=torch.float32, device=dev)
         head(feats, out=lg, fg_only=True)
         if record: marks[2].record(stream)
-        p = head._plan
         if use_tc:
-            call('sl_pop_bg_tc', ptr(feats), T, C, N_PIX, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
-                 ptr(p.split[3]), ptr(p.w3_bg), ptr(lg), K, 0, stream.cuda_stream)
+            head.bg_tc(feats, lg)
         else:
-            call('sl_pop_bg_simt', ptr(feats), T, C, N_PIX, ptr(p.W1p_t), ptr(p.W2_t), ptr(p.w3_bg), ptr(lg), K, 0,
-                 stream.cuda_stream)
+            head.bg_simt(feats, lg)
         if record: marks[3].record(stream)
         out = ops.upsample_argmax(lg, (TILE, TILE), label=labels, cm=ev.cm)
         if record:

@@ -107,12 +107,15 @@ SL_API int sl_pop_bg_simt(const uint16_t *feat, int B, int C, int N,
 
 /* Background logit on tcgen05 tensor cores with split-bf16 operands (2 + 3 MMA
  * passes, fp32 accumulation in TMEM).  C % 64 == 0, 64 <= C <= 512, N % 128 == 0.
- * Returns SL_EINVAL for shapes outside that range (callers fall back to _simt).
+ * Returns SL_EINVAL for shapes outside that range (callers use _simt there).
+ *   h1_ws: scratch for the hidden layer, sl_pop_bg_tc_ws_bytes(B, C, N) bytes
+ *          ([2][B*N][C] bf16: relu(W1' q) split into hi and lo halves), 16-byte aligned.
  */
+SL_API size_t sl_pop_bg_tc_ws_bytes(int B, int C, int N);
 SL_API int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
                  const uint16_t *W1p_hi, const uint16_t *W1p_lo,
                  const uint16_t *W2_hi, const uint16_t *W2_lo, const float *w3_bg,
-                 float *logits, int Ktot, int ch, void *stream);
+                 uint16_t *h1_ws, float *logits, int Ktot, int ch, void *stream);
 
 /* Test-time view aggregation at feature resolution (spec: this repo -- the reference
  * has no flip/sliding-window inference): out = scale * sum_v unflip(view_v).

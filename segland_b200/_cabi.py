@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'lib', 'libsegland_b200.so')
@@ -19,7 +19,7 @@ _SIGNATURES = {
     'sl_pop_prepare': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'sl_pop_fg_lowres': [_P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int, POINTER(c_int), _P],
     'sl_pop_bg_simt': [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P],
-    'sl_pop_bg_tc': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, _P],
+    'sl_pop_bg_tc': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P],
     'sl_views_reduce': [_P, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_float, _P, _P],
     'sl_upsample_argmax': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P],
     'sl_pseudo_label': [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
@@ -54,6 +54,8 @@ def lib():
             fn.restype = c_int
         handle.sl_error_string.argtypes = [c_int]
         handle.sl_error_string.restype = c_char_p
+        handle.sl_pop_bg_tc_ws_bytes.argtypes = [c_int, c_int, c_int]
+        handle.sl_pop_bg_tc_ws_bytes.restype = c_size_t
         if handle.sl_abi_version() != 1:
             raise ImportError(f'{LIB_PATH}: ABI version {handle.sl_abi_version()} != 1; rebuild')
         _lib = handle
@@ -61,7 +63,7 @@ def lib():
 
 
 def exported_names():
-    return list(_SIGNATURES) + ['sl_error_string']
+    return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes']
 
 
 def call(name, *args):

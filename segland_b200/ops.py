@@ -90,6 +90,7 @@ class PopHead:
             raise ValueError(bg_mode)
         self.bg_mode = bg_mode
         self._plan = None
+        self._h1_ws = None
         self.refresh()
 
     # -- construction helpers ------------------------------------------------------------
@@ -150,6 +151,23 @@ class PopHead:
             raise ValueError(f'bg_mode="tc" needs C % 64 == 0, C <= 512, N % 128 == 0 (C={self.C}, N={N})')
         return ok
 
+    def bg_tc(self, feats, out):
+        """Launch the tensor-core background MLP on bf16 features [B,C,h,w] into out[:,0]."""
+        B, C, h, w = feats.shape
+        N = h * w
+        need = _cabi.lib().sl_pop_bg_tc_ws_bytes(B, C, N)
+        if self._h1_ws is None or self._h1_ws.numel() * 2 < need or self._h1_ws.device != feats.device:
+            self._h1_ws = torch.empty(need // 2, dtype=torch.int16, device=feats.device)
+        p = self._plan
+        call('sl_pop_bg_tc', ptr(feats), B, C, N, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
+             ptr(p.split[3]), ptr(p.w3_bg), ptr(self._h1_ws), ptr(out), out.shape[1], 0, _stream())
+
+    def bg_simt(self, feats, out):
+        B, C, h, w = feats.shape
+        p = self._plan
+        call('sl_pop_bg_simt', ptr(feats), B, C, h * w, ptr(p.W1p_t), ptr(p.W2_t), ptr(p.w3_bg),
+             ptr(out), out.shape[1], 0, _stream())
+
     # -- forward ---------------------------------------------------------------------------
     def __call__(self, features, out=None, fg_only=False):
         """features [B,C,h,w] bf16 CUDA (other float dtypes are cast to bf16, as north_star
@@ -171,11 +189,9 @@ class PopHead:
              ptr(out), Ktot, self._ch_map, st)
         if not fg_only:
             if self._use_tc(N):
-                call('sl_pop_bg_tc', ptr(feats), B, C, N, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
-                     ptr(p.split[3]), ptr(p.w3_bg), ptr(out), Ktot, 0, st)
+                self.bg_tc(feats, out)
             else:
-                call('sl_pop_bg_simt', ptr(feats), B, C, N, ptr(p.W1p_t), ptr(p.W2_t), ptr(p.w3_bg),
-                     ptr(out), Ktot, 0, st)
+                self.bg_simt(feats, out)
         return out
 
     forward = __call__
