@@ -78,14 +78,17 @@ SL_API int sl_check_device(void);
  *   W2_t    [C_in][C_out] fp32, transposed W2_bg.
  *   W1p_hi/lo, W2_hi/lo  [C_out][C_in] bf16 split (hi = bf16(W), lo = bf16(W - hi)) for
  *           the tensor-core path; may all be NULL when only the SIMT path is used.
+ *   ws      scratch, sl_pop_prepare_ws_bytes(K, C) bytes (the two hidden layers of the 2K
+ *           +-s_hat_k vectors).
  */
+SL_API size_t sl_pop_prepare_ws_bytes(int K, int C);
 SL_API int sl_pop_prepare(const float *protos, int K, int Kb, int C,
                    const float *W1_fg, const float *W2_fg, const float *w3_fg,
                    const float *W1_bg, const float *W2_bg, const float *w3_bg,
                    float *s_hat, float *alpha, float *beta,
                    float *W1p_t, float *W2_t,
                    uint16_t *W1p_hi, uint16_t *W1p_lo, uint16_t *W2_hi, uint16_t *W2_lo,
-                   void *stream);
+                   float *ws, void *stream);
 
 /* K foreground logits at feature resolution (HBM-bound, CUDA cores).
  *   feat   [B,C,N] bf16 (features.flatten(2), pspnet_pop.py:148); N % 8 == 0,

@@ -16,7 +16,7 @@ _SIGNATURES = {
     # name: argtypes (restype is c_int unless noted)
     'sl_abi_version': [],
     'sl_check_device': [],
-    'sl_pop_prepare': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'sl_pop_prepare': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'sl_pop_fg_lowres': [_P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int, POINTER(c_int), _P],
     'sl_pop_bg_simt': [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P],
     'sl_pop_bg_tc': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P],
@@ -56,6 +56,8 @@ def lib():
         handle.sl_error_string.restype = c_char_p
         handle.sl_pop_bg_tc_ws_bytes.argtypes = [c_int, c_int, c_int]
         handle.sl_pop_bg_tc_ws_bytes.restype = c_size_t
+        handle.sl_pop_prepare_ws_bytes.argtypes = [c_int, c_int]
+        handle.sl_pop_prepare_ws_bytes.restype = c_size_t
         if handle.sl_abi_version() != 1:
             raise ImportError(f'{LIB_PATH}: ABI version {handle.sl_abi_version()} != 1; rebuild')
         _lib = handle
@@ -63,7 +65,7 @@ def lib():
 
 
 def exported_names():
-    return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes']
+    return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes', 'sl_pop_prepare_ws_bytes']
 
 
 def call(name, *args):

@@ -35,7 +35,10 @@ constexpr int B_BYTES_MAX = MAX_NT * BLOCK_K * 2;       // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2048 /*w3*/ + 256 /*barriers*/;
+// After the operand ring: a 32 KB region that holds w3 (MODE 2) or the epilogue's TMA-store staging
+// (MODE 1: 4 warps x 2 buffers x {hi,lo} x [32 rows][64 B]), then the barriers.
+constexpr int AUX_BYTES = 32768;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + AUX_BYTES + 256 /*barriers*/;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -67,6 +70,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// smem tile -> global (bulk async group); the source must be visible to the async proxy first.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -127,12 +144,14 @@ struct Params {
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1, Params p) {
+               const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
+               const __grid_constant__ CUtensorMap map_st0, const __grid_constant__ CUtensorMap map_st1, Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B wants 1024-byte tiles
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  float* w3s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);     // [512]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 2048);
+  float* w3s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);     // [512]  (MODE 2)
+  const uint32_t stage_out = base + STAGES * STAGE_BYTES;                 // store staging (MODE 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + AUX_BYTES);
   // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty; then the TMEM base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const uint32_t bar0 = smem_u32(bars);
@@ -149,6 +168,7 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0); tma_prefetch_desc(&map_b0); tma_prefetch_desc(&map_b1);
     if (MODE == 2) tma_prefetch_desc(&map_a1);
+    if (MODE == 1) { tma_prefetch_desc(&map_st0); tma_prefetch_desc(&map_st1); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -233,9 +253,9 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int sub = warp & 3;                     // TMEM sub-partition this warp may read
     const int row = sub * 32 + lane;              // row of the 128-pixel tile
     int acc = 0; uint32_t acc_phase = 0;
+    int chunk_ctr = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
       float logit = 0.f;
-      const size_t grow = static_cast<size_t>(mt) * BLOCK_M + row;       // global pixel row in [B*N]
       for (int nt = 0; nt < p.n_tiles; ++nt) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
@@ -254,13 +274,29 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               hi[j] = static_cast<uint32_t>(ah) | (static_cast<uint32_t>(bh) << 16);
               lo[j] = static_cast<uint32_t>(al) | (static_cast<uint32_t>(bl) << 16);
             }
-            const size_t off = grow * p.C + static_cast<size_t>(nt) * p.NT + c0;
-            uint4* dh = reinterpret_cast<uint4*>(p.h_hi + off);
-            uint4* dl = reinterpret_cast<uint4*>(p.h_lo + off);
+            // stage the 32x32 bf16 chunk (64 B per row, SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3) and
+            // hand it to TMA: the store engine writes full lines, the LSU only sees shared memory.
+            const int buf = chunk_ctr & 1;
+            ++chunk_ctr;
+            const uint32_t sbuf = stage_out + static_cast<uint32_t>(((warp - 2) * 2 + buf) * 4096);
+            if (lane == 0) tma_store_wait_read<1>();          // the store that last used this buffer has read it
+            __syncwarp();
+            const uint32_t rbase = sbuf + static_cast<uint32_t>(lane) * 64u;
+            const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              dh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-              dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+              const uint32_t off16 = ((static_cast<uint32_t>(q) ^ sw) << 4);
+              st_shared_v4(rbase + off16, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+              st_shared_v4(rbase + 2048u + off16, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int col = nt * p.NT + c0;
+              const int row0 = mt * BLOCK_M + sub * 32;
+              tma_store_2d(&map_st0, sbuf, col, row0);
+              tma_store_2d(&map_st1, sbuf + 2048u, col, row0);
+              tma_store_commit();
             }
           } else {
             const float* wv = w3s + nt * p.NT + c0;
@@ -272,6 +308,10 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));   // 4 warps -> barrier count 4
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      if (MODE == 1 && mt + static_cast<int>(gridDim.x) >= p.m_tiles) {
+        if (lane == 0) tma_store_wait_read<0>();     // last tile: staging must outlive the CTA's stores
+        __syncwarp();
       }
       if (MODE == 2) {
         const int img = mt / p.tiles_per_image;
@@ -307,7 +347,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // bf16 tensor of `rank` dims (innermost first), 128-byte swizzled box.
-static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint32_t* box) {
+static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint32_t* box,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return static_cast<int>(cudaErrorNotSupported);
   cuuint64_t strides[2];
@@ -315,7 +356,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t*
   if (rank == 3) strides[1] = dims[0] * dims[1] * 2;
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(cudaErrorInvalidValue);
 }
@@ -352,7 +393,7 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
   p.w3 = w3_bg;
   p.logits = logits;
 
-  CUtensorMap m_x, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l;
+  CUtensorMap m_x, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l, m_sh, m_sl;
   int rc;
   {  // features [B][C][N]: box = 64 pixels x 64 channels
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(B)};
@@ -372,6 +413,9 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
     cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
     if ((rc = make_map(&m_hh, p.h_hi, 2, dims, box))) return rc;
     if ((rc = make_map(&m_hl, p.h_lo, 2, dims, box))) return rc;
+    cuuint32_t sbox[2] = {32, 32};   // epilogue store: 32 channels (64 B) x 32 pixels, SWIZZLE_64B staging
+    if ((rc = make_map(&m_sh, p.h_hi, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map(&m_sl, p.h_lo, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
   cudaError_t e = cudaFuncSetAttribute(bg_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -379,9 +423,9 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = p.m_tiles < sl::kNumSMs ? p.m_tiles : sl::kNumSMs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  bg_gemm_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(m_x, m_x, m_w1h, m_w1l, p);
+  bg_gemm_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(m_x, m_x, m_w1h, m_w1l, m_sh, m_sl, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
-  bg_gemm_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(m_hh, m_hl, m_w2h, m_w2l, p);
+  bg_gemm_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(m_hh, m_hl, m_w2h, m_w2l, m_sh, m_sl, p);
   return SL_LAUNCH_RESULT();
 }

@@ -20,53 +20,62 @@ __global__ void __launch_bounds__(128) normalize_protos_kernel(const float* __re
   for (int i = threadIdx.x; i < C; i += 128) s_hat[static_cast<size_t>(blockIdx.x) * C + i] = row[i] / nrm;
 }
 
-// alpha_k = MLP(+s_hat_k), beta_k = MLP(-s_hat_k).  grid (K, 2), 256 threads.
-__global__ void __launch_bounds__(256) alpha_beta_kernel(const float* __restrict__ s_hat, int Kb, int C,
-                                                         const float* __restrict__ W1f, const float* __restrict__ W2f,
-                                                         const float* __restrict__ w3f, const float* __restrict__ W1g,
-                                                         const float* __restrict__ W2g, const float* __restrict__ w3g,
-                                                         float* __restrict__ alpha, float* __restrict__ beta) {
-  extern __shared__ float sm[];
-  float* x = sm;          // [C] input (+-s_hat_k)
-  float* h1 = sm + C;     // [C]
-  float* h2 = sm + 2 * C; // [C]
-  __shared__ float red[8];
-  const int k = blockIdx.x;
-  const float sign = blockIdx.y == 0 ? 1.f : -1.f;
-  const bool fg = k < Kb;
-  const float* W1 = fg ? W1f : W1g;
-  const float* W2 = fg ? W2f : W2g;
-  const float* w3 = fg ? w3f : w3g;
-  for (int i = threadIdx.x; i < C; i += 256) x[i] = sign * s_hat[static_cast<size_t>(k) * C + i];
-  __syncthreads();
+// alpha_k = MLP(+s_hat_k), beta_k = MLP(-s_hat_k) for all K classes: three small launches, one per
+// MLP layer, so that every weight row is read once by one warp (C/8 CTAs) instead of K*2 CTAs each
+// streaming both C x C matrices.  Vector v in [0, 2K): class v>>1, sign = v&1 ? -1 : +1.
+// Classes [0,Kb) use the fg weights, [Kb,K) the bg weights.
+
+// h1[v][o] = relu(+-W1x[o] . s_hat_k)        grid C/8, 256 threads (one warp per output row o)
+__global__ void __launch_bounds__(256) mlp1_kernel(const float* __restrict__ s_hat, int K, int Kb, int C,
+                                                   const float* __restrict__ W1f, const float* __restrict__ W1g,
+                                                   float* __restrict__ h1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < C; o += 8) {
-    const float* w = W1 + static_cast<size_t>(o) * C;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= C) return;
+  for (int k = 0; k < K; ++k) {
+    const float* w = (k < Kb ? W1f : W1g) + static_cast<size_t>(o) * C;
+    const float* s = s_hat + static_cast<size_t>(k) * C;
     float acc = 0.f;
-    for (int i = lane; i < C; i += 32) acc = fmaf(w[i], x[i], acc);
+    for (int i = lane; i < C; i += 32) acc = fmaf(__ldg(w + i), __ldg(s + i), acc);
     acc = warp_sum(acc);
-    if (lane == 0) h1[o] = fmaxf(acc, 0.f);
+    if (lane == 0) {
+      h1[static_cast<size_t>(2 * k) * C + o] = fmaxf(acc, 0.f);
+      h1[static_cast<size_t>(2 * k + 1) * C + o] = fmaxf(-acc, 0.f);
+    }
   }
-  __syncthreads();
-  for (int o = warp; o < C; o += 8) {
-    const float* w = W2 + static_cast<size_t>(o) * C;
+}
+
+// h2[v][o] = relu(W2x[o] . h1[v])
+__global__ void __launch_bounds__(256) mlp2_kernel(const float* __restrict__ h1, int K, int Kb, int C,
+                                                   const float* __restrict__ W2f, const float* __restrict__ W2g,
+                                                   float* __restrict__ h2) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= C) return;
+  for (int v = 0; v < 2 * K; ++v) {
+    const float* w = ((v >> 1) < Kb ? W2f : W2g) + static_cast<size_t>(o) * C;
+    const float* x = h1 + static_cast<size_t>(v) * C;
     float acc = 0.f;
-    for (int i = lane; i < C; i += 32) acc = fmaf(w[i], h1[i], acc);
+    for (int i = lane; i < C; i += 32) acc = fmaf(__ldg(w + i), x[i], acc);
     acc = warp_sum(acc);
-    if (lane == 0) h2[o] = fmaxf(acc, 0.f);
+    if (lane == 0) h2[static_cast<size_t>(v) * C + o] = fmaxf(acc, 0.f);
   }
-  __syncthreads();
+}
+
+// alpha/beta = w3x . h2[v]                   grid 2K, 128 threads
+__global__ void __launch_bounds__(128) mlp3_kernel(const float* __restrict__ h2, int Kb, int C,
+                                                   const float* __restrict__ w3f, const float* __restrict__ w3g,
+                                                   float* __restrict__ alpha, float* __restrict__ beta) {
+  __shared__ float red[4];
+  const int v = blockIdx.x, k = v >> 1;
+  const float* w3 = k < Kb ? w3f : w3g;
+  const float* x = h2 + static_cast<size_t>(v) * C;
   float acc = 0.f;
-  for (int i = threadIdx.x; i < C; i += 256) acc = fmaf(w3[i], h2[i], acc);
+  for (int i = threadIdx.x; i < C; i += 128) acc = fmaf(__ldg(w3 + i), x[i], acc);
   acc = warp_sum(acc);
-  if (lane == 0) red[warp] = acc;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i];
-    (blockIdx.y == 0 ? alpha : beta)[k] = t;
-  }
+  if (threadIdx.x == 0) ((v & 1) ? beta : alpha)[k] = red[0] + red[1] + red[2] + red[3];
 }
 
 // W1' = W1 (I - S^T S):  row o of W1' = W1[o] - sum_k (W1[o] . s_k) s_k.   grid C, 128 threads.
@@ -109,21 +118,29 @@ __global__ void __launch_bounds__(128) fold_weights_kernel(const float* __restri
 
 }  // namespace sl
 
+extern "C" size_t sl_pop_prepare_ws_bytes(int K, int C) {
+  if (K < 1 || C < 1) return 0;
+  return static_cast<size_t>(4) * K * C * sizeof(float);
+}
+
 extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const float* W1_fg, const float* W2_fg,
                               const float* w3_fg, const float* W1_bg, const float* W2_bg, const float* w3_bg,
                               float* s_hat, float* alpha, float* beta, float* W1p_t, float* W2_t, uint16_t* W1p_hi,
-                              uint16_t* W1p_lo, uint16_t* W2_hi, uint16_t* W2_lo, void* stream) {
+                              uint16_t* W1p_lo, uint16_t* W2_hi, uint16_t* W2_lo, float* ws, void* stream) {
   SL_CHECK_ARG(K >= 1 && K < SL_MAX_CLASSES && Kb >= 0 && Kb <= K);
   SL_CHECK_ARG(C >= 8 && C <= 1024 && C % 8 == 0);
   SL_CHECK_PTR(protos); SL_CHECK_PTR(W1_fg); SL_CHECK_PTR(W2_fg); SL_CHECK_PTR(w3_fg);
   SL_CHECK_PTR(W1_bg); SL_CHECK_PTR(W2_bg); SL_CHECK_PTR(w3_bg);
-  SL_CHECK_PTR(s_hat); SL_CHECK_PTR(alpha); SL_CHECK_PTR(beta);
+  SL_CHECK_PTR(s_hat); SL_CHECK_PTR(alpha); SL_CHECK_PTR(beta); SL_CHECK_PTR(ws);
   const int n_split = (W1p_hi != nullptr) + (W1p_lo != nullptr) + (W2_hi != nullptr) + (W2_lo != nullptr);
   SL_CHECK_ARG(n_split == 0 || n_split == 4);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   sl::normalize_protos_kernel<<<K, 128, 0, st>>>(protos, C, s_hat);
-  sl::alpha_beta_kernel<<<dim3(K, 2), 256, 3 * C * sizeof(float), st>>>(s_hat, Kb, C, W1_fg, W2_fg, w3_fg, W1_bg,
-                                                                        W2_bg, w3_bg, alpha, beta);
+  float* h1 = ws;                                        // [2K][C]
+  float* h2 = ws + static_cast<size_t>(2) * K * C;       // [2K][C]
+  sl::mlp1_kernel<<<(C + 7) / 8, 256, 0, st>>>(s_hat, K, Kb, C, W1_fg, W1_bg, h1);
+  sl::mlp2_kernel<<<(C + 7) / 8, 256, 0, st>>>(h1, K, Kb, C, W2_fg, W2_bg, h2);
+  sl::mlp3_kernel<<<2 * K, 128, 0, st>>>(h2, Kb, C, w3_fg, w3_bg, alpha, beta);
   if (W1p_t || W2_t || n_split)
     sl::fold_weights_kernel<<<C, 128, 0, st>>>(s_hat, K, C, W1_bg, W2_bg, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo);
   return SL_LAUNCH_RESULT();

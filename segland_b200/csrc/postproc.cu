@@ -161,6 +161,148 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(
   }
 }
 
+// ------------------------------------------------------------------ fast path (W % 4 == 0)
+// A thread owns 4 consecutive output columns of one image and walks down a band of output rows.
+// ATen's association is horizontal-first -- val = l0y*(l0x*a + l1x*b) + l1y*(l0x*c + l1x*d) -- so
+// the horizontal lerps Hrow[k][x] = l0x*in[k][r][x0] + l1x*in[k][r][x1] of a source row r serve every
+// output row that touches r (8 rows at the x8 scale of the stride-8 models).  Each thread caches
+// its own 4 columns of the two live source rows in shared memory (slot = r & 1, float4 per
+// channel: private to the thread, so no block barrier); an output pixel-channel then costs two
+// shared loads, two FMAs and the argmax compare instead of four global loads and six flops.
+// Bit-identical to the generic kernel (same expression tree).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) upsample_rows_kernel(
+    const float* __restrict__ logits_lr, int K, int h, int w, int H, int W, int rows_per_band, float sy, float sx,
+    const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred, float* __restrict__ conf,
+    float* __restrict__ probs, float* __restrict__ logits_hr, unsigned long long* __restrict__ cm) {
+  extern __shared__ __align__(16) float hrow[];                 // [2][K][THREADS] float4
+  __shared__ unsigned int hist[SL_MAX_CLASSES * SL_MAX_CLASSES];
+  const bool do_cm = cm != nullptr;
+  if (do_cm) {
+    for (int i = threadIdx.x; i < K * K; i += THREADS) hist[i] = 0u;
+    __syncthreads();
+  }
+  const int b = blockIdx.z;
+  const int x0 = (blockIdx.x * THREADS + threadIdx.x) * 4;
+  const bool col_ok = x0 < W;                                   // W % 4 == 0: all four columns or none
+  const int y_begin = blockIdx.y * rows_per_band;
+  const int y_end = min(H, y_begin + rows_per_band);
+  float4* my = reinterpret_cast<float4*>(hrow) + threadIdx.x;   // element [slot][k] at my[(slot*K + k) * THREADS]
+  SrcCoord cx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cx[j] = src_coord(sx, min(x0 + j, W - 1), w);
+  const float* plane = logits_lr + static_cast<size_t>(b) * K * h * w;
+  const size_t HW = static_cast<size_t>(H) * W;
+  int row_even = -1, row_odd = -1;                              // source rows held by slot 0 / slot 1
+
+  auto fill = [&](int r) {                                      // horizontal lerps of source row r
+    const int slot = r & 1;
+    if ((slot ? row_odd : row_even) == r) return;
+    if (slot) row_odd = r; else row_even = r;
+    const float* row = plane + static_cast<size_t>(r) * w;
+    for (int k = 0; k < K; ++k) {
+      const float* rk = row + static_cast<size_t>(k) * h * w;
+      float4 v;
+      v.x = cx[0].l0 * __ldg(rk + cx[0].i0) + cx[0].l1 * __ldg(rk + cx[0].i0 + cx[0].step);
+      v.y = cx[1].l0 * __ldg(rk + cx[1].i0) + cx[1].l1 * __ldg(rk + cx[1].i0 + cx[1].step);
+      v.z = cx[2].l0 * __ldg(rk + cx[2].i0) + cx[2].l1 * __ldg(rk + cx[2].i0 + cx[2].step);
+      v.w = cx[3].l0 * __ldg(rk + cx[3].i0) + cx[3].l1 * __ldg(rk + cx[3].i0 + cx[3].step);
+      my[(slot * K + k) * THREADS] = v;
+    }
+  };
+
+  for (int y = y_begin; y < y_end; ++y) {                       // uniform trip count across the block
+    int idx[4] = {0, 0, 0, 0};
+    int lab[4] = {-1, -1, -1, -1};
+    if (col_ok) {
+      const SrcCoord cy = src_coord(sy, y, h);
+      fill(cy.i0);
+      fill(cy.i0 + cy.step);
+      const float4* h0 = my + ((cy.i0 & 1) * K) * THREADS;
+      const float4* h1 = my + (((cy.i0 + cy.step) & 1) * K) * THREADS;
+      const size_t pix = (static_cast<size_t>(b) * H + y) * W + x0;
+      float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        const float4 a = h0[k * THREADS], c = h1[k * THREADS];
+        const float v[4] = {cy.l0 * a.x + cy.l1 * c.x, cy.l0 * a.y + cy.l1 * c.y, cy.l0 * a.z + cy.l1 * c.z,
+                            cy.l0 * a.w + cy.l1 * c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) argmax_step(v[j], k, best[j], idx[j]);
+        if (logits_hr)
+          *reinterpret_cast<float4*>(logits_hr + (static_cast<size_t>(b) * K + k) * HW + static_cast<size_t>(y) * W + x0) =
+              make_float4(v[0], v[1], v[2], v[3]);
+      }
+      if (conf || probs) {                                      // softmax: recompute instead of keeping K values
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < K; ++k) {
+          const float4 a = h0[k * THREADS], c = h1[k * THREADS];
+          s[0] += __expf(cy.l0 * a.x + cy.l1 * c.x - best[0]);
+          s[1] += __expf(cy.l0 * a.y + cy.l1 * c.y - best[1]);
+          s[2] += __expf(cy.l0 * a.z + cy.l1 * c.z - best[2]);
+          s[3] += __expf(cy.l0 * a.w + cy.l1 * c.w - best[3]);
+        }
+        const float inv[4] = {1.f / s[0], 1.f / s[1], 1.f / s[2], 1.f / s[3]};
+        if (conf) *reinterpret_cast<float4*>(conf + pix) = make_float4(inv[0], inv[1], inv[2], inv[3]);
+        if (probs)
+          for (int k = 0; k < K; ++k) {
+            const float4 a = h0[k * THREADS], c = h1[k * THREADS];
+            *reinterpret_cast<float4*>(probs + (static_cast<size_t>(b) * K + k) * HW + static_cast<size_t>(y) * W + x0) =
+                make_float4(__expf(cy.l0 * a.x + cy.l1 * c.x - best[0]) * inv[0],
+                            __expf(cy.l0 * a.y + cy.l1 * c.y - best[1]) * inv[1],
+                            __expf(cy.l0 * a.z + cy.l1 * c.z - best[2]) * inv[2],
+                            __expf(cy.l0 * a.w + cy.l1 * c.w - best[3]) * inv[3]);
+          }
+      }
+      if (pred) *reinterpret_cast<uchar4*>(pred + pix) = make_uchar4(idx[0], idx[1], idx[2], idx[3]);
+      if (do_cm) {
+        const uchar4 l4 = *reinterpret_cast<const uchar4*>(label + pix);
+        lab[0] = l4.x; lab[1] = l4.y; lab[2] = l4.z; lab[3] = l4.w;
+      }
+    }
+    if (do_cm) {
+      bool valid[4];
+      int bin[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        valid[j] = lab[j] >= 0 && lab[j] != ignore_label && lab[j] < K;
+        bin[j] = valid[j] ? lab[j] * K + idx[j] : 0;
+      }
+      // fast path: every lane's four pixels fall in one bin (label/pred maps are spatially coherent)
+      const bool uni = valid[0] && valid[1] && valid[2] && valid[3] && bin[0] == bin[1] && bin[1] == bin[2] &&
+                       bin[2] == bin[3];
+      if (__all_sync(0xffffffffu, uni)) {
+        const int lbin = __shfl_sync(0xffffffffu, bin[0], 0);
+        const unsigned same = __ballot_sync(0xffffffffu, bin[0] == lbin);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&hist[lbin], 4u * __popc(same));
+        if (bin[0] != lbin) atomicAdd(&hist[bin[0]], 4u);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hist_add_warp(hist, bin[j], valid[j]);
+      }
+    }
+  }
+  if (do_cm) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K; i += THREADS)
+      if (hist[i]) atomicAdd(&cm[i], static_cast<unsigned long long>(hist[i]));
+  }
+}
+
+template <int THREADS>
+static int launch_rows(const float* logits_lr, int B, int K, int h, int w, int H, int W, int rows_per_band, float sy,
+                       float sx, const uint8_t* label, int ignore_label, uint8_t* pred, float* conf, float* probs,
+                       float* logits_hr, unsigned long long* cm, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(2) * K * THREADS * sizeof(float4);
+  cudaError_t e = cudaFuncSetAttribute(upsample_rows_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  dim3 grid((W / 4 + THREADS - 1) / THREADS, (H + rows_per_band - 1) / rows_per_band, B);
+  upsample_rows_kernel<THREADS><<<grid, THREADS, smem, st>>>(logits_lr, K, h, w, H, W, rows_per_band, sy, sx, label,
+                                                           ignore_label, pred, conf, probs, logits_hr, cm);
+  return SL_LAUNCH_RESULT();
+}
+
 // ------------------------------------------------------------------ pseudo-labelling
 __global__ void __launch_bounds__(256) pseudo_label_kernel(const float* __restrict__ preds2, int B, int K2, int h, int w,
                                                            int H, int W, float sy, float sx, int n_base,
@@ -324,10 +466,22 @@ extern "C" int sl_upsample_argmax(const float* logits_lr, int B, int K, int h, i
     if (logits_hr) SL_CHECK_ALIGN(logits_hr, 16);
   }
   const float sy = sl::ac_scale(h, H), sx = sl::ac_scale(w, W);
-  const long long items = static_cast<long long>(B) * H * ((W + sl::UP_PX - 1) / sl::UP_PX);
-  const int grid = sl::grid_for(items, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto* cmu = reinterpret_cast<unsigned long long*>(cm);
+  if (W % 4 == 0 && B <= 65535) {
+    // Row-cached fast path.  Pick the CTA shape so that small problems still fill 148 SMs:
+    // shared memory per CTA = 2*K*THREADS*16 B (K=12, 256 threads: 96 KB -> 2 CTAs/SM).
+    const long long px = static_cast<long long>(B) * H * W;
+    const bool big = px >= (8ll << 20) && W >= 1024 && K <= 12;
+    const int rows = big ? 32 : 16;
+    if (big)
+      return sl::launch_rows<256>(logits_lr, B, K, h, w, H, W, rows, sy, sx, label, ignore_label, pred, conf, probs,
+                                  logits_hr, cmu, st);
+    return sl::launch_rows<64>(logits_lr, B, K, h, w, H, W, rows, sy, sx, label, ignore_label, pred, conf, probs,
+                               logits_hr, cmu, st);
+  }
+  const long long items = static_cast<long long>(B) * H * ((W + sl::UP_PX - 1) / sl::UP_PX);
+  const int grid = sl::grid_for(items, 8);
 #define SL_UP_LAUNCH(KP) sl::upsample_argmax_kernel<KP><<<grid, 256, 0, st>>>( \
       logits_lr, B, K, h, w, H, W, sy, sx, label, ignore_label, pred, conf, probs, logits_hr, cmu)
   if (!(conf || probs)) SL_UP_LAUNCH(0);

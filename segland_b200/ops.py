@@ -135,10 +135,11 @@ class PopHead:
         split = tuple(new(C, C, dtype=torch.int16) for _ in range(4)) if want_split else None
         plan = _Plan(new(K, C), new(K), new(K), new(C, C), new(C, C), bg[2], split)
         sp = split if split else (None,) * 4
+        ws = new(_cabi.lib().sl_pop_prepare_ws_bytes(K, C) // 4)
         with torch.cuda.device(dev):
             call('sl_pop_prepare', ptr(protos.contiguous()), K, self.Kb, C, ptr(fg[0]), ptr(fg[1]), ptr(fg[2]),
                  ptr(bg[0]), ptr(bg[1]), ptr(bg[2]), ptr(plan.s_hat), ptr(plan.alpha), ptr(plan.beta),
-                 ptr(plan.W1p_t), ptr(plan.W2_t), ptr(sp[0]), ptr(sp[1]), ptr(sp[2]), ptr(sp[3]), _stream())
+                 ptr(plan.W1p_t), ptr(plan.W2_t), ptr(sp[0]), ptr(sp[1]), ptr(sp[2]), ptr(sp[3]), ptr(ws), _stream())
         self._plan = plan
         self._ch_map = int_array([1 + k for k in range(K)])
         return self
