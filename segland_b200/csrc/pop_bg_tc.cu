@@ -15,11 +15,12 @@
 //   MODE 2  logit[pixel] = sum_n w3[n] relu(H1 W2^T)[pixel, n]: epilogue reduces over the n-tile
 //           in registers; one CTA owns every n-tile of its 128-pixel tile so no atomics.
 // Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2..5 = epilogue (tcgen05.ld, one TMEM lane = one pixel per thread).  128 x NT fp32
+// warps 2.. = epilogue (tcgen05.ld, one TMEM lane = one pixel per thread).  128 x NT fp32
 // accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of one n-tile
 // overlaps the MMAs of the next.  Operands arrive by TMA (SWIZZLE_128B) through a 4-stage
 // mbarrier ring: 16 KB (A) + up to 32 KB (B) per stage.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace sl {
@@ -34,9 +35,15 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int B_BYTES_MAX = MAX_NT * BLOCK_K * 2;       // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 192;
+// warps: 0 = TMA producer, 1 = MMA issuer, then the epilogue warps.  Layer 1's epilogue converts and
+// stores 128 x NT x {hi,lo} bf16 per n-tile and is the critical path there, so it gets 8 warps (two per
+// TMEM sub-partition, each taking half of the columns); layer 2's epilogue is a dot product: 4 warps.
+template <int MODE> struct Cfg {
+  static constexpr int EPI_WARPS = MODE == 1 ? 8 : 4;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+};
 // After the operand ring: a 32 KB region that holds w3 (MODE 2) or the epilogue's TMA-store staging
-// (MODE 1: 4 warps x 2 buffers x {hi,lo} x [32 rows][64 B]), then the barriers.
+// (MODE 1: 8 warps x {hi,lo} x [32 rows][64 B]), then the barriers.
 constexpr int AUX_BYTES = 32768;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + AUX_BYTES + 256 /*barriers*/;
 
@@ -139,10 +146,11 @@ struct Params {
   uint16_t* h_lo;
   const float* w3;  // MODE 2
   float* logits;    // MODE 2 out
+  int debug;        // SL_TC_DEBUG experiments: 1 = no epilogue stores, 2 = no epilogue work at all
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(Cfg<MODE>::THREADS, 1)
 bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
                const __grid_constant__ CUtensorMap map_st0, const __grid_constant__ CUtensorMap map_st1, Params p) {
@@ -170,7 +178,7 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (MODE == 2) tma_prefetch_desc(&map_a1);
     if (MODE == 1) { tma_prefetch_desc(&map_st0); tma_prefetch_desc(&map_st1); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg<MODE>::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -179,7 +187,7 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (MODE == 2)
-    for (int i = threadIdx.x; i < p.C; i += NUM_THREADS) w3s[i] = p.w3[i];
+    for (int i = threadIdx.x; i < p.C; i += Cfg<MODE>::THREADS) w3s[i] = p.w3[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -249,18 +257,24 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
   } else {
-    // ===================================================================== epilogue (4 warps)
+    // ===================================================================== epilogue
     const int sub = warp & 3;                     // TMEM sub-partition this warp may read
     const int row = sub * 32 + lane;              // row of the 128-pixel tile
+    const int half = (warp - 2) >> 2;             // MODE 1: which half of the n-tile's 32-column chunks
+    const int n_chunks = p.NT / 32;
+    const int c_begin = Cfg<MODE>::EPI_WARPS == 8 ? (half == 0 ? 0 : (n_chunks + 1) / 2) : 0;
+    const int c_end = Cfg<MODE>::EPI_WARPS == 8 ? (half == 0 ? (n_chunks + 1) / 2 : n_chunks) : n_chunks;
+    const uint32_t sbuf = stage_out + static_cast<uint32_t>((warp - 2) * 4096);
     int acc = 0; uint32_t acc_phase = 0;
-    int chunk_ctr = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
       float logit = 0.f;
       for (int nt = 0; nt < p.n_tiles; ++nt) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(acc * MAX_NT);
-        for (int c0 = 0; c0 < p.NT; c0 += 32) {
+        for (int ch = c_begin; ch < c_end; ++ch) {
+          if (p.debug & 2) break;
+          const int c0 = ch * 32;
           uint32_t r[32];
           tc_ld32(taddr + c0, r);
           tc_ld_wait();
@@ -269,17 +283,17 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float a = fmaxf(__uint_as_float(r[2 * j]), 0.f), b = fmaxf(__uint_as_float(r[2 * j + 1]), 0.f);
-              const uint16_t ah = f32_to_bf16_rn(a), bh = f32_to_bf16_rn(b);
-              const uint16_t al = f32_to_bf16_rn(a - bf16_bits_to_f32(ah)), bl = f32_to_bf16_rn(b - bf16_bits_to_f32(bh));
-              hi[j] = static_cast<uint32_t>(ah) | (static_cast<uint32_t>(bh) << 16);
-              lo[j] = static_cast<uint32_t>(al) | (static_cast<uint32_t>(bl) << 16);
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);          // one cvt.rn.bf16x2.f32
+              const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hb << 16),
+                                                              b - __uint_as_float(hb & 0xffff0000u));
+              hi[j] = hb;
+              lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
             }
             // stage the 32x32 bf16 chunk (64 B per row, SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3) and
             // hand it to TMA: the store engine writes full lines, the LSU only sees shared memory.
-            const int buf = chunk_ctr & 1;
-            ++chunk_ctr;
-            const uint32_t sbuf = stage_out + static_cast<uint32_t>(((warp - 2) * 2 + buf) * 4096);
-            if (lane == 0) tma_store_wait_read<1>();          // the store that last used this buffer has read it
+            if (p.debug & 1) continue;
+            if (lane == 0) tma_store_wait_read<0>();          // the previous store has drained this buffer
             __syncwarp();
             const uint32_t rbase = sbuf + static_cast<uint32_t>(lane) * 64u;
             const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
@@ -306,18 +320,18 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));   // 4 warps -> barrier count 4
+        if (lane == 0) mbar_arrive(tempty_bar(acc));   // one arrival per epilogue warp
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-      if (MODE == 1 && mt + static_cast<int>(gridDim.x) >= p.m_tiles) {
-        if (lane == 0) tma_store_wait_read<0>();     // last tile: staging must outlive the CTA's stores
-        __syncwarp();
       }
       if (MODE == 2) {
         const int img = mt / p.tiles_per_image;
         const int n = (mt - img * p.tiles_per_image) * BLOCK_M + row;
         p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
       }
+    }
+    if (MODE == 1) {
+      if (lane == 0) tma_store_wait_read<0>();         // staging must outlive the CTA's last stores
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -392,6 +406,10 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
   p.h_lo = h1_ws + static_cast<size_t>(B) * N * C;
   p.w3 = w3_bg;
   p.logits = logits;
+  {
+    const char* dbg = getenv("SL_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
 
   CUtensorMap m_x, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l, m_sh, m_sl;
   int rc;
@@ -423,9 +441,9 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = p.m_tiles < sl::kNumSMs ? p.m_tiles : sl::kNumSMs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  bg_gemm_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(m_x, m_x, m_w1h, m_w1l, m_sh, m_sl, p);
+  bg_gemm_kernel<1><<<grid, Cfg<1>::THREADS, SMEM_BYTES, st>>>(m_x, m_x, m_w1h, m_w1l, m_sh, m_sl, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
-  bg_gemm_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(m_hh, m_hl, m_w2h, m_w2l, m_sh, m_sl, p);
+  bg_gemm_kernel<2><<<grid, Cfg<2>::THREADS, SMEM_BYTES, st>>>(m_hh, m_hl, m_w2h, m_w2l, m_sh, m_sl, p);
   return SL_LAUNCH_RESULT();
 }

@@ -168,10 +168,21 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(
 // output row that touches r (8 rows at the x8 scale of the stride-8 models).  Each thread caches
 // its own 4 columns of the two live source rows in shared memory (slot = r & 1, float4 per
 // channel: private to the thread, so no block barrier); an output pixel-channel then costs two
-// shared loads, two FMAs and the argmax compare instead of four global loads and six flops.
-// Bit-identical to the generic kernel (same expression tree).
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) upsample_rows_kernel(
+// shared loads, a multiply, an FMA and a 3-instruction argmax step instead of four global loads
+// and six flops.  Bit-identical to the generic kernel (same expression tree).  Non-finite inputs
+// are detected when a source row is staged and routed to the NaN-aware (np.argmax) compare.
+
+// Warp-aggregated histogram update for (bin, count) pairs: lanes holding the same bin are grouped
+// with match.any, their counts summed with redux, and one shared-memory atomic is issued per
+// distinct bin in the warp.
+__device__ __forceinline__ void hist_add_grouped(unsigned int* hist, int bin, unsigned int cnt) {
+  const unsigned peers = __match_any_sync(0xffffffffu, bin);
+  const unsigned total = __reduce_add_sync(peers, cnt);
+  if ((threadIdx.x & 31) == (__ffs(peers) - 1) && total) atomicAdd(&hist[bin], total);
+}
+
+template <int THREADS, bool EXTRA>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8) upsample_rows_kernel(
     const float* __restrict__ logits_lr, int K, int h, int w, int H, int W, int rows_per_band, float sy, float sx,
     const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred, float* __restrict__ conf,
     float* __restrict__ probs, float* __restrict__ logits_hr, unsigned long long* __restrict__ cm) {
@@ -188,98 +199,116 @@ __global__ void __launch_bounds__(THREADS) upsample_rows_kernel(
   const int y_begin = blockIdx.y * rows_per_band;
   const int y_end = min(H, y_begin + rows_per_band);
   float4* my = reinterpret_cast<float4*>(hrow) + threadIdx.x;   // element [slot][k] at my[(slot*K + k) * THREADS]
-  SrcCoord cx[4];
+  int xi[4], xs[4];
+  float xl0[4], xl1[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) cx[j] = src_coord(sx, min(x0 + j, W - 1), w);
-  const float* plane = logits_lr + static_cast<size_t>(b) * K * h * w;
+  for (int j = 0; j < 4; ++j) {
+    const SrcCoord c = src_coord(sx, min(x0 + j, W - 1), w);
+    xi[j] = c.i0; xs[j] = c.i0 + c.step; xl0[j] = c.l0; xl1[j] = c.l1;
+  }
+  const int hw = h * w;
+  const float* plane = logits_lr + static_cast<size_t>(b) * K * hw;
   const size_t HW = static_cast<size_t>(H) * W;
   int row_even = -1, row_odd = -1;                              // source rows held by slot 0 / slot 1
+  bool bad_even = false, bad_odd = false;                       // slot holds a non-finite value
 
   auto fill = [&](int r) {                                      // horizontal lerps of source row r
     const int slot = r & 1;
     if ((slot ? row_odd : row_even) == r) return;
-    if (slot) row_odd = r; else row_even = r;
-    const float* row = plane + static_cast<size_t>(r) * w;
-    for (int k = 0; k < K; ++k) {
-      const float* rk = row + static_cast<size_t>(k) * h * w;
+    const float* rk = plane + r * w;
+    float4* dst = my + slot * K * THREADS;
+    bool bad = false;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k, rk += hw, dst += THREADS) {
       float4 v;
-      v.x = cx[0].l0 * __ldg(rk + cx[0].i0) + cx[0].l1 * __ldg(rk + cx[0].i0 + cx[0].step);
-      v.y = cx[1].l0 * __ldg(rk + cx[1].i0) + cx[1].l1 * __ldg(rk + cx[1].i0 + cx[1].step);
-      v.z = cx[2].l0 * __ldg(rk + cx[2].i0) + cx[2].l1 * __ldg(rk + cx[2].i0 + cx[2].step);
-      v.w = cx[3].l0 * __ldg(rk + cx[3].i0) + cx[3].l1 * __ldg(rk + cx[3].i0 + cx[3].step);
-      my[(slot * K + k) * THREADS] = v;
+      v.x = xl0[0] * __ldg(rk + xi[0]) + xl1[0] * __ldg(rk + xs[0]);
+      v.y = xl0[1] * __ldg(rk + xi[1]) + xl1[1] * __ldg(rk + xs[1]);
+      v.z = xl0[2] * __ldg(rk + xi[2]) + xl1[2] * __ldg(rk + xs[2]);
+      v.w = xl0[3] * __ldg(rk + xi[3]) + xl1[3] * __ldg(rk + xs[3]);
+      bad |= !(fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w) < INFINITY);
+      *dst = v;
     }
+    if (slot) { row_odd = r; bad_odd = bad; } else { row_even = r; bad_even = bad; }
   };
 
-  for (int y = y_begin; y < y_end; ++y) {                       // uniform trip count across the block
+  size_t pix = (static_cast<size_t>(b) * H + y_begin) * W + x0;
+  // labels are fetched one row ahead so the load latency hides behind a whole row of arithmetic
+  uchar4 l4_next = make_uchar4(0, 0, 0, 0);
+  if (do_cm && col_ok && y_begin < y_end) l4_next = *reinterpret_cast<const uchar4*>(label + pix);
+  for (int y = y_begin; y < y_end; ++y, pix += W) {             // uniform trip count across the block
     int idx[4] = {0, 0, 0, 0};
-    int lab[4] = {-1, -1, -1, -1};
+    const uchar4 l4 = l4_next;
     if (col_ok) {
+      if (do_cm && y + 1 < y_end) l4_next = *reinterpret_cast<const uchar4*>(label + pix + W);
       const SrcCoord cy = src_coord(sy, y, h);
+      const int r1 = cy.i0 + cy.step;
       fill(cy.i0);
-      fill(cy.i0 + cy.step);
+      fill(r1);
       const float4* h0 = my + ((cy.i0 & 1) * K) * THREADS;
-      const float4* h1 = my + (((cy.i0 + cy.step) & 1) * K) * THREADS;
-      const size_t pix = (static_cast<size_t>(b) * H + y) * W + x0;
+      const float4* h1 = my + ((r1 & 1) * K) * THREADS;
+      const float l0 = cy.l0, l1 = cy.l1;
       float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      const bool bad = ((cy.i0 & 1) ? bad_odd : bad_even) | ((r1 & 1) ? bad_odd : bad_even);
+      if (!bad) {
 #pragma unroll 4
-      for (int k = 0; k < K; ++k) {
-        const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-        const float v[4] = {cy.l0 * a.x + cy.l1 * c.x, cy.l0 * a.y + cy.l1 * c.y, cy.l0 * a.z + cy.l1 * c.z,
-                            cy.l0 * a.w + cy.l1 * c.w};
+        for (int k = 0; k < K; ++k) {
+          const float4 a = h0[k * THREADS], c = h1[k * THREADS];
+          const float v[4] = {l0 * a.x + l1 * c.x, l0 * a.y + l1 * c.y, l0 * a.z + l1 * c.z, l0 * a.w + l1 * c.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) argmax_step(v[j], k, best[j], idx[j]);
-        if (logits_hr)
-          *reinterpret_cast<float4*>(logits_hr + (static_cast<size_t>(b) * K + k) * HW + static_cast<size_t>(y) * W + x0) =
-              make_float4(v[0], v[1], v[2], v[3]);
+          for (int j = 0; j < 4; ++j)
+            if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; }
+          if (EXTRA && logits_hr)
+            *reinterpret_cast<float4*>(logits_hr + (static_cast<size_t>(b) * K + k) * HW + (pix - static_cast<size_t>(b) * HW)) =
+                make_float4(v[0], v[1], v[2], v[3]);
+        }
+      } else {
+        for (int k = 0; k < K; ++k) {
+          const float4 a = h0[k * THREADS], c = h1[k * THREADS];
+          const float v[4] = {l0 * a.x + l1 * c.x, l0 * a.y + l1 * c.y, l0 * a.z + l1 * c.z, l0 * a.w + l1 * c.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) argmax_step(v[j], k, best[j], idx[j]);
+          if (EXTRA && logits_hr)
+            *reinterpret_cast<float4*>(logits_hr + (static_cast<size_t>(b) * K + k) * HW + (pix - static_cast<size_t>(b) * HW)) =
+                make_float4(v[0], v[1], v[2], v[3]);
+        }
       }
-      if (conf || probs) {                                      // softmax: recompute instead of keeping K values
+      if (EXTRA && (conf || probs)) {                           // softmax: recompute instead of keeping K values
         float s[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k = 0; k < K; ++k) {
           const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-          s[0] += __expf(cy.l0 * a.x + cy.l1 * c.x - best[0]);
-          s[1] += __expf(cy.l0 * a.y + cy.l1 * c.y - best[1]);
-          s[2] += __expf(cy.l0 * a.z + cy.l1 * c.z - best[2]);
-          s[3] += __expf(cy.l0 * a.w + cy.l1 * c.w - best[3]);
+          s[0] += __expf(l0 * a.x + l1 * c.x - best[0]);
+          s[1] += __expf(l0 * a.y + l1 * c.y - best[1]);
+          s[2] += __expf(l0 * a.z + l1 * c.z - best[2]);
+          s[3] += __expf(l0 * a.w + l1 * c.w - best[3]);
         }
         const float inv[4] = {1.f / s[0], 1.f / s[1], 1.f / s[2], 1.f / s[3]};
         if (conf) *reinterpret_cast<float4*>(conf + pix) = make_float4(inv[0], inv[1], inv[2], inv[3]);
         if (probs)
           for (int k = 0; k < K; ++k) {
             const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-            *reinterpret_cast<float4*>(probs + (static_cast<size_t>(b) * K + k) * HW + static_cast<size_t>(y) * W + x0) =
-                make_float4(__expf(cy.l0 * a.x + cy.l1 * c.x - best[0]) * inv[0],
-                            __expf(cy.l0 * a.y + cy.l1 * c.y - best[1]) * inv[1],
-                            __expf(cy.l0 * a.z + cy.l1 * c.z - best[2]) * inv[2],
-                            __expf(cy.l0 * a.w + cy.l1 * c.w - best[3]) * inv[3]);
+            *reinterpret_cast<float4*>(probs + (static_cast<size_t>(b) * K + k) * HW + (pix - static_cast<size_t>(b) * HW)) =
+                make_float4(__expf(l0 * a.x + l1 * c.x - best[0]) * inv[0], __expf(l0 * a.y + l1 * c.y - best[1]) * inv[1],
+                            __expf(l0 * a.z + l1 * c.z - best[2]) * inv[2], __expf(l0 * a.w + l1 * c.w - best[3]) * inv[3]);
           }
       }
       if (pred) *reinterpret_cast<uchar4*>(pred + pix) = make_uchar4(idx[0], idx[1], idx[2], idx[3]);
-      if (do_cm) {
-        const uchar4 l4 = *reinterpret_cast<const uchar4*>(label + pix);
-        lab[0] = l4.x; lab[1] = l4.y; lab[2] = l4.z; lab[3] = l4.w;
-      }
     }
     if (do_cm) {
-      bool valid[4];
-      int bin[4];
+      // per-thread pre-aggregation: pixels that share the first valid pixel's bin are counted together
+      // (label/pred maps are piecewise constant), stragglers go one by one; then one grouped update.
+      const int lab[4] = {l4.x, l4.y, l4.z, l4.w};
+      int bin0 = -1;
+      unsigned int cnt = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        valid[j] = lab[j] >= 0 && lab[j] != ignore_label && lab[j] < K;
-        bin[j] = valid[j] ? lab[j] * K + idx[j] : 0;
+        const bool valid = col_ok && lab[j] != ignore_label && lab[j] < K;
+        const int bj = lab[j] * K + idx[j];
+        if (valid) {
+          if (bin0 < 0) bin0 = bj;
+          if (bj == bin0) ++cnt; else atomicAdd(&hist[bj], 1u);
+        }
       }
-      // fast path: every lane's four pixels fall in one bin (label/pred maps are spatially coherent)
-      const bool uni = valid[0] && valid[1] && valid[2] && valid[3] && bin[0] == bin[1] && bin[1] == bin[2] &&
-                       bin[2] == bin[3];
-      if (__all_sync(0xffffffffu, uni)) {
-        const int lbin = __shfl_sync(0xffffffffu, bin[0], 0);
-        const unsigned same = __ballot_sync(0xffffffffu, bin[0] == lbin);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&hist[lbin], 4u * __popc(same));
-        if (bin[0] != lbin) atomicAdd(&hist[bin[0]], 4u);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) hist_add_warp(hist, bin[j], valid[j]);
-      }
+      hist_add_grouped(hist, bin0 < 0 ? 0 : bin0, cnt);
     }
   }
   if (do_cm) {
@@ -294,12 +323,13 @@ static int launch_rows(const float* logits_lr, int B, int K, int h, int w, int H
                        float sx, const uint8_t* label, int ignore_label, uint8_t* pred, float* conf, float* probs,
                        float* logits_hr, unsigned long long* cm, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(2) * K * THREADS * sizeof(float4);
-  cudaError_t e = cudaFuncSetAttribute(upsample_rows_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+  const bool extra = conf || probs || logits_hr;
+  auto kern = extra ? upsample_rows_kernel<THREADS, true> : upsample_rows_kernel<THREADS, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid((W / 4 + THREADS - 1) / THREADS, (H + rows_per_band - 1) / rows_per_band, B);
-  upsample_rows_kernel<THREADS><<<grid, THREADS, smem, st>>>(logits_lr, K, h, w, H, W, rows_per_band, sy, sx, label,
-                                                           ignore_label, pred, conf, probs, logits_hr, cm);
+  kern<<<grid, THREADS, smem, st>>>(logits_lr, K, h, w, H, W, rows_per_band, sy, sx, label, ignore_label, pred, conf,
+                                    probs, logits_hr, cm);
   return SL_LAUNCH_RESULT();
 }
 
