@@ -78,6 +78,8 @@ SL_API int sl_check_device(void);
  *   W2_t    [C_in][C_out] fp32, transposed W2_bg.
  *   W1p_hi/lo, W2_hi/lo  [C_out][C_in] bf16 split (hi = bf16(W), lo = bf16(W - hi)) for
  *           the tensor-core path; may all be NULL when only the SIMT path is used.
+ *   W1p_f16, W2_f16  [C_out][C_in] IEEE fp16 copies of W1' and W2 (both or neither; NULL when
+ *           unused).  SL_TC_BALANCED reads W2_f16.
  *   ws      scratch, sl_pop_prepare_ws_bytes(K, C) bytes (the two hidden layers of the 2K
  *           +-s_hat_k vectors).
  */
@@ -88,7 +90,7 @@ SL_API int sl_pop_prepare(const float *protos, int K, int Kb, int C,
                    float *s_hat, float *alpha, float *beta,
                    float *W1p_t, float *W2_t,
                    uint16_t *W1p_hi, uint16_t *W1p_lo, uint16_t *W2_hi, uint16_t *W2_lo,
-                   float *ws, void *stream);
+                   uint16_t *W1p_f16, uint16_t *W2_f16, float *ws, void *stream);
 
 /* K foreground logits at feature resolution (HBM-bound, CUDA cores).
  *   feat   [B,C,N] bf16 (features.flatten(2), pspnet_pop.py:148); N % 8 == 0,
@@ -108,17 +110,23 @@ SL_API int sl_pop_bg_simt(const uint16_t *feat, int B, int C, int N,
                    const float *W1p_t, const float *W2_t, const float *w3_bg,
                    float *logits, int Ktot, int ch, void *stream);
 
-/* Background logit on tcgen05 tensor cores with split-bf16 operands (2 + 3 MMA
- * passes, fp32 accumulation in TMEM).  C % 64 == 0, 64 <= C <= 512, N % 128 == 0.
- * Returns SL_EINVAL for shapes outside that range (callers use _simt there).
- *   h1_ws: scratch for the hidden layer, sl_pop_bg_tc_ws_bytes(B, C, N) bytes
- *          ([2][B*N][C] bf16: relu(W1' q) split into hi and lo halves), 16-byte aligned.
+/* Background logit on tcgen05 tensor cores, fp32 accumulation in TMEM.
+ * C % 64 == 0, 64 <= C <= 512, N % 128 == 0; SL_EINVAL outside that range (callers use _simt).
+ *   precision  SL_TC_PRECISE  split-bf16 operands, 2 + 3 MMA passes: ~5e-6 of the fp32 reference.
+ *              SL_TC_BALANCED layer 1 split-bf16 (2 passes), layer 2 single-pass fp16 (3 passes):
+ *                             ~3e-4 relative to the tensor maximum.  Needs W2_f16.
+ *              The fp16 mode requires |relu(W1' q)| < 65504 (fp16 range).
+ *   Unused weight pointers for the chosen mode may be NULL.
+ *   h1_ws: scratch for the hidden layer, sl_pop_bg_tc_ws_bytes(B, C, N) bytes, 128-byte aligned
+ *          (two 128-pixel tiles per SM; it stays L2-resident).
  */
+#define SL_TC_PRECISE 0
+#define SL_TC_BALANCED 1
 SL_API size_t sl_pop_bg_tc_ws_bytes(int B, int C, int N);
 SL_API int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
                  const uint16_t *W1p_hi, const uint16_t *W1p_lo,
-                 const uint16_t *W2_hi, const uint16_t *W2_lo, const float *w3_bg,
-                 uint16_t *h1_ws, float *logits, int Ktot, int ch, void *stream);
+                 const uint16_t *W2_hi, const uint16_t *W2_lo,
+                 const uint16_t *W2_f16, const float *w3_bg, int precision, uint16_t *h1_ws, float *logits, int Ktot, int ch, void *stream);
 
 /* Test-time view aggregation at feature resolution (spec: this repo -- the reference
  * has no flip/sliding-window inference): out = scale * sum_v unflip(view_v).

@@ -8,18 +8,23 @@
 //   layer 2:  h = relu(.) = h_hi + h_lo  ->  h_hi.W2hi + h_lo.W2hi + h_hi.W2lo         (3 passes)
 // which lands within ~5e-6 of the fp32 reference.
 //
-// Two launches of one warp-specialised persistent GEMM kernel (sm_100a):
-//   MODE 1  H1[pixels, C] = relu(X^T W1'^T): A = feature tile straight from the NCHW tensor
-//           (MN-major UMMA operand, pixels contiguous), epilogue splits h into bf16 hi/lo and
-//           writes them K-major for layer 2.
-//   MODE 2  logit[pixel] = sum_n w3[n] relu(H1 W2^T)[pixel, n]: epilogue reduces over the n-tile
-//           in registers; one CTA owns every n-tile of its 128-pixel tile so no atomics.
+// One persistent, warp-specialised kernel (sm_100a) runs both layers.  A CTA owns 128-pixel tiles
+// t_0, t_1, ... and walks the job list
+//     G1(t_0) | G1(t_1) G2(t_0) | G1(t_2) G2(t_1) | ... | G2(t_last)
+// where G1(t) = relu(X_t W1'^T) split into bf16 hi/lo and written to a per-CTA, two-slot scratch tile
+// (256 KB per slot: it never leaves L2), and G2(t) = w3 . relu(H1_t W2^T).  Running G1 one tile ahead
+// hides the store -> load turnaround of the scratch tile behind a full layer-1 tile of MMAs.
+//   G1: A = feature tile straight from the NCHW tensor (MN-major UMMA operand, pixels contiguous).
+//   G2: A = the scratch tile (K-major); the epilogue reduces over channels in registers; a CTA owns
+//       every n-tile of its pixel tile, so no atomics.
 // Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2.. = epilogue (tcgen05.ld, one TMEM lane = one pixel per thread).  128 x NT fp32
-// accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of one n-tile
-// overlaps the MMAs of the next.  Operands arrive by TMA (SWIZZLE_128B) through a 4-stage
-// mbarrier ring: 16 KB (A) + up to 32 KB (B) per stage.
+// warps 2..9 = epilogue (tcgen05.ld, one TMEM lane = one pixel per thread; two warps per TMEM
+// sub-partition split the columns of a G1 tile).  128 x NT fp32 accumulators are double-buffered in
+// TMEM (2 x 256 columns), so the epilogue of one job overlaps the MMAs of the next.  Operands arrive
+// by TMA (SWIZZLE_128B) through a 4-stage mbarrier ring: 16 KB (A) + up to 32 KB (B) per stage; G1's
+// epilogue leaves through SWIZZLE_64B shared-memory staging and TMA bulk stores.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include "common.cuh"
 
@@ -35,17 +40,13 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int B_BYTES_MAX = MAX_NT * BLOCK_K * 2;       // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int TMEM_COLS = 512;
-// warps: 0 = TMA producer, 1 = MMA issuer, then the epilogue warps.  Layer 1's epilogue converts and
-// stores 128 x NT x {hi,lo} bf16 per n-tile and is the critical path there, so it gets 8 warps (two per
-// TMEM sub-partition, each taking half of the columns); layer 2's epilogue is a dot product: 4 warps.
-template <int MODE> struct Cfg {
-  static constexpr int EPI_WARPS = MODE == 1 ? 8 : 4;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
-};
-// After the operand ring: a 32 KB region that holds w3 (MODE 2) or the epilogue's TMA-store staging
-// (MODE 1: 8 warps x {hi,lo} x [32 rows][64 B]), then the barriers.
-constexpr int AUX_BYTES = 32768;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + AUX_BYTES + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int STAGING_BYTES = EPI_WARPS * 4096;         // per warp: {hi,lo} x [32 rows][64 B]
+constexpr int W3_BYTES = 2048;
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + W3_BYTES + BAR_BYTES;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -88,6 +89,9 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// full completion (writes performed), not just "source read"
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -128,57 +132,67 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return static_cast<uint64_t>((saddr & 0x3ffff) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
          (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A/B.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | (0u << 16) |
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate; operand formats 0 = fp16, 1 = bf16.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | (0u << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 struct Params {
-  int C;            // channels (K of both layers and N of both layers)
-  int NT;           // n-tile width
-  int n_tiles;      // C / NT
-  int m_tiles;      // B*N / 128
+  int C;                // channels (K of both layers and N of both layers)
+  int NT;               // n-tile width
+  int n_tiles;          // C / NT
+  int m_tiles;          // B*N / 128
   int tiles_per_image;  // N / 128
-  int N;            // pixels per image
-  int Ktot, ch;     // logits layout
-  uint16_t* h_hi;   // MODE 1 out: [B*N][C] bf16
-  uint16_t* h_lo;
-  const float* w3;  // MODE 2
-  float* logits;    // MODE 2 out
-  int debug;        // SL_TC_DEBUG experiments: 1 = no epilogue stores, 2 = no epilogue work at all
+  int N;                // pixels per image
+  int Ktot, ch;         // logits layout
+  int l1_passes;        // 2: split-bf16 W1' (hi, lo)
+  int h_f16;            // hidden layer stored as one fp16 tile (layer 2 = 1 pass) instead of bf16 hi/lo (3 passes)
+  const float* w3;
+  float* logits;
+  int debug;            // SL_TC_DEBUG experiments (timing only, results invalid): 1 = no st.shared staging,
+                        // 2 = no TMA stores, 4 = no LDTM/convert in G1
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(Cfg<MODE>::THREADS, 1)
-bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
-               const __grid_constant__ CUtensorMap map_st0, const __grid_constant__ CUtensorMap map_st1, Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B wants 1024-byte tiles
-  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  float* w3s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);     // [512]  (MODE 2)
-  const uint32_t stage_out = base + STAGES * STAGE_BYTES;                 // store staging (MODE 1)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + AUX_BYTES);
-  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty; then the TMEM base slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+struct Maps {           // 9 x 128 B of kernel parameter space
+  CUtensorMap x;                 // features [B][C][N], box 64 px x 64 ch
+  CUtensorMap w1h, w1l, w2h, w2l;  // weights [C][C], box 64 k x NT rows
+  CUtensorMap hh_ld, hl_ld;      // scratch [ctas*2*128][C], box 64 k x 128 rows (SWIZZLE_128B)
+  CUtensorMap hh_st, hl_st;      // same tensors, box 32 ch x 32 rows (SWIZZLE_64B) for the epilogue stores
+};
+
+__global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  if ((base & 1023u) != 0) asm volatile("trap;");                        // SWIZZLE_128B wants 1024-byte tiles
+  const uint32_t stage_out = base + STAGES * STAGE_BYTES;                // G1 store staging
+  float* w3s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES);   // [512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES + W3_BYTES);
+  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, [2S+4,2S+6) h1_full; then the
+  // TMEM base slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+  auto h1_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int PASSES = MODE == 1 ? 2 : 3;
   const int kblocks = p.C / BLOCK_K;
   const uint32_t b_bytes = static_cast<uint32_t>(p.NT) * BLOCK_K * 2;
+  const int n_my = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  auto tile_of = [&](int s) { return static_cast<int>(blockIdx.x) + s * static_cast<int>(gridDim.x); };
+  auto ws_row0 = [&](int s) { return (static_cast<int>(blockIdx.x) * 2 + (s & 1)) * BLOCK_M; };
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a0); tma_prefetch_desc(&map_b0); tma_prefetch_desc(&map_b1);
-    if (MODE == 2) tma_prefetch_desc(&map_a1);
-    if (MODE == 1) { tma_prefetch_desc(&map_st0); tma_prefetch_desc(&map_st1); }
+    tma_prefetch_desc(&maps.x); tma_prefetch_desc(&maps.w1h); tma_prefetch_desc(&maps.w1l);
+    tma_prefetch_desc(&maps.w2h); tma_prefetch_desc(&maps.w2l); tma_prefetch_desc(&maps.hh_ld);
+    tma_prefetch_desc(&maps.hl_ld); tma_prefetch_desc(&maps.hh_st); tma_prefetch_desc(&maps.hl_st);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg<MODE>::EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); mbar_init(h1_bar(s), EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -186,8 +200,7 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                  "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (MODE == 2)
-    for (int i = threadIdx.x; i < p.C; i += Cfg<MODE>::THREADS) w3s[i] = p.w3[i];
+  for (int i = threadIdx.x; i < p.C; i += THREADS) w3s[i] = p.w3[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -197,89 +210,112 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-        for (int nt = 0; nt < p.n_tiles; ++nt) {
-          for (int pass = 0; pass < PASSES; ++pass) {
-            const CUtensorMap* ma = (MODE == 2 && pass == 1) ? &map_a1 : &map_a0;
-            const CUtensorMap* mb = (MODE == 1 ? pass == 1 : pass == 2) ? &map_b1 : &map_b0;
-            for (int kb = 0; kb < kblocks; ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-              mbar_expect_tx(full_bar(stage), A_BYTES + b_bytes);
-              if (MODE == 1) {
-                // feature tile: 64 channels x 128 pixels as two 64-pixel (128-byte) column blocks
-                const int img = mt / p.tiles_per_image, n0 = (mt - img * p.tiles_per_image) * BLOCK_M;
-                tma_load_3d(sa, ma, full_bar(stage), n0, kb * BLOCK_K, img);
-                tma_load_3d(sa + A_BYTES / 2, ma, full_bar(stage), n0 + 64, kb * BLOCK_K, img);
-              } else {
-                tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, mt * BLOCK_M);
-              }
-              tma_load_2d(sb, mb, full_bar(stage), kb * BLOCK_K, nt * p.NT);
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      auto load_job = [&](bool g2, int s, int nt) {
+        const int passes = g2 ? (p.h_f16 ? 1 : 3) : p.l1_passes;
+        const int mt = tile_of(s);
+        const int img = mt / p.tiles_per_image, n0 = (mt - img * p.tiles_per_image) * BLOCK_M;
+        for (int pass = 0; pass < passes; ++pass) {
+          const CUtensorMap* ma = g2 ? (pass == 1 ? &maps.hl_ld : &maps.hh_ld) : &maps.x;
+          const CUtensorMap* mb = g2 ? (pass == 2 ? &maps.w2l : &maps.w2h) : (pass == 1 ? &maps.w1l : &maps.w1h);
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+            mbar_expect_tx(full_bar(stage), A_BYTES + b_bytes);
+            if (!g2) {   // feature tile: 64 channels x 128 pixels as two 64-pixel (128-byte) column blocks
+              tma_load_3d(sa, ma, full_bar(stage), n0, kb * BLOCK_K, img);
+              tma_load_3d(sa + A_BYTES / 2, ma, full_bar(stage), n0 + 64, kb * BLOCK_K, img);
+            } else {
+              tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, ws_row0(s));
             }
+            tma_load_2d(sb, mb, full_bar(stage), kb * BLOCK_K, nt * p.NT);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
+        }
+      };
+      for (int s = 0; s <= n_my; ++s) {
+        if (s < n_my)
+          for (int nt = 0; nt < p.n_tiles; ++nt) load_job(false, s, nt);
+        if (s >= 1) {
+          // the scratch tile of t_{s-1} is complete once all 8 epilogue warps have drained their stores
+          mbar_wait(h1_bar((s - 1) & 1), static_cast<uint32_t>(((s - 1) >> 1) & 1));
+          fence_proxy_async_all();
+          for (int nt = 0; nt < p.n_tiles; ++nt) load_job(true, s - 1, nt);
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_M, p.NT, MODE == 1);
+      const uint32_t idesc_g1 = make_idesc(BLOCK_M, p.NT, true, 1u, p.l1_passes == 1 ? 0u : 1u);
+      const uint32_t idesc_g2 = make_idesc(BLOCK_M, p.NT, false, p.h_f16 ? 0u : 1u, p.h_f16 ? 0u : 1u);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-        for (int nt = 0; nt < p.n_tiles; ++nt) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      auto mma_job = [&](bool g2) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MAX_NT);
+        const uint32_t idesc = g2 ? idesc_g2 : idesc_g1;
+        uint32_t accumulate = 0;
+        const int iters = (g2 ? (p.h_f16 ? 1 : 3) : p.l1_passes) * kblocks;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MAX_NT);
-          uint32_t accumulate = 0;
-          for (int it = 0; it < PASSES * kblocks; ++it) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              uint64_t da, db;
-              if (MODE == 1)   // MN-major: 16 k-rows of 128 B = 2 KB per UMMA_K; 64-pixel blocks 8 KB apart
-                da = make_desc(sa + k * (UMMA_K * 128), A_BYTES / 2, 1024);
-              else             // K-major: 32 bytes along the 128-byte row per UMMA_K
-                da = make_desc(sa + k * (UMMA_K * 2), 16, 1024);
-              db = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-              tc_mma(d_tmem, da, db, idesc, accumulate);
-              accumulate = 1;
-            }
-            tc_commit(empty_bar(stage));          // frees the smem stage once these MMAs retire
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // G1, MN-major A: 16 k-rows of 128 B = 2 KB per UMMA_K, the two 64-pixel blocks 8 KB apart.
+            // G2, K-major A: 32 bytes along the 128-byte row per UMMA_K.
+            const uint64_t da = g2 ? make_desc(sa + k * (UMMA_K * 2), 16, 1024)
+                                   : make_desc(sa + k * (UMMA_K * 128), A_BYTES / 2, 1024);
+            const uint64_t db = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            tc_mma(d_tmem, da, db, idesc, accumulate);
+            accumulate = 1;
           }
-          tc_commit(tfull_bar(acc));              // accumulator complete -> epilogue
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          tc_commit(empty_bar(stage));          // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        tc_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      };
+      for (int s = 0; s <= n_my; ++s) {
+        if (s < n_my)
+          for (int nt = 0; nt < p.n_tiles; ++nt) mma_job(false);
+        if (s >= 1)
+          for (int nt = 0; nt < p.n_tiles; ++nt) mma_job(true);
       }
     }
   } else {
-    // ===================================================================== epilogue
+    // ===================================================================== epilogue (8 warps)
     const int sub = warp & 3;                     // TMEM sub-partition this warp may read
     const int row = sub * 32 + lane;              // row of the 128-pixel tile
-    const int half = (warp - 2) >> 2;             // MODE 1: which half of the n-tile's 32-column chunks
+    const int half = (warp - 2) >> 2;             // which half of a G1 n-tile's 32-column chunks
     const int n_chunks = p.NT / 32;
-    const int c_begin = Cfg<MODE>::EPI_WARPS == 8 ? (half == 0 ? 0 : (n_chunks + 1) / 2) : 0;
-    const int c_end = Cfg<MODE>::EPI_WARPS == 8 ? (half == 0 ? (n_chunks + 1) / 2 : n_chunks) : n_chunks;
+    const int c_split = (n_chunks + 1) / 2;
     const uint32_t sbuf = stage_out + static_cast<uint32_t>((warp - 2) * 4096);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-      float logit = 0.f;
-      for (int nt = 0; nt < p.n_tiles; ++nt) {
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(acc * MAX_NT);
+    float logit = 0.f;
+    auto epi_job = [&](bool g2, int s, int nt) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(acc * MAX_NT);
+      if (!g2) {
+        const int c_begin = half == 0 ? 0 : c_split, c_end = half == 0 ? c_split : n_chunks;
         for (int ch = c_begin; ch < c_end; ++ch) {
-          if (p.debug & 2) break;
+          if (p.debug & 4) break;
           const int c0 = ch * 32;
           uint32_t r[32];
           tc_ld32(taddr + c0, r);
           tc_ld_wait();
-          if (MODE == 1) {
-            uint32_t hi[16], lo[16];
+          uint32_t hi[16], lo[16];
+          if (p.h_f16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __half2 h2 = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * j]), 0.f),
+                                                   fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
+              hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              lo[j] = 0u;
+            }
+          } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float a = fmaxf(__uint_as_float(r[2 * j]), 0.f), b = fmaxf(__uint_as_float(r[2 * j + 1]), 0.f);
@@ -290,48 +326,66 @@ bg_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               hi[j] = hb;
               lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
             }
-            // stage the 32x32 bf16 chunk (64 B per row, SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3) and
-            // hand it to TMA: the store engine writes full lines, the LSU only sees shared memory.
-            if (p.debug & 1) continue;
-            if (lane == 0) tma_store_wait_read<0>();          // the previous store has drained this buffer
-            __syncwarp();
-            const uint32_t rbase = sbuf + static_cast<uint32_t>(lane) * 64u;
-            const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+          }
+          // stage the 32x32 16-bit chunk (64 B per row, SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3) and
+          // hand it to TMA: the store engine writes full lines, the LSU only sees shared memory.
+          if (lane == 0) tma_store_wait_read<0>();          // the previous store has drained this buffer
+          __syncwarp();
+          const uint32_t rbase = sbuf + static_cast<uint32_t>(lane) * 64u;
+          const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+          if (!(p.debug & 1))
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t off16 = ((static_cast<uint32_t>(q) ^ sw) << 4);
-              st_shared_v4(rbase + off16, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-              st_shared_v4(rbase + 2048u + off16, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              const int col = nt * p.NT + c0;
-              const int row0 = mt * BLOCK_M + sub * 32;
-              tma_store_2d(&map_st0, sbuf, col, row0);
-              tma_store_2d(&map_st1, sbuf + 2048u, col, row0);
-              tma_store_commit();
-            }
-          } else {
-            const float* wv = w3s + nt * p.NT + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) logit = fmaf(wv[j], fmaxf(__uint_as_float(r[j]), 0.f), logit);
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t off16 = ((static_cast<uint32_t>(q) ^ sw) << 4);
+            st_shared_v4(rbase + off16, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            if (!p.h_f16) st_shared_v4(rbase + 2048u + off16, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 2)) {
+            const int col = nt * p.NT + c0;
+            const int row0 = ws_row0(s) + sub * 32;
+            tma_store_2d(&maps.hh_st, sbuf, col, row0);
+            if (!p.h_f16) tma_store_2d(&maps.hl_st, sbuf + 2048u, col, row0);
+            tma_store_commit();
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));   // one arrival per epilogue warp
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      } else if (half == 0) {
+        if (nt == 0) logit = 0.f;
+        for (int c0 = 0; c0 < p.NT; c0 += 32) {
+          uint32_t r[32];
+          tc_ld32(taddr + c0, r);
+          tc_ld_wait();
+          const float* wv = w3s + nt * p.NT + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) logit = fmaf(wv[j], fmaxf(__uint_as_float(r[j]), 0.f), logit);
+        }
       }
-      if (MODE == 2) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));   // one arrival per epilogue warp
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (!g2 && nt == p.n_tiles - 1) {
+        // scratch tile complete for this warp: wait until its bulk stores have landed, then tell the producer
+        if (lane == 0) {
+          tma_store_wait_all();
+          fence_proxy_async_all();
+          mbar_arrive(h1_bar(s & 1));
+        }
+        __syncwarp();
+      }
+      if (g2 && half == 0 && nt == p.n_tiles - 1) {
+        const int mt = tile_of(s);
         const int img = mt / p.tiles_per_image;
         const int n = (mt - img * p.tiles_per_image) * BLOCK_M + row;
         p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
       }
-    }
-    if (MODE == 1) {
-      if (lane == 0) tma_store_wait_read<0>();         // staging must outlive the CTA's last stores
-      __syncwarp();
+    };
+    for (int s = 0; s <= n_my; ++s) {
+      if (s < n_my)
+        for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(false, s, nt);
+      if (s >= 1)
+        for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(true, s - 1, nt);
     }
   }
   tc_fence_before();
@@ -380,19 +434,26 @@ static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t*
 
 extern "C" size_t sl_pop_bg_tc_ws_bytes(int B, int C, int N) {
   if (B < 1 || C < 1 || N < 1) return 0;
-  return static_cast<size_t>(2) * B * N * C * sizeof(uint16_t);
+  // per CTA: 2 slots x 128 rows x C channels x {hi, lo} bf16; sized for a full grid of 148 CTAs
+  return static_cast<size_t>(sl::kNumSMs) * 2 * sl::tc::BLOCK_M * C * 2 * sizeof(uint16_t);
 }
 
 extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uint16_t* W1p_hi, const uint16_t* W1p_lo,
-                            const uint16_t* W2_hi, const uint16_t* W2_lo, const float* w3_bg, uint16_t* h1_ws,
+                            const uint16_t* W2_hi, const uint16_t* W2_lo, const uint16_t* W2_f16,
+                            const float* w3_bg, int precision, uint16_t* h1_ws,
                             float* logits, int Ktot, int ch, void* stream) {
   using namespace sl::tc;
-  SL_CHECK_PTR(feat); SL_CHECK_PTR(W1p_hi); SL_CHECK_PTR(W1p_lo); SL_CHECK_PTR(W2_hi); SL_CHECK_PTR(W2_lo);
-  SL_CHECK_PTR(w3_bg); SL_CHECK_PTR(h1_ws); SL_CHECK_PTR(logits);
+  // (a bf16-feature x fp16-weight single pass for layer 1 was tried: tcgen05 kind::f16 traps on mixed A/B formats)
+  SL_CHECK_ARG(precision == SL_TC_PRECISE || precision == SL_TC_BALANCED);
+  SL_CHECK_PTR(feat); SL_CHECK_PTR(w3_bg); SL_CHECK_PTR(h1_ws); SL_CHECK_PTR(logits);
+  SL_CHECK_PTR(W1p_hi); SL_CHECK_PTR(W1p_lo);
+  if (precision == SL_TC_PRECISE) { SL_CHECK_PTR(W2_hi); SL_CHECK_PTR(W2_lo); } else { SL_CHECK_PTR(W2_f16); }
+  // pointers the chosen mode does not read alias a valid buffer so every tensor map stays well formed
+  if (precision != SL_TC_PRECISE) { W2_hi = W2_f16; W2_lo = W2_f16; }
   SL_CHECK_ARG(B >= 1 && C >= 64 && C <= 512 && C % 64 == 0 && N >= 128 && N % 128 == 0);
   SL_CHECK_ARG(Ktot >= 1 && Ktot <= SL_MAX_CLASSES && ch >= 0 && ch < Ktot);
   SL_CHECK_ARG(static_cast<long long>(B) * N / BLOCK_M < (1ll << 30));
-  SL_CHECK_ALIGN(feat, 16); SL_CHECK_ALIGN(h1_ws, 16);
+  SL_CHECK_ALIGN(feat, 16); SL_CHECK_ALIGN(h1_ws, 128);
   SL_CHECK_ALIGN(W1p_hi, 16); SL_CHECK_ALIGN(W1p_lo, 16); SL_CHECK_ALIGN(W2_hi, 16); SL_CHECK_ALIGN(W2_lo, 16);
 
   Params p;
@@ -402,48 +463,45 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
   p.m_tiles = static_cast<int>(static_cast<long long>(B) * N / BLOCK_M);
   p.tiles_per_image = N / BLOCK_M;
   p.N = N; p.Ktot = Ktot; p.ch = ch;
-  p.h_hi = h1_ws;
-  p.h_lo = h1_ws + static_cast<size_t>(B) * N * C;
   p.w3 = w3_bg;
   p.logits = logits;
+  p.l1_passes = 2;
+  p.h_f16 = precision == SL_TC_PRECISE ? 0 : 1;
   {
     const char* dbg = getenv("SL_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+  const int grid = p.m_tiles < sl::kNumSMs ? p.m_tiles : sl::kNumSMs;
+  const size_t ws_rows = static_cast<size_t>(sl::kNumSMs) * 2 * BLOCK_M;
+  uint16_t* h_hi = h1_ws;
+  uint16_t* h_lo = h1_ws + ws_rows * C;
 
-  CUtensorMap m_x, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l, m_sh, m_sl;
+  Maps m;
   int rc;
   {  // features [B][C][N]: box = 64 pixels x 64 channels
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(B)};
     cuuint32_t box[3] = {64, BLOCK_K, 1};
-    if ((rc = make_map(&m_x, feat, 3, dims, box))) return rc;
+    if ((rc = make_map(&m.x, feat, 3, dims, box))) return rc;
   }
   {  // weights [C_out][C_in]: box = 64 k x NT rows
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(C)};
     cuuint32_t box[2] = {BLOCK_K, static_cast<cuuint32_t>(p.NT)};
-    if ((rc = make_map(&m_w1h, W1p_hi, 2, dims, box))) return rc;
-    if ((rc = make_map(&m_w1l, W1p_lo, 2, dims, box))) return rc;
-    if ((rc = make_map(&m_w2h, W2_hi, 2, dims, box))) return rc;
-    if ((rc = make_map(&m_w2l, W2_lo, 2, dims, box))) return rc;
+    if ((rc = make_map(&m.w1h, W1p_hi, 2, dims, box))) return rc;
+    if ((rc = make_map(&m.w1l, W1p_lo, 2, dims, box))) return rc;
+    if ((rc = make_map(&m.w2h, W2_hi, 2, dims, box))) return rc;
+    if ((rc = make_map(&m.w2l, W2_lo, 2, dims, box))) return rc;
   }
-  {  // hidden activations [B*N][C]: box = 64 k x 128 pixels
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(B) * N};
+  {  // scratch [ctas*2*128][C]: loads 64 k x 128 rows, stores 32 ch (64 B) x 32 rows through SWIZZLE_64B staging
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(ws_rows)};
     cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
-    if ((rc = make_map(&m_hh, p.h_hi, 2, dims, box))) return rc;
-    if ((rc = make_map(&m_hl, p.h_lo, 2, dims, box))) return rc;
-    cuuint32_t sbox[2] = {32, 32};   // epilogue store: 32 channels (64 B) x 32 pixels, SWIZZLE_64B staging
-    if ((rc = make_map(&m_sh, p.h_hi, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if ((rc = make_map(&m_sl, p.h_lo, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map(&m.hh_ld, h_hi, 2, dims, box))) return rc;
+    if ((rc = make_map(&m.hl_ld, h_lo, 2, dims, box))) return rc;
+    cuuint32_t sbox[2] = {32, 32};
+    if ((rc = make_map(&m.hh_st, h_hi, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map(&m.hl_st, h_lo, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
-  cudaError_t e = cudaFuncSetAttribute(bg_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(bg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
-  e = cudaFuncSetAttribute(bg_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  const int grid = p.m_tiles < sl::kNumSMs ? p.m_tiles : sl::kNumSMs;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  bg_gemm_kernel<1><<<grid, Cfg<1>::THREADS, SMEM_BYTES, st>>>(m_x, m_x, m_w1h, m_w1l, m_sh, m_sl, p);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return static_cast<int>(e);
-  bg_gemm_kernel<2><<<grid, Cfg<2>::THREADS, SMEM_BYTES, st>>>(m_hh, m_hl, m_w2h, m_w2l, m_sh, m_sl, p);
+  bg_fused_kernel<<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(m, p);
   return SL_LAUNCH_RESULT();
 }

@@ -2,6 +2,7 @@
 //   reference: networks/pspnet_pop.py:106,113 (F.normalize of the prototypes),
 //              :46-52,57-63 (classifier / classifier_n), :112,118 (bg = q - sum_k p_k s_k).
 // Three tiny kernels (K <= 31, C <= 1024): total work ~ K*C^2 FMA, negligible next to one tile.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace sl {
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(128) fold_weights_kernel(const float* __restri
                                                            const float* __restrict__ W1, const float* __restrict__ W2,
                                                            float* __restrict__ W1p_t, float* __restrict__ W2_t,
                                                            uint16_t* __restrict__ W1p_hi, uint16_t* __restrict__ W1p_lo,
-                                                           uint16_t* __restrict__ W2_hi, uint16_t* __restrict__ W2_lo) {
+                                                           uint16_t* __restrict__ W2_hi, uint16_t* __restrict__ W2_lo,
+                                                           uint16_t* __restrict__ W1p_f16, uint16_t* __restrict__ W2_f16) {
   __shared__ float u[SL_MAX_CLASSES];
   const int o = blockIdx.x;
   const float* w1 = W1 + static_cast<size_t>(o) * C;
@@ -113,6 +115,11 @@ __global__ void __launch_bounds__(128) fold_weights_kernel(const float* __restri
       W2_hi[idx] = bh;
       W2_lo[idx] = f32_to_bf16_rn(b - bf16_bits_to_f32(bh));
     }
+    if (W1p_f16) {
+      const size_t idx = static_cast<size_t>(o) * C + i;
+      W1p_f16[idx] = __half_as_ushort(__float2half_rn(a));
+      W2_f16[idx] = __half_as_ushort(__float2half_rn(b));
+    }
   }
 }
 
@@ -126,7 +133,8 @@ extern "C" size_t sl_pop_prepare_ws_bytes(int K, int C) {
 extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const float* W1_fg, const float* W2_fg,
                               const float* w3_fg, const float* W1_bg, const float* W2_bg, const float* w3_bg,
                               float* s_hat, float* alpha, float* beta, float* W1p_t, float* W2_t, uint16_t* W1p_hi,
-                              uint16_t* W1p_lo, uint16_t* W2_hi, uint16_t* W2_lo, float* ws, void* stream) {
+                              uint16_t* W1p_lo, uint16_t* W2_hi, uint16_t* W2_lo, uint16_t* W1p_f16,
+                              uint16_t* W2_f16, float* ws, void* stream) {
   SL_CHECK_ARG(K >= 1 && K < SL_MAX_CLASSES && Kb >= 0 && Kb <= K);
   SL_CHECK_ARG(C >= 8 && C <= 1024 && C % 8 == 0);
   SL_CHECK_PTR(protos); SL_CHECK_PTR(W1_fg); SL_CHECK_PTR(W2_fg); SL_CHECK_PTR(w3_fg);
@@ -134,6 +142,7 @@ extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const f
   SL_CHECK_PTR(s_hat); SL_CHECK_PTR(alpha); SL_CHECK_PTR(beta); SL_CHECK_PTR(ws);
   const int n_split = (W1p_hi != nullptr) + (W1p_lo != nullptr) + (W2_hi != nullptr) + (W2_lo != nullptr);
   SL_CHECK_ARG(n_split == 0 || n_split == 4);
+  SL_CHECK_ARG((W1p_f16 != nullptr) == (W2_f16 != nullptr));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   sl::normalize_protos_kernel<<<K, 128, 0, st>>>(protos, C, s_hat);
   float* h1 = ws;                                        // [2K][C]
@@ -141,7 +150,8 @@ extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const f
   sl::mlp1_kernel<<<(C + 7) / 8, 256, 0, st>>>(s_hat, K, Kb, C, W1_fg, W1_bg, h1);
   sl::mlp2_kernel<<<(C + 7) / 8, 256, 0, st>>>(h1, K, Kb, C, W2_fg, W2_bg, h2);
   sl::mlp3_kernel<<<2 * K, 128, 0, st>>>(h2, Kb, C, w3_fg, w3_bg, alpha, beta);
-  if (W1p_t || W2_t || n_split)
-    sl::fold_weights_kernel<<<C, 128, 0, st>>>(s_hat, K, C, W1_bg, W2_bg, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo);
+  if (W1p_t || W2_t || n_split || W1p_f16)
+    sl::fold_weights_kernel<<<C, 128, 0, st>>>(s_hat, K, C, W1_bg, W2_bg, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo,
+                                               W1p_f16, W2_f16);
   return SL_LAUNCH_RESULT();
 }

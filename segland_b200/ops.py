@@ -50,7 +50,8 @@ class _Plan:
     W1p_t: torch.Tensor
     W2_t: torch.Tensor
     w3_bg: torch.Tensor
-    split: tuple | None      # (W1p_hi, W1p_lo, W2_hi, W2_lo) uint16 views of bf16
+    split: tuple | None      # (W1p_hi, W1p_lo, W2_hi, W2_lo) bf16 bit patterns
+    f16: tuple | None        # (W1p_f16, W2_f16) fp16 bit patterns
 
 
 class PopHead:
@@ -62,12 +63,19 @@ class PopHead:
     [bg, base_1..Kb, novel_1..Kn] (pspnet_pop.py:159).  In ft mode the background and novel
     channels use classifier_n, base channels use classifier (pspnet_pop.py:150-157).
 
-    bg_mode: 'tc'   tcgen05 split-bf16 tensor-core MLP (C % 64 == 0, C <= 512, N % 128 == 0)
+    bg_mode: 'tc'   tcgen05 tensor-core MLP (C % 64 == 0, C <= 512, N % 128 == 0)
              'simt' exact fp32 CUDA-core MLP (any C % 8 == 0, C <= 768)
              'auto' tc when the shape allows, else simt
+    tc_precision: 'precise' (split-bf16, 5 MMA passes, ~5e-6 of fp32; the default and the mode the
+             parity claims are made for) or 'balanced' (layer 2 in single-pass fp16, 3 passes, ~4e-4
+             relative to the tensor maximum: inside the 1e-3 logit bound, but near-tie argmax flips
+             become ~100x more frequent); see include/segland_b200.h.
     """
 
-    def __init__(self, base_emb, classifier, novel_emb=None, classifier_n=None, device=None, bg_mode='auto'):
+    TC_PRECISIONS = {'precise': 0, 'balanced': 1}
+
+    def __init__(self, base_emb, classifier, novel_emb=None, classifier_n=None, device=None, bg_mode='auto',
+                 tc_precision='precise'):
         check_device()
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
@@ -89,6 +97,9 @@ class PopHead:
         if bg_mode not in ('auto', 'tc', 'simt'):
             raise ValueError(bg_mode)
         self.bg_mode = bg_mode
+        if tc_precision not in self.TC_PRECISIONS:
+            raise ValueError(tc_precision)
+        self.tc_precision = tc_precision
         self._plan = None
         self._h1_ws = None
         self.refresh()
@@ -133,13 +144,16 @@ class PopHead:
         new = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
         want_split = self.bg_mode != 'simt' and C % 64 == 0 and 64 <= C <= 512
         split = tuple(new(C, C, dtype=torch.int16) for _ in range(4)) if want_split else None
-        plan = _Plan(new(K, C), new(K), new(K), new(C, C), new(C, C), bg[2], split)
+        f16 = tuple(new(C, C, dtype=torch.int16) for _ in range(2)) if want_split else None
+        plan = _Plan(new(K, C), new(K), new(K), new(C, C), new(C, C), bg[2], split, f16)
         sp = split if split else (None,) * 4
+        hf = f16 if f16 else (None,) * 2
         ws = new(_cabi.lib().sl_pop_prepare_ws_bytes(K, C) // 4)
         with torch.cuda.device(dev):
             call('sl_pop_prepare', ptr(protos.contiguous()), K, self.Kb, C, ptr(fg[0]), ptr(fg[1]), ptr(fg[2]),
                  ptr(bg[0]), ptr(bg[1]), ptr(bg[2]), ptr(plan.s_hat), ptr(plan.alpha), ptr(plan.beta),
-                 ptr(plan.W1p_t), ptr(plan.W2_t), ptr(sp[0]), ptr(sp[1]), ptr(sp[2]), ptr(sp[3]), ptr(ws), _stream())
+                 ptr(plan.W1p_t), ptr(plan.W2_t), ptr(sp[0]), ptr(sp[1]), ptr(sp[2]), ptr(sp[3]), ptr(hf[0]), ptr(hf[1]),
+                 ptr(ws), _stream())
         self._plan = plan
         self._ch_map = int_array([1 + k for k in range(K)])
         return self
@@ -161,7 +175,8 @@ class PopHead:
             self._h1_ws = torch.empty(need // 2, dtype=torch.int16, device=feats.device)
         p = self._plan
         call('sl_pop_bg_tc', ptr(feats), B, C, N, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
-             ptr(p.split[3]), ptr(p.w3_bg), ptr(self._h1_ws), ptr(out), out.shape[1], 0, _stream())
+             ptr(p.split[3]), ptr(p.f16[1]), ptr(p.w3_bg), self.TC_PRECISIONS[self.tc_precision],
+             ptr(self._h1_ws), ptr(out), out.shape[1], 0, _stream())
 
     def bg_simt(self, feats, out):
         B, C, h, w = feats.shape

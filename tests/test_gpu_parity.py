@@ -124,6 +124,21 @@ def test_head_tc_matches_simt_on_device(ops):
     assert_close_rel(b[:, 0].cpu(), a[:, 0].cpu(), 2e-4, 'tc vs simt bg')
 
 
+@pytest.mark.parametrize('C,Kn,hw', [(512, 0, 64), (512, 4, 32), (192, 4, 64), (64, 4, 16)])
+def test_head_tc_balanced_mode(ops, C, Kn, hw):
+    """Opt-in reduced-pass mode (layer 2 in fp16): still inside north_star's 1e-3 relative bound,
+    measured relative to the tensor maximum; the default 'precise' mode is ~100x tighter."""
+    st = synth.make_head_state(C, 7, Kn, seed=300 + C)
+    labels = synth.make_labels(1, hw * 8, hw * 8, st.n_classes, seed=C + 1, coarse=8)
+    feats = synth.make_features(labels, st, 8, seed=C + 1)
+    ref = ref_ops.ref_head(feats.float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
+    bal = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n, bg_mode='tc', tc_precision='balanced')(feats.cuda())
+    pre = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n, bg_mode='tc', tc_precision='precise')(feats.cuda())
+    assert rel_err(bal[:, 0].cpu(), ref[:, 0]) <= RTOL
+    assert rel_err(pre[:, 0].cpu(), ref[:, 0]) <= 5e-5
+    assert torch.equal(bal[:, 1:], pre[:, 1:])
+
+
 def test_head_argument_errors(ops):
     st = synth.make_head_state(64, 7, 0, seed=1)
     head = make_head(ops, st, 'simt')
