@@ -195,7 +195,8 @@ def run_ours(args, rank, world, local_rank):
     if reps > 1:                                     # make the repeats distinct bytes (not that caches care)
         noise = torch.randn(T, 1, HW_LR, HW_LR, device=dev, generator=torch.Generator(dev).manual_seed(rank))
         feats = (feats.float() + 0.05 * noise).to(torch.bfloat16).contiguous()
-    head = ops.PopHead(st.base_emb, st.cls, None, None, device=dev, bg_mode=args.bg_mode)
+    head = ops.PopHead(st.base_emb, st.cls, None, None, device=dev, bg_mode=args.bg_mode,
+                       tc_precision=args.tc_precision)
     ev = sweep.TileEvaluator(head, (TILE, TILE))
     use_tc = head._use_tc(N_PIX)
 
@@ -304,7 +305,9 @@ def run_ours(args, rank, world, local_rank):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16 features, f32 accumulate',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'tiles_per_step_per_gpu': T, 'C': C, 'feature_hw': HW_LR, 'classes': K,
-                   'mode': 'base', 'bg_path': 'tcgen05 split-bf16' if use_tc else 'fp32 CUDA cores',
+                   'mode': 'base', 'bg_path': (f'tcgen05 {args.tc_precision} ' + ('(split-bf16, 2+3 passes)' if args.tc_precision == 'precise'
+                                                                    else '(split-bf16 L1, fp16 L2, 2+1 passes)'))
+                   if use_tc else 'fp32 CUDA cores',
                    'l2_policy': f'inputs larger than L2 ({T * C * N_PIX * 2 / 1e6:.0f} MB features per step)',
                    'parallelism': f'dp{world}'},
         'kernel_ms_per_step': kern_ms,
@@ -397,6 +400,8 @@ def main():
     ap.add_argument('--e2e-tiles', type=int, default=8)
     ap.add_argument('--cpu-tiles', type=int, default=8, help='tiles in the bounded CPU-baseline sample (0 = skip)')
     ap.add_argument('--bg-mode', default='auto', choices=['auto', 'tc', 'simt'])
+    ap.add_argument('--tc-precision', default='precise', choices=['precise', 'balanced'],
+                    help="tensor-core background MLP mode; 'precise' is the parity-grade default")
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

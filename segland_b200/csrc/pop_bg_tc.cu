@@ -42,7 +42,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
-constexpr int STAGING_BYTES = EPI_WARPS * 4096;         // per warp: {hi,lo} x [32 rows][64 B]
+constexpr int STAGING_BYTES = 2 * 16384;                // per 4-warp group: {hi,lo} x [128 rows][64 B]
 constexpr int W3_BYTES = 2048;
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + W3_BYTES + BAR_BYTES;
@@ -69,20 +69,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+// L2 eviction-priority policies (the fixed createpolicy encodings CUTLASS uses as TMA::CacheHintSm90):
+// features stream through once -> evict first; weights and the hidden-layer scratch tile are re-used
+// by every CTA / re-read within microseconds -> evict last, so they are not pushed out to HBM.
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
 }
 // smem tile -> global (bulk async group); the source must be visible to the async proxy first.
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -158,7 +168,7 @@ struct Maps {           // 9 x 128 B of kernel parameter space
   CUtensorMap x;                 // features [B][C][N], box 64 px x 64 ch
   CUtensorMap w1h, w1l, w2h, w2l;  // weights [C][C], box 64 k x NT rows
   CUtensorMap hh_ld, hl_ld;      // scratch [ctas*2*128][C], box 64 k x 128 rows (SWIZZLE_128B)
-  CUtensorMap hh_st, hl_st;      // same tensors, box 32 ch x 32 rows (SWIZZLE_64B) for the epilogue stores
+  CUtensorMap hh_st, hl_st;      // same tensors, box 32 ch x 128 rows (SWIZZLE_64B) for the epilogue stores
 };
 
 __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
     tma_prefetch_desc(&maps.hl_ld); tma_prefetch_desc(&maps.hh_st); tma_prefetch_desc(&maps.hl_st);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); mbar_init(h1_bar(s), EPI_WARPS);
+      mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); mbar_init(h1_bar(s), 2);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -222,12 +232,12 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
             const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
             mbar_expect_tx(full_bar(stage), A_BYTES + b_bytes);
             if (!g2) {   // feature tile: 64 channels x 128 pixels as two 64-pixel (128-byte) column blocks
-              tma_load_3d(sa, ma, full_bar(stage), n0, kb * BLOCK_K, img);
-              tma_load_3d(sa + A_BYTES / 2, ma, full_bar(stage), n0 + 64, kb * BLOCK_K, img);
+              tma_load_3d(sa, ma, full_bar(stage), n0, kb * BLOCK_K, img, L2_EVICT_FIRST);
+              tma_load_3d(sa + A_BYTES / 2, ma, full_bar(stage), n0 + 64, kb * BLOCK_K, img, L2_EVICT_FIRST);
             } else {
-              tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, ws_row0(s));
+              tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, ws_row0(s), L2_EVICT_LAST);
             }
-            tma_load_2d(sb, mb, full_bar(stage), kb * BLOCK_K, nt * p.NT);
+            tma_load_2d(sb, mb, full_bar(stage), kb * BLOCK_K, nt * p.NT, L2_EVICT_LAST);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -291,7 +301,9 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
     const int half = (warp - 2) >> 2;             // which half of a G1 n-tile's 32-column chunks
     const int n_chunks = p.NT / 32;
     const int c_split = (n_chunks + 1) / 2;
-    const uint32_t sbuf = stage_out + static_cast<uint32_t>((warp - 2) * 4096);
+    const uint32_t sbuf = stage_out + static_cast<uint32_t>(half * 16384);   // shared by the group's 4 warps
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;                  // issues the group's TMA stores
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); };
     int acc = 0; uint32_t acc_phase = 0;
     float logit = 0.f;
     auto epi_job = [&](bool g2, int s, int nt) {
@@ -327,26 +339,27 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
               lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
             }
           }
-          // stage the 32x32 16-bit chunk (64 B per row, SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3) and
-          // hand it to TMA: the store engine writes full lines, the LSU only sees shared memory.
-          if (lane == 0) tma_store_wait_read<0>();          // the previous store has drained this buffer
-          __syncwarp();
-          const uint32_t rbase = sbuf + static_cast<uint32_t>(lane) * 64u;
-          const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+          // stage the group's 128x32 16-bit chunk (64 B per row, SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3)
+          // and hand it to TMA as ONE 8 KB store per array: the store engine writes full lines and the
+          // TMA unit sees 4x fewer descriptors than with per-warp stores.
+          if (leader) tma_store_wait_read<0>();             // the previous store has drained the buffer
+          group_sync();
+          const uint32_t rbase = sbuf + static_cast<uint32_t>(row) * 64u;
+          const uint32_t sw = static_cast<uint32_t>((row >> 1) & 3);
           if (!(p.debug & 1))
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t off16 = ((static_cast<uint32_t>(q) ^ sw) << 4);
             st_shared_v4(rbase + off16, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-            if (!p.h_f16) st_shared_v4(rbase + 2048u + off16, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            if (!p.h_f16) st_shared_v4(rbase + 8192u + off16, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
           }
           fence_async_smem();
-          __syncwarp();
-          if (lane == 0 && !(p.debug & 2)) {
+          group_sync();
+          if (leader && !(p.debug & 2)) {
             const int col = nt * p.NT + c0;
-            const int row0 = ws_row0(s) + sub * 32;
-            tma_store_2d(&maps.hh_st, sbuf, col, row0);
-            if (!p.h_f16) tma_store_2d(&maps.hl_st, sbuf + 2048u, col, row0);
+            const int row0 = ws_row0(s);
+            tma_store_2d(&maps.hh_st, sbuf, col, row0, L2_EVICT_LAST);
+            if (!p.h_f16) tma_store_2d(&maps.hl_st, sbuf + 8192u, col, row0, L2_EVICT_LAST);
             tma_store_commit();
           }
         }
@@ -366,8 +379,8 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
       if (lane == 0) mbar_arrive(tempty_bar(acc));   // one arrival per epilogue warp
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       if (!g2 && nt == p.n_tiles - 1) {
-        // scratch tile complete for this warp: wait until its bulk stores have landed, then tell the producer
-        if (lane == 0) {
+        // scratch tile complete for this group: wait until its bulk stores have landed, then tell the producer
+        if (leader) {
           tma_store_wait_all();
           fence_proxy_async_all();
           mbar_arrive(h1_bar(s & 1));
@@ -491,12 +504,12 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
     if ((rc = make_map(&m.w2h, W2_hi, 2, dims, box))) return rc;
     if ((rc = make_map(&m.w2l, W2_lo, 2, dims, box))) return rc;
   }
-  {  // scratch [ctas*2*128][C]: loads 64 k x 128 rows, stores 32 ch (64 B) x 32 rows through SWIZZLE_64B staging
+  {  // scratch [ctas*2*128][C]: loads 64 k x 128 rows, stores 32 ch (64 B) x 128 rows through SWIZZLE_64B staging
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(ws_rows)};
     cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
     if ((rc = make_map(&m.hh_ld, h_hi, 2, dims, box))) return rc;
     if ((rc = make_map(&m.hl_ld, h_lo, 2, dims, box))) return rc;
-    cuuint32_t sbox[2] = {32, 32};
+    cuuint32_t sbox[2] = {32, BLOCK_M};
     if ((rc = make_map(&m.hh_st, h_hi, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if ((rc = make_map(&m.hl_st, h_lo, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }

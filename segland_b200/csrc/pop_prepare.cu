@@ -26,22 +26,48 @@ __global__ void __launch_bounds__(128) normalize_protos_kernel(const float* __re
 // streaming both C x C matrices.  Vector v in [0, 2K): class v>>1, sign = v&1 ? -1 : +1.
 // Classes [0,Kb) use the fg weights, [Kb,K) the bg weights.
 
-// h1[v][o] = relu(+-W1x[o] . s_hat_k)        grid C/8, 256 threads (one warp per output row o)
+// One warp per output row o keeps that weight row in registers and sweeps the input vectors, which
+// the CTA stages in shared memory VCHUNK at a time (so they are read from L2 once per CTA, not once
+// per warp, and every dot product streams from conflict-free shared memory).
+constexpr int VCHUNK = 8;          // input vectors staged per pass: 8 * C * 4 B <= 32 KB at C = 1024
+constexpr int MAXC_REG = 32;       // C <= 1024 -> at most 32 weights per lane
+
+// h1[v][o] = relu(+-W1x[o] . s_hat_k)        grid C/8, 256 threads
 __global__ void __launch_bounds__(256) mlp1_kernel(const float* __restrict__ s_hat, int K, int Kb, int C,
                                                    const float* __restrict__ W1f, const float* __restrict__ W1g,
                                                    float* __restrict__ h1) {
+  extern __shared__ float xs[];     // [VCHUNK][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * 8 + warp;
-  if (o >= C) return;
-  for (int k = 0; k < K; ++k) {
-    const float* w = (k < Kb ? W1f : W1g) + static_cast<size_t>(o) * C;
-    const float* s = s_hat + static_cast<size_t>(k) * C;
-    float acc = 0.f;
-    for (int i = lane; i < C; i += 32) acc = fmaf(__ldg(w + i), __ldg(s + i), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      h1[static_cast<size_t>(2 * k) * C + o] = fmaxf(acc, 0.f);
-      h1[static_cast<size_t>(2 * k + 1) * C + o] = fmaxf(-acc, 0.f);
+  const int per_lane = (C + 31) / 32;
+  float wf[MAXC_REG], wg[MAXC_REG];
+#pragma unroll
+  for (int j = 0; j < MAXC_REG; ++j) {
+    const int i = lane + 32 * j;
+    const bool ok = j < per_lane && i < C && o < C;
+    wf[j] = ok ? __ldg(W1f + static_cast<size_t>(o) * C + i) : 0.f;
+    wg[j] = ok ? __ldg(W1g + static_cast<size_t>(o) * C + i) : 0.f;
+  }
+  for (int k0 = 0; k0 < K; k0 += VCHUNK) {
+    const int nk = min(VCHUNK, K - k0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nk * C; idx += 256) xs[idx] = s_hat[static_cast<size_t>(k0) * C + idx];
+    __syncthreads();
+    for (int kk = 0; kk < nk; ++kk) {
+      const int k = k0 + kk;
+      const bool fg = k < Kb;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXC_REG; ++j)
+        if (j < per_lane) {
+          const int i = lane + 32 * j;
+          acc = fmaf(fg ? wf[j] : wg[j], i < C ? xs[kk * C + i] : 0.f, acc);
+        }
+      acc = warp_sum(acc);
+      if (lane == 0 && o < C) {
+        h1[static_cast<size_t>(2 * k) * C + o] = fmaxf(acc, 0.f);
+        h1[static_cast<size_t>(2 * k + 1) * C + o] = fmaxf(-acc, 0.f);
+      }
     }
   }
 }
@@ -50,16 +76,37 @@ __global__ void __launch_bounds__(256) mlp1_kernel(const float* __restrict__ s_h
 __global__ void __launch_bounds__(256) mlp2_kernel(const float* __restrict__ h1, int K, int Kb, int C,
                                                    const float* __restrict__ W2f, const float* __restrict__ W2g,
                                                    float* __restrict__ h2) {
+  extern __shared__ float xs[];     // [VCHUNK][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * 8 + warp;
-  if (o >= C) return;
-  for (int v = 0; v < 2 * K; ++v) {
-    const float* w = ((v >> 1) < Kb ? W2f : W2g) + static_cast<size_t>(o) * C;
-    const float* x = h1 + static_cast<size_t>(v) * C;
-    float acc = 0.f;
-    for (int i = lane; i < C; i += 32) acc = fmaf(__ldg(w + i), x[i], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) h2[static_cast<size_t>(v) * C + o] = fmaxf(acc, 0.f);
+  const int per_lane = (C + 31) / 32;
+  float wf[MAXC_REG], wg[MAXC_REG];
+#pragma unroll
+  for (int j = 0; j < MAXC_REG; ++j) {
+    const int i = lane + 32 * j;
+    const bool ok = j < per_lane && i < C && o < C;
+    wf[j] = ok ? __ldg(W2f + static_cast<size_t>(o) * C + i) : 0.f;
+    wg[j] = ok ? __ldg(W2g + static_cast<size_t>(o) * C + i) : 0.f;
+  }
+  const int V = 2 * K;
+  for (int v0 = 0; v0 < V; v0 += VCHUNK) {
+    const int nv = min(VCHUNK, V - v0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nv * C; idx += 256) xs[idx] = h1[static_cast<size_t>(v0) * C + idx];
+    __syncthreads();
+    for (int vv = 0; vv < nv; ++vv) {
+      const int v = v0 + vv;
+      const bool fg = (v >> 1) < Kb;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXC_REG; ++j)
+        if (j < per_lane) {
+          const int i = lane + 32 * j;
+          acc = fmaf(fg ? wf[j] : wg[j], i < C ? xs[vv * C + i] : 0.f, acc);
+        }
+      acc = warp_sum(acc);
+      if (lane == 0 && o < C) h2[static_cast<size_t>(v) * C + o] = fmaxf(acc, 0.f);
+    }
   }
 }
 
@@ -147,8 +194,9 @@ extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const f
   sl::normalize_protos_kernel<<<K, 128, 0, st>>>(protos, C, s_hat);
   float* h1 = ws;                                        // [2K][C]
   float* h2 = ws + static_cast<size_t>(2) * K * C;       // [2K][C]
-  sl::mlp1_kernel<<<(C + 7) / 8, 256, 0, st>>>(s_hat, K, Kb, C, W1_fg, W1_bg, h1);
-  sl::mlp2_kernel<<<(C + 7) / 8, 256, 0, st>>>(h1, K, Kb, C, W2_fg, W2_bg, h2);
+  const size_t xs_bytes = static_cast<size_t>(sl::VCHUNK) * C * sizeof(float);
+  sl::mlp1_kernel<<<(C + 7) / 8, 256, xs_bytes, st>>>(s_hat, K, Kb, C, W1_fg, W1_bg, h1);
+  sl::mlp2_kernel<<<(C + 7) / 8, 256, xs_bytes, st>>>(h1, K, Kb, C, W2_fg, W2_bg, h2);
   sl::mlp3_kernel<<<2 * K, 128, 0, st>>>(h2, Kb, C, w3_fg, w3_bg, alpha, beta);
   if (W1p_t || W2_t || n_split || W1p_f16)
     sl::fold_weights_kernel<<<C, 128, 0, st>>>(s_hat, K, C, W1_bg, W2_bg, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo,

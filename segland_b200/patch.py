@@ -1,0 +1,102 @@
+"""Drop-in installation into an unmodified SegLand checkout.
+
+    import segland_b200.patch as slp
+    slp.patch()          # after `sys.path` contains the SegLand tree, before building models
+
+replaces, in place,
+  * `GFSS_Model.forward` of every importable `networks/*_pop.py` model: in eval mode
+    (`eval_base.py:167`, `eval_ft.py:167`, `ft_pop.py:327`, `train_base.py:331`) the head after the
+    decoder -- `orthogonal_decompose` + `classifier` / `classifier_n` + channel assembly
+    (`pspnet_pop.py:143-159`, `:171-182`) -- runs in libsegland_b200.so; backbones and decoders stay
+    stock PyTorch.  Training-mode calls (`forward_novel`, loss dicts) fall through to the reference.
+  * `utils.pyt_utils.get_confusion_matrix` and `utils.pyt_utils.intersectionAndUnionGPU`.
+The scripts (`eval_base.py`, `eval_ft.py`, `ft_pop.py`, `train_base.py`) need no edits: they look these
+names up at call time.  `unpatch()` restores the originals.
+"""
+from __future__ import annotations
+
+import importlib
+
+import torch
+
+from . import ops
+
+MODEL_MODULES = ('pspnet_pop', 'pspplus_pop', 'deeplab_pop', 'vggunet_pop', 'seghr_pop', 'swin_pop',
+                 'convnext_pop', 'lsk_pop')
+_BASE_FORWARD = ('pspnet_pop', 'pspplus_pop', 'deeplab_pop')     # ResNet backbones: backbone.base_forward(img)
+_originals = []
+
+
+def _features(model, img):
+    """The part of forward_all/forward_base before the head (`pspnet_pop.py:141-142` and siblings)."""
+    if hasattr(model, 'net') and not hasattr(model, 'decoder'):           # vggunet_pop.py
+        return model.net(img)
+    name = type(model).__module__.rsplit('.', 1)[-1]
+    feats = model.backbone.base_forward(img) if name in _BASE_FORWARD else model.backbone(img)
+    return model.decoder(feats)
+
+
+def _head_params(model):
+    ps = [model.base_emb] + list(model.classifier.parameters())
+    if getattr(model, 'is_ft', False):
+        ps += [model.novel_emb] + list(model.classifier_n.parameters())
+    return ps
+
+
+def head_for(model, **kw):
+    """The cached PopHead of a GFSS_Model, rebuilt when any head parameter was modified in place
+    (optimizer steps bump tensor._version) or re-assigned (load_state_dict copies in place too)."""
+    sig = tuple((p.data_ptr(), p._version, str(p.device)) for p in _head_params(model))
+    cached = getattr(model, '_sl_head', None)
+    if cached is None or cached[0] != sig:
+        head = ops.PopHead.from_model(model, device=model.base_emb.device, **kw)
+        object.__setattr__(model, '_sl_head', (sig, head))
+        return head
+    return cached[1]
+
+
+def _make_forward(orig_forward):
+    def forward(self, img, mask=None, img_b=None, mask_b=None):
+        wants_loss = self.criterion is not None and mask is not None
+        if self.training or (wants_loss and not self.is_ft) or not img.is_cuda:
+            return orig_forward(self, img, mask, img_b, mask_b)
+        with torch.no_grad():
+            feats = _features(self, img)
+            return head_for(self)(feats)
+    forward._sl_patched = True
+    return forward
+
+
+def patch(verbose=False):
+    """Install the B200 path into every importable reference module.  Returns the list of patched names."""
+    ops.check_device()
+    done = []
+    for name in MODEL_MODULES:
+        try:
+            mod = importlib.import_module('networks.' + name)
+        except Exception:                                              # noqa: BLE001  (missing timm etc.)
+            continue
+        cls = getattr(mod, 'GFSS_Model', None)
+        if cls is None or getattr(cls.forward, '_sl_patched', False):
+            continue
+        _originals.append((cls, 'forward', cls.forward))
+        cls.forward = _make_forward(cls.forward)
+        done.append(f'networks.{name}.GFSS_Model.forward')
+    try:
+        pu = importlib.import_module('utils.pyt_utils')
+        for fn in ('get_confusion_matrix', 'intersectionAndUnionGPU'):
+            if getattr(pu, fn, None) is not getattr(ops, fn):
+                _originals.append((pu, fn, getattr(pu, fn)))
+                setattr(pu, fn, getattr(ops, fn))
+                done.append(f'utils.pyt_utils.{fn}')
+    except Exception:                                                  # noqa: BLE001
+        pass
+    if verbose:
+        print('segland_b200.patch:', ', '.join(done) or 'nothing to patch')
+    return done
+
+
+def unpatch():
+    while _originals:
+        obj, name, val = _originals.pop()
+        setattr(obj, name, val)

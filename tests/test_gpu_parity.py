@@ -390,3 +390,74 @@ def test_full_size_properties(ops):
     lg1 = ev.head(feats[:1]).clone()
     lg2 = ev.head((feats[:1].float() * 2).to(torch.bfloat16))
     assert torch.equal(lg2, 2 * lg1)
+
+
+# ------------------------------------------------------------------------- drop-in patching
+def test_patch_installs_into_reference_shaped_modules(ops, golden):
+    """segland_b200.patch against stand-ins with the reference's module/attribute names (the real tree
+    is not on the GPU box): eval-mode forward goes through the CUDA head and matches the golden logits
+    the real GFSS_Model produced; training mode falls through to the original forward."""
+    import sys
+    import types
+    import torch.nn as nn
+    from segland_b200 import patch as slp
+
+    z = golden('head_ft_c64')
+    st = state_from_npz(z)
+    C = 64
+
+    class Backbone(nn.Module):
+        def base_forward(self, x):
+            return x
+
+    def mlp(ws):
+        seq = nn.Sequential(nn.Conv2d(C, C, 1, bias=False), nn.ReLU(inplace=True), nn.Conv2d(C, C, 1, bias=False),
+                            nn.ReLU(inplace=True), nn.Conv2d(C, 1, 1, bias=False))
+        with torch.no_grad():
+            seq[0].weight.copy_(ws[0].view(C, C, 1, 1)); seq[2].weight.copy_(ws[1].view(C, C, 1, 1))
+            seq[4].weight.copy_(ws[2].view(1, C, 1, 1))
+        return seq
+
+    class GFSS_Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone, self.decoder = Backbone(), nn.Identity()
+            self.classifier, self.classifier_n = mlp(st.cls), mlp(st.cls_n)
+            self.base_emb = nn.Parameter(st.base_emb.clone(), requires_grad=False)
+            self.novel_emb = nn.Parameter(st.novel_emb.clone())
+            self.is_ft, self.criterion, self.n_base, self.n_novel = True, None, 7, 4
+
+        def forward(self, img, mask=None, img_b=None, mask_b=None):
+            return 'reference path'
+
+    GFSS_Model.__module__ = 'networks.pspnet_pop'
+    nets, mod, utils, pu = (types.ModuleType(n) for n in ('networks', 'networks.pspnet_pop', 'utils', 'utils.pyt_utils'))
+    mod.GFSS_Model = GFSS_Model
+    pu.get_confusion_matrix = pu.intersectionAndUnionGPU = lambda *a, **k: 'reference metric'
+    saved = {k: sys.modules.get(k) for k in ('networks', 'networks.pspnet_pop', 'utils', 'utils.pyt_utils')}
+    sys.modules.update({'networks': nets, 'networks.pspnet_pop': mod, 'utils': utils, 'utils.pyt_utils': pu})
+    try:
+        done = slp.patch()
+        assert 'networks.pspnet_pop.GFSS_Model.forward' in done and 'utils.pyt_utils.get_confusion_matrix' in done
+        model = GFSS_Model().cuda().eval()
+        feats = bf16_from_bits(z['feats_bf16_bits']).cuda()
+        out = model(feats)
+        assert_close_rel(out.cpu(), torch.from_numpy(z['logits']), RTOL, 'patched forward')
+        assert model(feats.cpu()) == 'reference path'                    # CPU tensors are not ours to take
+        model.train()
+        assert model(feats) == 'reference path'                          # training falls through
+        model.eval()
+        with torch.no_grad():
+            model.novel_emb.mul_(2.0)                                    # in-place update -> head rebuilt
+        out2 = model(feats)
+        assert_close_rel(out2.cpu(), torch.from_numpy(z['logits']), RTOL, 'normalised prototypes are scale free')
+        assert pu.get_confusion_matrix is ops.get_confusion_matrix
+        slp.unpatch()
+        assert GFSS_Model().cuda().eval()(feats) == 'reference path'
+    finally:
+        slp.unpatch()
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
