@@ -48,7 +48,7 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons of one GPU during the timed region (NVML)."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -233,6 +233,7 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         step(False)
+    ev.finalize(base_classes=KB)                             # warm the (lazy) NCCL communicator as well
     ev.reset()
     barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank))
@@ -314,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
         'roofline': roofline,
         'stage_s': stage_s,
         'e2e': e2e,
-        'gpu_launches': args.steps * 6,
+        'gpu_launches': args.steps * 8,      # per step: 5 (prepare) + fg + bg + upsample/argmax/confusion
         'clocks': clocks,
         'miou_total': float(mious[2]),
     }
@@ -393,7 +394,7 @@ def run_e2e(ev, head, feats_h, labels_h, Te, steps, dev, world, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--tiles', type=int, default=32, help='distinct 1024^2 tiles per step per GPU')

@@ -93,8 +93,8 @@ SL_API int sl_pop_prepare(const float *protos, int K, int Kb, int C,
                    uint16_t *W1p_f16, uint16_t *W2_f16, float *ws, void *stream);
 
 /* K foreground logits at feature resolution (HBM-bound, CUDA cores).
- *   feat   [B,C,N] bf16 (features.flatten(2), pspnet_pop.py:148); N % 8 == 0,
- *          16-byte aligned.
+ *   feat   [B,C,N] bf16 (features.flatten(2), pspnet_pop.py:148); C % 8 == 0, C <= 512,
+ *          N % 8 == 0, 16-byte aligned.
  *   logits [B,Ktot,N] fp32; channel ch_map[k] (host array of K ints) receives class
  *          k's logit -- forward_all's order [bg, base.., novel..] (pspnet_pop.py:159)
  *          is ch_map[k] = 1 + k.
@@ -111,7 +111,7 @@ SL_API int sl_pop_bg_simt(const uint16_t *feat, int B, int C, int N,
                    float *logits, int Ktot, int ch, void *stream);
 
 /* Background logit on tcgen05 tensor cores, fp32 accumulation in TMEM.
- * C % 64 == 0, 64 <= C <= 512, N % 128 == 0; SL_EINVAL outside that range (callers use _simt).
+ * C % 32 == 0, 32 <= C <= 512, N % 128 == 0; SL_EINVAL outside that range (callers use _simt).
  *   precision  SL_TC_PRECISE  split-bf16 operands, 2 + 3 MMA passes: ~5e-6 of the fp32 reference.
  *              SL_TC_BALANCED layer 1 split-bf16 (2 passes), layer 2 single-pass fp16 (3 passes):
  *                             ~3e-4 relative to the tensor maximum.  Needs W2_f16.

@@ -23,10 +23,9 @@
 // TMEM (2 x 256 columns), so the epilogue of one job overlaps the MMAs of the next.  Operands arrive
 // by TMA (SWIZZLE_128B) through a 4-stage mbarrier ring: 16 KB (A) + up to 32 KB (B) per stage; G1's
 // epilogue leaves through SWIZZLE_64B shared-memory staging and TMA bulk stores.
-#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstdlib>
-#include "common.cuh"
+#include "tma.cuh"
 
 namespace sl {
 namespace tc {
@@ -48,67 +47,7 @@ constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + W3_BYTES + BAR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-// L2 eviction-priority policies (the fixed createpolicy encodings CUTLASS uses as TMA::CacheHintSm90):
-// features stream through once -> evict first; weights and the hidden-layer scratch tile are re-used
-// by every CTA / re-read within microseconds -> evict last, so they are not pushed out to HBM.
-constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
-constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-      "[%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-      "[%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
-}
-// smem tile -> global (bulk async group); the source must be visible to the async proxy first.
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t policy) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-// full completion (writes performed), not just "source read"
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
+// (mbarrier / TMA wrappers and make_map live in tma.cuh)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -189,7 +128,7 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
   auto h1_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = p.C / BLOCK_K;
+  const int kblocks = (p.C + BLOCK_K - 1) / BLOCK_K;   // a partial last k-block is zero-filled by TMA (OOB)
   const uint32_t b_bytes = static_cast<uint32_t>(p.NT) * BLOCK_K * 2;
   const int n_my = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   auto tile_of = [&](int s) { return static_cast<int>(blockIdx.x) + s * static_cast<int>(gridDim.x); };
@@ -409,39 +348,6 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
   }
 }
 
-// ------------------------------------------------------------------ host: tensor maps
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;           // benign race: every thread resolves the same pointer
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
-// bf16 tensor of `rank` dims (innermost first), 128-byte swizzled box.
-static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint32_t* box,
-                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return static_cast<int>(cudaErrorNotSupported);
-  cuuint64_t strides[2];
-  strides[0] = dims[0] * 2;
-  if (rank == 3) strides[1] = dims[0] * dims[1] * 2;
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : static_cast<int>(cudaErrorInvalidValue);
-}
-
 }  // namespace tc
 }  // namespace sl
 
@@ -463,7 +369,7 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
   if (precision == SL_TC_PRECISE) { SL_CHECK_PTR(W2_hi); SL_CHECK_PTR(W2_lo); } else { SL_CHECK_PTR(W2_f16); }
   // pointers the chosen mode does not read alias a valid buffer so every tensor map stays well formed
   if (precision != SL_TC_PRECISE) { W2_hi = W2_f16; W2_lo = W2_f16; }
-  SL_CHECK_ARG(B >= 1 && C >= 64 && C <= 512 && C % 64 == 0 && N >= 128 && N % 128 == 0);
+  SL_CHECK_ARG(B >= 1 && C >= 32 && C <= 512 && C % 32 == 0 && N >= 128 && N % 128 == 0);
   SL_CHECK_ARG(Ktot >= 1 && Ktot <= SL_MAX_CLASSES && ch >= 0 && ch < Ktot);
   SL_CHECK_ARG(static_cast<long long>(B) * N / BLOCK_M < (1ll << 30));
   SL_CHECK_ALIGN(feat, 16); SL_CHECK_ALIGN(h1_ws, 128);
@@ -471,7 +377,11 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
 
   Params p;
   p.C = C;
-  p.NT = C <= MAX_NT ? C : C / 2;
+  // n-tile = the largest divisor of C that is a multiple of 32 (epilogue chunk) and fits one TMEM buffer:
+  // 512 -> 256, 480 -> 160, 384 -> 192, 192 -> 192, 96 -> 96
+  p.NT = 32;
+  for (int nt = 32; nt <= MAX_NT && nt <= C; nt += 32)
+    if (C % nt == 0) p.NT = nt;
   p.n_tiles = C / p.NT;
   p.m_tiles = static_cast<int>(static_cast<long long>(B) * N / BLOCK_M);
   p.tiles_per_image = N / BLOCK_M;

@@ -63,7 +63,7 @@ class PopHead:
     [bg, base_1..Kb, novel_1..Kn] (pspnet_pop.py:159).  In ft mode the background and novel
     channels use classifier_n, base channels use classifier (pspnet_pop.py:150-157).
 
-    bg_mode: 'tc'   tcgen05 tensor-core MLP (C % 64 == 0, C <= 512, N % 128 == 0)
+    bg_mode: 'tc'   tcgen05 tensor-core MLP (C % 32 == 0, C <= 512, N % 128 == 0)
              'simt' exact fp32 CUDA-core MLP (any C % 8 == 0, C <= 768)
              'auto' tc when the shape allows, else simt
     tc_precision: 'precise' (split-bf16, 5 MMA passes, ~5e-6 of fp32; the default and the mode the
@@ -142,7 +142,7 @@ class PopHead:
         fg = self.cls
         bg = self.cls_n if self.cls_n is not None else self.cls
         new = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
-        want_split = self.bg_mode != 'simt' and C % 64 == 0 and 64 <= C <= 512
+        want_split = self.bg_mode != 'simt' and C % 32 == 0 and 32 <= C <= 512
         split = tuple(new(C, C, dtype=torch.int16) for _ in range(4)) if want_split else None
         f16 = tuple(new(C, C, dtype=torch.int16) for _ in range(2)) if want_split else None
         plan = _Plan(new(K, C), new(K), new(K), new(C, C), new(C, C), bg[2], split, f16)
@@ -163,7 +163,7 @@ class PopHead:
             return False
         ok = self._plan.split is not None and N % 128 == 0
         if self.bg_mode == 'tc' and not ok:
-            raise ValueError(f'bg_mode="tc" needs C % 64 == 0, C <= 512, N % 128 == 0 (C={self.C}, N={N})')
+            raise ValueError(f'bg_mode="tc" needs C % 32 == 0, C <= 512, N % 128 == 0 (C={self.C}, N={N})')
         return ok
 
     def bg_tc(self, feats, out):

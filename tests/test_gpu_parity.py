@@ -32,7 +32,7 @@ def make_head(ops, st, bg_mode):
 
 
 def tc_ok(C, N):
-    return C % 64 == 0 and 64 <= C <= 512 and N % 128 == 0
+    return C % 32 == 0 and 32 <= C <= 512 and N % 128 == 0
 
 
 # ------------------------------------------------------------------------------------ head
@@ -72,7 +72,8 @@ def test_head_vs_golden(ops, golden, name, bg_mode):
 @pytest.mark.parametrize('mode,C,Kn,hw,bg_mode', [
     ('base', 512, 0, 64, 'simt'), ('ft', 512, 4, 64, 'simt'), ('base', 512, 0, 64, 'tc'), ('ft', 512, 4, 64, 'tc'),
     ('ft', 192, 4, 64, 'tc'), ('ft', 96, 4, 32, 'simt'), ('ft', 480, 4, 16, 'simt'), ('ft', 256, 4, 32, 'tc'),
-    ('ft', 128, 4, 32, 'tc')])
+    ('ft', 128, 4, 32, 'tc'), ('ft', 96, 4, 32, 'tc'), ('ft', 480, 4, 16, 'tc'), ('base', 320, 0, 16, 'tc'),
+    ('ft', 32, 4, 16, 'tc'), ('ft', 448, 4, 16, 'tc'), ('base', 64, 0, 32, 'tc')])
 def test_head_vs_oracle_seeded(ops, mode, C, Kn, hw, bg_mode):
     """Seeded synthetic tiles at model geometries the golden files do not cover."""
     if bg_mode == 'tc' and not tc_ok(C, hw * hw):
