@@ -9,11 +9,13 @@
 // which lands within ~5e-6 of the fp32 reference.
 //
 // One persistent, warp-specialised kernel (sm_100a) runs both layers.  A CTA owns 128-pixel tiles
-// t_0, t_1, ... and walks the job list
-//     G1(t_0) | G1(t_1) G2(t_0) | G1(t_2) G2(t_1) | ... | G2(t_last)
-// where G1(t) = relu(X_t W1'^T) split into bf16 hi/lo and written to a per-CTA, two-slot scratch tile
-// (256 KB per slot: it never leaves L2), and G2(t) = w3 . relu(H1_t W2^T).  Running G1 one tile ahead
-// hides the store -> load turnaround of the scratch tile behind a full layer-1 tile of MMAs.
+// t_0, t_1, ... and for each runs the jobs  G1(t, n-tile 0..) then G2(t, n-tile 0..)  where
+// G1 = relu(X_t W1'^T) split into bf16 hi/lo and written to a per-CTA scratch tile (256 KB; 38.8 MB
+// for the whole grid, which stays L2-resident -- a two-slot, one-tile-ahead variant was measured
+// first and spilled 0.9 GB per step to HBM), and G2 = w3 . relu(H1_t W2^T).  The store -> load
+// turnaround of the scratch tile is hidden by readiness barriers per layer-1 n-tile: layer 2 walks its
+// k-blocks in the order layer 1 produced them (k-block major, passes inner), so it starts on the
+// first n-tile's columns while the epilogue of the last one is still draining.
 //   G1: A = feature tile straight from the NCHW tensor (MN-major UMMA operand, pixels contiguous).
 //   G2: A = the scratch tile (K-major); the epilogue reduces over channels in registers; a CTA owns
 //       every n-tile of its pixel tile, so no atomics.
@@ -43,6 +45,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int STAGING_BYTES = 2 * 16384;                // per 4-warp group: {hi,lo} x [128 rows][64 B]
 constexpr int W3_BYTES = 2048;
+constexpr int MAX_N_TILES = 16;          // C / 32 at C = 512
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + W3_BYTES + BAR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
@@ -106,7 +109,7 @@ struct Params {
 struct Maps {           // 9 x 128 B of kernel parameter space
   CUtensorMap x;                 // features [B][C][N], box 64 px x 64 ch
   CUtensorMap w1h, w1l, w2h, w2l;  // weights [C][C], box 64 k x NT rows
-  CUtensorMap hh_ld, hl_ld;      // scratch [ctas*2*128][C], box 64 k x 128 rows (SWIZZLE_128B)
+  CUtensorMap hh_ld, hl_ld;      // scratch [ctas*128][C], box 64 k x 128 rows (SWIZZLE_128B)
   CUtensorMap hh_st, hl_st;      // same tensors, box 32 ch x 128 rows (SWIZZLE_64B) for the epilogue stores
 };
 
@@ -117,9 +120,9 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
   const uint32_t stage_out = base + STAGES * STAGE_BYTES;                // G1 store staging
   float* w3s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES);   // [512]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES + W3_BYTES);
-  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, [2S+4,2S+6) h1_full; then the
-  // TMEM base slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, [2S+4,2S+4+16) h1_ready per
+  // layer-1 n-tile; then the TMEM base slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + MAX_N_TILES);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
@@ -132,16 +135,17 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
   const uint32_t b_bytes = static_cast<uint32_t>(p.NT) * BLOCK_K * 2;
   const int n_my = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   auto tile_of = [&](int s) { return static_cast<int>(blockIdx.x) + s * static_cast<int>(gridDim.x); };
-  auto ws_row0 = [&](int s) { return (static_cast<int>(blockIdx.x) * 2 + (s & 1)) * BLOCK_M; };
+  const int ws_row0 = static_cast<int>(blockIdx.x) * BLOCK_M;     // this CTA's scratch tile
+  // last layer-1 n-tile whose columns k-block kb of layer 2 reads
+  auto dep_of_kb = [&](int kb) { return min(p.n_tiles - 1, (kb * BLOCK_K + BLOCK_K - 1) / p.NT); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.x); tma_prefetch_desc(&maps.w1h); tma_prefetch_desc(&maps.w1l);
     tma_prefetch_desc(&maps.w2h); tma_prefetch_desc(&maps.w2l); tma_prefetch_desc(&maps.hh_ld);
     tma_prefetch_desc(&maps.hl_ld); tma_prefetch_desc(&maps.hh_st); tma_prefetch_desc(&maps.hl_st);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); mbar_init(h1_bar(s), 2);
-    }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
+    for (int s = 0; s < MAX_N_TILES; ++s) mbar_init(h1_bar(s), 2);      // one arrival per epilogue group
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -159,36 +163,45 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      auto load_job = [&](bool g2, int s, int nt) {
-        const int passes = g2 ? (p.h_f16 ? 1 : 3) : p.l1_passes;
+      auto stage_wait = [&]() {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), A_BYTES + b_bytes);
+      };
+      auto stage_next = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1u; } };
+      for (int s = 0; s < n_my; ++s) {
         const int mt = tile_of(s);
         const int img = mt / p.tiles_per_image, n0 = (mt - img * p.tiles_per_image) * BLOCK_M;
-        for (int pass = 0; pass < passes; ++pass) {
-          const CUtensorMap* ma = g2 ? (pass == 1 ? &maps.hl_ld : &maps.hh_ld) : &maps.x;
-          const CUtensorMap* mb = g2 ? (pass == 2 ? &maps.w2l : &maps.w2h) : (pass == 1 ? &maps.w1l : &maps.w1h);
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-            mbar_expect_tx(full_bar(stage), A_BYTES + b_bytes);
-            if (!g2) {   // feature tile: 64 channels x 128 pixels as two 64-pixel (128-byte) column blocks
-              tma_load_3d(sa, ma, full_bar(stage), n0, kb * BLOCK_K, img, L2_EVICT_FIRST);
-              tma_load_3d(sa + A_BYTES / 2, ma, full_bar(stage), n0 + 64, kb * BLOCK_K, img, L2_EVICT_FIRST);
-            } else {
-              tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, ws_row0(s), L2_EVICT_LAST);
+        // ---- layer 1: passes outer, k-blocks inner
+        for (int nt = 0; nt < p.n_tiles; ++nt)
+          for (int pass = 0; pass < p.l1_passes; ++pass)
+            for (int kb = 0; kb < kblocks; ++kb) {
+              stage_wait();
+              const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+              // feature tile: 64 channels x 128 pixels as two 64-pixel (128-byte) column blocks
+              tma_load_3d(sa, &maps.x, full_bar(stage), n0, kb * BLOCK_K, img, L2_EVICT_FIRST);
+              tma_load_3d(sa + A_BYTES / 2, &maps.x, full_bar(stage), n0 + 64, kb * BLOCK_K, img, L2_EVICT_FIRST);
+              tma_load_2d(sb, pass == 1 ? &maps.w1l : &maps.w1h, full_bar(stage), kb * BLOCK_K, nt * p.NT, L2_EVICT_LAST);
+              stage_next();
             }
-            tma_load_2d(sb, mb, full_bar(stage), kb * BLOCK_K, nt * p.NT, L2_EVICT_LAST);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        // ---- layer 2: k-blocks outer (in the order layer 1 produced their columns), passes inner
+        const int l2_passes = p.h_f16 ? 1 : 3;
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
+          int ready = -1;                                      // layer-1 n-tiles known to have landed
+          for (int kb = 0; kb < kblocks; ++kb) {
+            if (nt == 0)
+              for (const int need = dep_of_kb(kb); ready < need;) {
+                ++ready;
+                mbar_wait(h1_bar(ready), static_cast<uint32_t>(s & 1));
+                fence_proxy_async_all();
+              }
+            for (int pass = 0; pass < l2_passes; ++pass) {
+              stage_wait();
+              const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+              tma_load_2d(sa, pass == 1 ? &maps.hl_ld : &maps.hh_ld, full_bar(stage), kb * BLOCK_K, ws_row0, L2_EVICT_LAST);
+              tma_load_2d(sb, pass == 2 ? &maps.w2l : &maps.w2h, full_bar(stage), kb * BLOCK_K, nt * p.NT, L2_EVICT_LAST);
+              stage_next();
+            }
           }
-        }
-      };
-      for (int s = 0; s <= n_my; ++s) {
-        if (s < n_my)
-          for (int nt = 0; nt < p.n_tiles; ++nt) load_job(false, s, nt);
-        if (s >= 1) {
-          // the scratch tile of t_{s-1} is complete once all 8 epilogue warps have drained their stores
-          mbar_wait(h1_bar((s - 1) & 1), static_cast<uint32_t>(((s - 1) >> 1) & 1));
-          fence_proxy_async_all();
-          for (int nt = 0; nt < p.n_tiles; ++nt) load_job(true, s - 1, nt);
         }
       }
     }
@@ -226,11 +239,9 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
         tc_commit(tfull_bar(acc));              // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       };
-      for (int s = 0; s <= n_my; ++s) {
-        if (s < n_my)
-          for (int nt = 0; nt < p.n_tiles; ++nt) mma_job(false);
-        if (s >= 1)
-          for (int nt = 0; nt < p.n_tiles; ++nt) mma_job(true);
+      for (int s = 0; s < n_my; ++s) {
+        for (int nt = 0; nt < p.n_tiles; ++nt) mma_job(false);
+        for (int nt = 0; nt < p.n_tiles; ++nt) mma_job(true);
       }
     }
   } else {
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
           group_sync();
           if (leader && !(p.debug & 2)) {
             const int col = nt * p.NT + c0;
-            const int row0 = ws_row0(s);
+            const int row0 = ws_row0;
             tma_store_2d(&maps.hh_st, sbuf, col, row0, L2_EVICT_LAST);
             if (!p.h_f16) tma_store_2d(&maps.hl_st, sbuf + 8192u, col, row0, L2_EVICT_LAST);
             tma_store_commit();
@@ -317,12 +328,12 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));   // one arrival per epilogue warp
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      if (!g2 && nt == p.n_tiles - 1) {
-        // scratch tile complete for this group: wait until its bulk stores have landed, then tell the producer
+      if (!g2) {
+        // this group's share of layer-1 n-tile nt: wait until its bulk stores have landed, then tell the producer
         if (leader) {
           tma_store_wait_all();
           fence_proxy_async_all();
-          mbar_arrive(h1_bar(s & 1));
+          mbar_arrive(h1_bar(nt));
         }
         __syncwarp();
       }
@@ -333,11 +344,9 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
         p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
       }
     };
-    for (int s = 0; s <= n_my; ++s) {
-      if (s < n_my)
-        for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(false, s, nt);
-      if (s >= 1)
-        for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(true, s - 1, nt);
+    for (int s = 0; s < n_my; ++s) {
+      for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(false, s, nt);
+      for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(true, s, nt);
     }
   }
   tc_fence_before();
@@ -353,8 +362,8 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
 
 extern "C" size_t sl_pop_bg_tc_ws_bytes(int B, int C, int N) {
   if (B < 1 || C < 1 || N < 1) return 0;
-  // per CTA: 2 slots x 128 rows x C channels x {hi, lo} bf16; sized for a full grid of 148 CTAs
-  return static_cast<size_t>(sl::kNumSMs) * 2 * sl::tc::BLOCK_M * C * 2 * sizeof(uint16_t);
+  // per CTA: 128 rows x C channels x {hi, lo} bf16; sized for a full grid of 148 CTAs
+  return static_cast<size_t>(sl::kNumSMs) * sl::tc::BLOCK_M * C * 2 * sizeof(uint16_t);
 }
 
 extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uint16_t* W1p_hi, const uint16_t* W1p_lo,
@@ -395,7 +404,7 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
     p.debug = dbg ? atoi(dbg) : 0;
   }
   const int grid = p.m_tiles < sl::kNumSMs ? p.m_tiles : sl::kNumSMs;
-  const size_t ws_rows = static_cast<size_t>(sl::kNumSMs) * 2 * BLOCK_M;
+  const size_t ws_rows = static_cast<size_t>(sl::kNumSMs) * BLOCK_M;
   uint16_t* h_hi = h1_ws;
   uint16_t* h_lo = h1_ws + ws_rows * C;
 
@@ -414,7 +423,7 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
     if ((rc = make_map(&m.w2h, W2_hi, 2, dims, box))) return rc;
     if ((rc = make_map(&m.w2l, W2_lo, 2, dims, box))) return rc;
   }
-  {  // scratch [ctas*2*128][C]: loads 64 k x 128 rows, stores 32 ch (64 B) x 128 rows through SWIZZLE_64B staging
+  {  // scratch [ctas*128][C]: loads 64 k x 128 rows, stores 32 ch (64 B) x 128 rows through SWIZZLE_64B staging
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(ws_rows)};
     cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
     if ((rc = make_map(&m.hh_ld, h_hi, 2, dims, box))) return rc;
