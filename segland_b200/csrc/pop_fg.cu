@@ -22,10 +22,8 @@ struct ChMap { int ch[SL_MAX_CLASSES]; };
 
 constexpr int FG_WARPS = 16;
 constexpr int FG_THREADS = FG_WARPS * 32;
-constexpr int FG_STAGES = 3;
 constexpr int FG_CB = 8;                       // channels per stage
-constexpr int FG_PX = 256;                     // pixels per item (8 per lane)
-constexpr int FG_STAGE_BYTES = FG_CB * FG_PX * 2;
+constexpr int FG_RING_BYTES = 12288;           // per-warp ring: 3 x 4 KB (8 px/lane) or 6 x 2 KB (4 px/lane)
 
 // d = a * b + d on two packed fp32 lanes (sm_100 FFMA2)
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
@@ -34,17 +32,22 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
       : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
 }
 
-template <int KC>  // classes handled by this launch (1..12)
+// KC: classes handled by this launch (1..12).  PXL: pixels per lane -- 8 (items of 256 pixels, 128-bit
+// shared loads) while the KC x 8 accumulators fit the 128-register budget of a 512-thread CTA, else 4.
+template <int KC, int PXL>
 __global__ void __launch_bounds__(FG_THREADS, 1)
 pop_fg_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N, const float* __restrict__ s_hat,
               const float* __restrict__ alpha, const float* __restrict__ beta, int K, int k_base,
               float* __restrict__ logits, int Ktot, ChMap map) {
   constexpr int KP = (KC + 3) & ~3;            // prototype row padded for 128-bit shared loads
+  constexpr int FG_PX = 32 * PXL;              // pixels per item
+  constexpr int FG_STAGE_BYTES = FG_CB * FG_PX * 2;
+  constexpr int FG_STAGES = FG_RING_BYTES / FG_STAGE_BYTES;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  // [ring: FG_WARPS x FG_STAGES x 4 KB][st: Cpad x KP fp32][barriers: FG_WARPS x FG_STAGES]
+  // [ring: FG_WARPS x 12 KB][st: Cpad x KP fp32][barriers: FG_WARPS x 8]
   const int Cpad = (C + FG_CB - 1) / FG_CB * FG_CB;
   uint8_t* ring = smem_raw;
-  float* st = reinterpret_cast<float*>(smem_raw + FG_WARPS * FG_STAGES * FG_STAGE_BYTES);
+  float* st = reinterpret_cast<float*>(smem_raw + FG_WARPS * FG_RING_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(st + Cpad * KP);
   __shared__ int ch_of[SL_MAX_CLASSES];
   __shared__ float alpha_s[SL_MAX_CLASSES], beta_s[SL_MAX_CLASSES];
@@ -62,8 +65,8 @@ pop_fg_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N, co
     const int c = idx / KP, k = idx - c * KP;
     st[idx] = (c < C && k < KC && k_base + k < K) ? s_hat[static_cast<size_t>(k_base + k) * C + c] : 0.f;
   }
-  const uint32_t my_ring = tc::smem_u32(ring) + static_cast<uint32_t>(warp * FG_STAGES * FG_STAGE_BYTES);
-  const uint32_t my_bars = tc::smem_u32(bars) + static_cast<uint32_t>(warp * FG_STAGES * 8);
+  const uint32_t my_ring = tc::smem_u32(ring) + static_cast<uint32_t>(warp * FG_RING_BYTES);
+  const uint32_t my_bars = tc::smem_u32(bars) + static_cast<uint32_t>(warp * 8 * 8);
   if (lane == 0) {
     for (int s = 0; s < FG_STAGES; ++s) tc::mbar_init(my_bars + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -78,7 +81,7 @@ pop_fg_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N, co
   const long long first = static_cast<long long>(blockIdx.x) + static_cast<long long>(warp) * gridDim.x;
   const long long stride = static_cast<long long>(gridDim.x) * FG_WARPS;
   uint32_t phase_bits = 0;                                     // bit s = parity to wait for on stage s
-  const uint8_t* my_ring_ptr = ring + warp * FG_STAGES * FG_STAGE_BYTES;
+  const uint8_t* my_ring_ptr = ring + warp * FG_RING_BYTES;
 
   for (long long item = first; item < n_items; item += stride) {
     const int b = static_cast<int>(item / items_per_image);
@@ -92,11 +95,11 @@ pop_fg_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N, co
     if (lane == 0)
       for (int cb = 0; cb < FG_STAGES - 1 && cb < n_cb; ++cb) issue(cb);
 
-    float2 acc[KC][4];
+    float2 acc[KC][PXL / 2];
 #pragma unroll
     for (int k = 0; k < KC; ++k)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[k][j] = make_float2(0.f, 0.f);
+      for (int j = 0; j < PXL / 2; ++j) acc[k][j] = make_float2(0.f, 0.f);
 
     for (int cb = 0; cb < n_cb; ++cb) {
       const int s = cb % FG_STAGES;
@@ -104,12 +107,18 @@ pop_fg_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N, co
       if (lane == 0 && cb + FG_STAGES - 1 < n_cb) issue(cb + FG_STAGES - 1);
       tc::mbar_wait(my_bars + 8u * s, (phase_bits >> s) & 1u);
       phase_bits ^= 1u << s;
-      const uint4* src = reinterpret_cast<const uint4*>(my_ring_ptr + s * FG_STAGE_BYTES) + lane;
+      const uint8_t* src = my_ring_ptr + s * FG_STAGE_BYTES + lane * (PXL * 2);
 #pragma unroll
       for (int cc = 0; cc < FG_CB; ++cc) {
-        const uint4 v = src[cc * (FG_PX * 2 / 16)];
-        const float2 x[4] = {make_float2(bf16lo(v.x), bf16hi(v.x)), make_float2(bf16lo(v.y), bf16hi(v.y)),
-                             make_float2(bf16lo(v.z), bf16hi(v.z)), make_float2(bf16lo(v.w), bf16hi(v.w))};
+        float2 x[PXL / 2];
+        if constexpr (PXL == 8) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + cc * (FG_PX * 2));
+          x[0] = make_float2(bf16lo(v.x), bf16hi(v.x)); x[1] = make_float2(bf16lo(v.y), bf16hi(v.y));
+          x[2] = make_float2(bf16lo(v.z), bf16hi(v.z)); x[3] = make_float2(bf16lo(v.w), bf16hi(v.w));
+        } else {
+          const uint2 v = *reinterpret_cast<const uint2*>(src + cc * (FG_PX * 2));
+          x[0] = make_float2(bf16lo(v.x), bf16hi(v.x)); x[1] = make_float2(bf16lo(v.y), bf16hi(v.y));
+        }
         const float4* srow = reinterpret_cast<const float4*>(st + (cb * FG_CB + cc) * KP);
 #pragma unroll
         for (int k4 = 0; k4 < KP / 4; ++k4) {
@@ -120,7 +129,7 @@ pop_fg_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N, co
             if (4 * k4 + kk < KC) {
               const float2 s2 = make_float2(sv[kk], sv[kk]);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) ffma2(acc[4 * k4 + kk][j], s2, x[j]);
+              for (int j = 0; j < PXL / 2; ++j) ffma2(acc[4 * k4 + kk][j], s2, x[j]);
             }
           }
         }
@@ -128,38 +137,39 @@ pop_fg_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N, co
       __syncwarp();                                            // stage s may be overwritten from here on
     }
 
-    const int n = n0 + lane * 8;
-    if (n < N) {                                               // N % 8 == 0: all 8 pixels or none
+    const int n = n0 + lane * PXL;
+    if (n < N) {                                               // N % 8 == 0: all PXL pixels or none
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
         const int kk = k_base + k;
         if (kk < K) {
           const float a = alpha_s[kk], bt = beta_s[kk];
-          float o[8];
+          float o[PXL];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < PXL / 2; ++j) {
             const float p0 = acc[k][j].x, p1 = acc[k][j].y;
             o[2 * j] = p0 >= 0.f ? p0 * a : -p0 * bt;
             o[2 * j + 1] = p1 >= 0.f ? p1 * a : -p1 * bt;
           }
           float4* dst = reinterpret_cast<float4*>(logits + (static_cast<size_t>(b) * Ktot + ch_of[kk]) * N + n);
           dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          if constexpr (PXL == 8) dst[1] = make_float4(o[4], o[5], o[6], o[7]);
         }
       }
     }
   }
 }
 
-template <int KC>
+template <int KC, int PXL>
 static int launch_fg(const CUtensorMap& map_x, int B, int C, int N, const float* s_hat, const float* alpha,
                      const float* beta, int K, int k_base, float* logits, int Ktot, const ChMap& map,
                      cudaStream_t st) {
   constexpr int KP = (KC + 3) & ~3;
   const int Cpad = (C + FG_CB - 1) / FG_CB * FG_CB;
-  const size_t smem = static_cast<size_t>(FG_WARPS) * FG_STAGES * FG_STAGE_BYTES + static_cast<size_t>(Cpad) * KP * 4 +
-                      static_cast<size_t>(FG_WARPS) * FG_STAGES * 8;
-  auto kern = pop_fg_kernel<KC>;
+  const size_t smem = static_cast<size_t>(FG_WARPS) * FG_RING_BYTES + static_cast<size_t>(Cpad) * KP * 4 +
+                      static_cast<size_t>(FG_WARPS) * 8 * 8;
+  auto kern = pop_fg_kernel<KC, PXL>;
+  constexpr int FG_PX = 32 * PXL;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const long long items = static_cast<long long>(B) * ((N + FG_PX - 1) / FG_PX);
@@ -184,22 +194,23 @@ extern "C" int sl_pop_fg_lowres(const uint16_t* feat, int B, int C, int N, const
     SL_CHECK_ARG(ch_map_host[k] >= 0 && ch_map_host[k] < Ktot);
     map.ch[k] = ch_map_host[k];
   }
-  CUtensorMap map_x;   // features [B][C][N] bf16: box = 256 pixels x 8 channels, no swizzle (rows are read linearly)
-  {
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(B)};
-    cuuint32_t box[3] = {sl::FG_PX, sl::FG_CB, 1};
-    const int rc = sl::tc::make_map(&map_x, feat, 3, dims, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc) return rc;
-  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // Up to 12 classes per pass keep the accumulators in registers; more classes take extra passes.
   for (int k_base = 0; k_base < K; k_base += 12) {
     const int kc = (K - k_base) < 12 ? (K - k_base) : 12;
+    const int pxl = kc <= 8 ? 8 : 4;
+    CUtensorMap map_x;   // features [B][C][N] bf16: box = 32*pxl pixels x 8 channels, no swizzle (rows are read linearly)
+    {
+      cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(B)};
+      cuuint32_t box[3] = {static_cast<cuuint32_t>(32 * pxl), sl::FG_CB, 1};
+      const int rcm = sl::tc::make_map(&map_x, feat, 3, dims, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rcm) return rcm;
+    }
     int rc = SL_EINVAL;
-#define SL_FG_CASE(KC) case KC: rc = sl::launch_fg<KC>(map_x, B, C, N, s_hat, alpha, beta, K, k_base, logits, Ktot, map, st); break
+#define SL_FG_CASE(KC, PXL) case KC: rc = sl::launch_fg<KC, PXL>(map_x, B, C, N, s_hat, alpha, beta, K, k_base, logits, Ktot, map, st); break
     switch (kc) {
-      SL_FG_CASE(1); SL_FG_CASE(2); SL_FG_CASE(3); SL_FG_CASE(4); SL_FG_CASE(5); SL_FG_CASE(6);
-      SL_FG_CASE(7); SL_FG_CASE(8); SL_FG_CASE(9); SL_FG_CASE(10); SL_FG_CASE(11); SL_FG_CASE(12);
+      SL_FG_CASE(1, 8); SL_FG_CASE(2, 8); SL_FG_CASE(3, 8); SL_FG_CASE(4, 8); SL_FG_CASE(5, 8); SL_FG_CASE(6, 8);
+      SL_FG_CASE(7, 8); SL_FG_CASE(8, 8); SL_FG_CASE(9, 4); SL_FG_CASE(10, 4); SL_FG_CASE(11, 4); SL_FG_CASE(12, 4);
     }
 #undef SL_FG_CASE
     if (rc != 0) return rc;

@@ -181,6 +181,20 @@ __device__ __forceinline__ void hist_add_grouped(unsigned int* hist, int bin, un
   if ((threadIdx.x & 31) == (__ffs(peers) - 1) && total) atomicAdd(&hist[bin], total);
 }
 
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
+        "l"(reinterpret_cast<const unsigned long long&>(c)));
+  return d;
+}
+
 template <int THREADS, bool EXTRA>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8) upsample_rows_kernel(
     const float* __restrict__ logits_lr, int K, int h, int w, int H, int W, int rows_per_band, float sy, float sx,
@@ -232,14 +246,26 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8) upsample_rows
   };
 
   size_t pix = (static_cast<size_t>(b) * H + y_begin) * W + x0;
-  // labels are fetched one row ahead so the load latency hides behind a whole row of arithmetic
-  uchar4 l4_next = make_uchar4(0, 0, 0, 0);
-  if (do_cm && col_ok && y_begin < y_end) l4_next = *reinterpret_cast<const uchar4*>(label + pix);
-  for (int y = y_begin; y < y_end; ++y, pix += W) {             // uniform trip count across the block
+  // labels are fetched four rows ahead so the load latency hides behind several rows of arithmetic
+  uchar4 lq0 = make_uchar4(0, 0, 0, 0), lq1 = lq0, lq2 = lq0, lq3 = lq0;
+  if (do_cm && col_ok) {
+    const uint8_t* lp = label + pix;
+    if (y_begin + 0 < y_end) lq0 = *reinterpret_cast<const uchar4*>(lp);
+    if (y_begin + 1 < y_end) lq1 = *reinterpret_cast<const uchar4*>(lp + W);
+    if (y_begin + 2 < y_end) lq2 = *reinterpret_cast<const uchar4*>(lp + 2 * static_cast<size_t>(W));
+    if (y_begin + 3 < y_end) lq3 = *reinterpret_cast<const uchar4*>(lp + 3 * static_cast<size_t>(W));
+  }
+  // confusion counts: vertical run-length accumulation per thread (label and prediction maps are piecewise
+  // constant, so a thread's four pixels usually stay in one bin for many rows): no warp collectives, one
+  // shared-memory atomic per run.
+  int run_bin = 0;
+  unsigned int run_cnt = 0;
+  for (int y = y_begin; y < y_end; ++y, pix += W) {
     int idx[4] = {0, 0, 0, 0};
-    const uchar4 l4 = l4_next;
+    const uchar4 l4 = lq0;
     if (col_ok) {
-      if (do_cm && y + 1 < y_end) l4_next = *reinterpret_cast<const uchar4*>(label + pix + W);
+      lq0 = lq1; lq1 = lq2; lq2 = lq3;
+      if (do_cm && y + 4 < y_end) lq3 = *reinterpret_cast<const uchar4*>(label + pix + 4 * static_cast<size_t>(W));
       const SrcCoord cy = src_coord(sy, y, h);
       const int r1 = cy.i0 + cy.step;
       fill(cy.i0);
@@ -253,7 +279,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8) upsample_rows
 #pragma unroll 4
         for (int k = 0; k < K; ++k) {
           const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-          const float v[4] = {l0 * a.x + l1 * c.x, l0 * a.y + l1 * c.y, l0 * a.z + l1 * c.z, l0 * a.w + l1 * c.w};
+          // l0*a + l1*c on packed fp32 pairs (FMUL2 + FFMA2): same products and sums as the scalar form
+          float2 t01 = mul2(make_float2(l0, l0), make_float2(a.x, a.y)), t23 = mul2(make_float2(l0, l0), make_float2(a.z, a.w));
+          t01 = fma2(make_float2(l1, l1), make_float2(c.x, c.y), t01);
+          t23 = fma2(make_float2(l1, l1), make_float2(c.z, c.w), t23);
+          const float v[4] = {t01.x, t01.y, t23.x, t23.y};
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; }
@@ -293,24 +323,33 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8) upsample_rows
       }
       if (pred) *reinterpret_cast<uchar4*>(pred + pix) = make_uchar4(idx[0], idx[1], idx[2], idx[3]);
     }
-    if (do_cm) {
-      // per-thread pre-aggregation: pixels that share the first valid pixel's bin are counted together
-      // (label/pred maps are piecewise constant), stragglers go one by one; then one grouped update.
+    if (do_cm && col_ok) {
       const int lab[4] = {l4.x, l4.y, l4.z, l4.w};
-      int bin0 = -1;
-      unsigned int cnt = 0;
+      int bin[4];
+      bool valid[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool valid = col_ok && lab[j] != ignore_label && lab[j] < K;
-        const int bj = lab[j] * K + idx[j];
-        if (valid) {
-          if (bin0 < 0) bin0 = bj;
-          if (bj == bin0) ++cnt; else atomicAdd(&hist[bj], 1u);
-        }
+        valid[j] = lab[j] != ignore_label && lab[j] < K;
+        bin[j] = lab[j] * K + idx[j];
       }
-      hist_add_grouped(hist, bin0 < 0 ? 0 : bin0, cnt);
+      const bool uni = valid[0] && valid[1] && valid[2] && valid[3] && bin[0] == bin[1] && bin[1] == bin[2] &&
+                       bin[2] == bin[3];
+      if (uni && bin[0] == run_bin) {
+        run_cnt += 4u;                                          // the common case: 2 instructions
+      } else if (uni) {
+        if (run_cnt) atomicAdd(&hist[run_bin], run_cnt);
+        run_bin = bin[0];
+        run_cnt = 4u;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (valid[j]) {
+            if (bin[j] == run_bin) ++run_cnt; else atomicAdd(&hist[bin[j]], 1u);
+          }
+      }
     }
   }
+  if (do_cm && run_cnt) atomicAdd(&hist[run_bin], run_cnt);
   if (do_cm) {
     __syncthreads();
     for (int i = threadIdx.x; i < K * K; i += THREADS)
