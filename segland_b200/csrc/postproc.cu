@@ -407,41 +407,39 @@ __global__ void __launch_bounds__(256) confusion_kernel(const uint8_t* __restric
   const long long nvec = vec ? n / 16 : 0;
   const long long stride = static_cast<long long>(gridDim.x) * 256;
   const long long start = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  const long long iters = (nvec + stride - 1) / stride;
   unsigned int my_bad = 0;
-  for (long long it = 0; it < iters; ++it) {
-    const long long v = start + it * stride;
-    const bool active = v < nvec;
-    uint4 g4 = make_uint4(0, 0, 0, 0), p4 = g4;
-    if (active) {
-      g4 = ld_stream_u4(gt + v * 16);
-      p4 = ld_stream_u4(pr + v * 16);
-    }
+  // run-length accumulation: consecutive pixels of a thread mostly fall in one bin
+  int run_bin = 0;
+  unsigned int run_cnt = 0;
+  auto add = [&](int g, int p) {
+    if (g == ignore_label) return;
+    if (g >= K || p >= K) { ++my_bad; return; }
+    const int bin = g * K + p;
+    if (bin == run_bin) { ++run_cnt; return; }
+    if (run_cnt) atomicAdd(&hist[run_bin], run_cnt);
+    run_bin = bin;
+    run_cnt = 1u;
+  };
+  for (long long v = start; v < nvec; v += stride) {
+    const uint4 g4 = ld_stream_u4(gt + v * 16), p4 = ld_stream_u4(pr + v * 16);
     const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
     const uint32_t pw[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 4; ++q) {
+      // fast path: four equal (gt, pred) byte pairs in this word pair
+      const uint32_t g0 = gw[q] & 0xffu, p0 = pw[q] & 0xffu;
+      if (gw[q] == g0 * 0x01010101u && pw[q] == p0 * 0x01010101u && static_cast<int>(g0) != ignore_label &&
+          static_cast<int>(g0) < K && static_cast<int>(p0) < K && static_cast<int>(g0) * K + static_cast<int>(p0) == run_bin) {
+        run_cnt += 4u;
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int g = (gw[q] >> (8 * j)) & 0xff, p = (pw[q] >> (8 * j)) & 0xff;
-        const bool keep = active && g != ignore_label;
-        const bool valid = keep && g < K && p < K;
-        my_bad += (keep && !valid);
-        hist_add_warp(hist, valid ? g * K + p : 0, valid);
+        for (int j = 0; j < 4; ++j) add((gw[q] >> (8 * j)) & 0xff, (pw[q] >> (8 * j)) & 0xff);
       }
+    }
   }
   // scalar tail (and the whole array when the pointers are not 16-byte aligned)
-  const long long tail0 = nvec * 16;
-  const long long titers = (n - tail0 + stride - 1) / stride;
-  for (long long it = 0; it < titers; ++it) {
-    const long long i = tail0 + start + it * stride;
-    const bool active = i < n;
-    const int g = active ? gt[i] : 0, p = active ? pr[i] : 0;
-    const bool keep = active && g != ignore_label;
-    const bool valid = keep && g < K && p < K;
-    my_bad += (keep && !valid);
-    hist_add_warp(hist, valid ? g * K + p : 0, valid);
-  }
+  for (long long i = nvec * 16 + start; i < n; i += stride) add(gt[i], pr[i]);
+  if (run_cnt) atomicAdd(&hist[run_bin], run_cnt);
   if (my_bad) atomicAdd(&bad, my_bad);
   __syncthreads();
   for (int i = threadIdx.x; i < K * K; i += 256)

@@ -6,17 +6,20 @@
 
 namespace sl {
 
-// ---- MAP step 1: bilinear align_corners=True resample of the mask to feature resolution, plus the
-// per-image mask sum (one CTA per image -> fixed summation order).
+// ---- MAP step 1: bilinear align_corners=True resample of the mask to feature resolution.  grid
+// (chunks of 1024 low-res pixels, B); every CTA also leaves the sum of its chunk, and step 2 adds the
+// chunk sums of an image in index order -> fixed summation order, bit-reproducible.
+constexpr int MAP_CHUNK = 1024;
 __global__ void __launch_bounds__(256) map_mask_kernel(const float* __restrict__ mask, int h, int w, int H, int W,
                                                        float sy, float sx, float* __restrict__ mask_lr,
-                                                       float* __restrict__ msum) {
+                                                       float* __restrict__ partial, int n_chunks) {
   __shared__ float red[8];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const float* src = mask + static_cast<size_t>(b) * H * W;
   float* dst = mask_lr + static_cast<size_t>(b) * h * w;
   float acc = 0.f;
-  for (int i = threadIdx.x; i < h * w; i += 256) {
+  const int i_end = min(h * w, (static_cast<int>(blockIdx.x) + 1) * MAP_CHUNK);
+  for (int i = blockIdx.x * MAP_CHUNK + threadIdx.x; i < i_end; i += 256) {
     const int y = i / w, x = i - y * w;
     const SrcCoord cy = src_coord(sy, y, H), cx = src_coord(sx, x, W);
     const float* r0 = src + static_cast<size_t>(cy.i0) * W + cx.i0;
@@ -33,7 +36,7 @@ __global__ void __launch_bounds__(256) map_mask_kernel(const float* __restrict__
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i];
-    msum[b] = t;
+    partial[static_cast<size_t>(b) * n_chunks + blockIdx.x] = t;
   }
 }
 
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(256) map_mask_kernel(const float* __restrict__
 constexpr int MAP_CH = 4;
 __global__ void __launch_bounds__(256) map_reduce_kernel(const uint16_t* __restrict__ feat, int C, int N,
                                                          const float* __restrict__ mask_lr,
-                                                         const float* __restrict__ msum,
+                                                         const float* __restrict__ partial, int n_chunks,
                                                          float* __restrict__ per_image) {
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -53,13 +56,8 @@ __global__ void __launch_bounds__(256) map_reduce_kernel(const uint16_t* __restr
   float acc[MAP_CH];
 #pragma unroll
   for (int j = 0; j < MAP_CH; ++j) acc[j] = 0.f;
-  for (int n = lane * 8; n < N; n += 32 * 8) {
-    const float4 ma = __ldg(reinterpret_cast<const float4*>(m + n));
-    const float4 mb = __ldg(reinterpret_cast<const float4*>(m + n + 4));
-    uint4 v[MAP_CH];
-#pragma unroll
-    for (int j = 0; j < MAP_CH; ++j)
-      v[j] = (c0 + j < C) ? ld_stream_u4(f + static_cast<size_t>(j) * N + n) : make_uint4(0, 0, 0, 0);
+  // two 8-pixel groups per lane per iteration: 2 x MAP_CH independent 128-bit loads in flight
+  auto accumulate = [&](const uint4 (&v)[MAP_CH], const float4& ma, const float4& mb) {
 #pragma unroll
     for (int j = 0; j < MAP_CH; ++j) {
       float a = acc[j];
@@ -69,8 +67,32 @@ __global__ void __launch_bounds__(256) map_reduce_kernel(const uint16_t* __restr
       a = fmaf(bf16lo(v[j].w), mb.z, a); a = fmaf(bf16hi(v[j].w), mb.w, a);
       acc[j] = a;
     }
+  };
+  int n = lane * 8;
+  for (; n + 256 < N; n += 512) {
+    uint4 v0[MAP_CH], v1[MAP_CH];
+#pragma unroll
+    for (int j = 0; j < MAP_CH; ++j) {
+      const bool ok = c0 + j < C;
+      v0[j] = ok ? ld_stream_u4(f + static_cast<size_t>(j) * N + n) : make_uint4(0, 0, 0, 0);
+      v1[j] = ok ? ld_stream_u4(f + static_cast<size_t>(j) * N + n + 256) : make_uint4(0, 0, 0, 0);
+    }
+    const float4 ma0 = __ldg(reinterpret_cast<const float4*>(m + n)), mb0 = __ldg(reinterpret_cast<const float4*>(m + n + 4));
+    const float4 ma1 = __ldg(reinterpret_cast<const float4*>(m + n + 256)), mb1 = __ldg(reinterpret_cast<const float4*>(m + n + 260));
+    accumulate(v0, ma0, mb0);
+    accumulate(v1, ma1, mb1);
   }
-  const float denom = msum[b] + 1e-5f;
+  for (; n < N; n += 256) {
+    uint4 v[MAP_CH];
+#pragma unroll
+    for (int j = 0; j < MAP_CH; ++j)
+      v[j] = (c0 + j < C) ? ld_stream_u4(f + static_cast<size_t>(j) * N + n) : make_uint4(0, 0, 0, 0);
+    const float4 ma = __ldg(reinterpret_cast<const float4*>(m + n)), mb = __ldg(reinterpret_cast<const float4*>(m + n + 4));
+    accumulate(v, ma, mb);
+  }
+  float msum = 0.f;
+  for (int i = 0; i < n_chunks; ++i) msum += partial[static_cast<size_t>(b) * n_chunks + i];
+  const float denom = msum + 1e-5f;
 #pragma unroll
   for (int j = 0; j < MAP_CH; ++j) {
     const float t = warp_sum(acc[j]);
@@ -158,10 +180,12 @@ extern "C" int sl_map_proto(const uint16_t* feat, const float* mask, int B, int 
   SL_CHECK_ARG(N % 8 == 0 && N < (1ll << 30));
   SL_CHECK_ALIGN(feat, 16); SL_CHECK_ALIGN(mask_lr_ws, 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* msum = mask_lr_ws + static_cast<size_t>(B) * N;   // the B mask sums follow the [B,N] map
-  sl::map_mask_kernel<<<B, 256, 0, st>>>(mask, h, w, H, W, sl::ac_scale(H, h), sl::ac_scale(W, w), mask_lr_ws, msum);
+  const int n_chunks = static_cast<int>((N + sl::MAP_CHUNK - 1) / sl::MAP_CHUNK);
+  float* partial = mask_lr_ws + static_cast<size_t>(B) * N;   // [B][n_chunks] chunk sums follow the [B,N] map
+  sl::map_mask_kernel<<<dim3(n_chunks, B), 256, 0, st>>>(mask, h, w, H, W, sl::ac_scale(H, h), sl::ac_scale(W, w),
+                                                        mask_lr_ws, partial, n_chunks);
   dim3 grid((C + 8 * sl::MAP_CH - 1) / (8 * sl::MAP_CH), B);
-  sl::map_reduce_kernel<<<grid, 256, 0, st>>>(feat, C, static_cast<int>(N), mask_lr_ws, msum, per_image);
+  sl::map_reduce_kernel<<<grid, 256, 0, st>>>(feat, C, static_cast<int>(N), mask_lr_ws, partial, n_chunks, per_image);
   sl::map_mean_kernel<<<(C + 127) / 128, 128, 0, st>>>(per_image, B, C, proto);
   return SL_LAUNCH_RESULT();
 }
