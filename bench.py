@@ -45,6 +45,11 @@ def load_peaks():
     return {'hbm_gbs': 6650.0, 'tflops_burst': 1590.0, 'tflops_sustained': 1400.0, 'source': 'fallback'}
 
 
+def load_traffic():
+    p = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons of one GPU during the timed region (NVML)."""
 
@@ -276,15 +281,23 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     # ---- roofline of the dominant kernel
+    traffic = load_traffic()
     bg_flops = (4.0 * C * C + 2.0 * C) * N_PIX * T           # algorithmic: two CxC layers + w3 dot, per launch
+    passes = (5 if args.tc_precision == 'precise' else 3) if use_tc else 2
+    bg_exec_flops = (2.0 * C * C * passes + 2.0 * C) * N_PIX * T   # MMA FLOPs actually issued (split operands)
     fg_bytes = (C * N_PIX * 2 + KB * N_PIX * 4) * T          # features in + K fg logits out
     post_bytes = (K * N_PIX * 4 + 2 * TILE * TILE) * T       # low-res logits in + label in + pred out
     dominant = max(kern_ms, key=kern_ms.get)
     if dominant == 'bg':
         ach = bg_flops / (kern_ms['bg'] * 1e-3) / 1e12
         roofline = {'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': ach / peaks['tflops_sustained'], 'traffic': None,
-                    'kernel': 'pop_bg_tc' if use_tc else 'pop_bg_simt',
+                    'frac': ach / peaks['tflops_sustained'],
+                    'traffic': traffic.get('bg_fused_kernel', {}).get(args.tc_precision) if use_tc else None,
+                    'traffic_note': 'dram read+write bytes per 32-tile launch from profiles/r1_traffic.json (ncu --set full)',
+                    'kernel': 'bg_fused_kernel (sl_pop_bg_tc)' if use_tc else 'pop_bg_simt_kernel',
+                    'mma_passes': passes,
+                    'achieved_executed': bg_exec_flops / (kern_ms['bg'] * 1e-3) / 1e12,
+                    'frac_executed_of_burst': bg_exec_flops / (kern_ms['bg'] * 1e-3) / 1e12 / peaks['tflops_burst'],
                     'peak_source': peaks['source'] + ' bf16 sustained (kernel timed inside a long step)',
                     'flops_per_launch': bg_flops}
     else:
@@ -296,8 +309,9 @@ def run_ours(args, rank, world, local_rank):
     fg_gbs = fg_bytes / (kern_ms['fg'] * 1e-3) / 1e9
     stage_s = {'value': T / (stage_s_ms * 1e-3), 'unit': '1024x1024 tiles/s (fg logits + upsample/argmax/confusion; '
                'no background MLP)', 'ms_per_step': stage_s_ms,
-               'roofline_hbm': {'kernel': 'pop_fg', 'achieved': fg_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                                'frac': fg_gbs / peaks['hbm_gbs'], 'bytes_per_launch': fg_bytes},
+               'roofline_hbm': {'kernel': 'pop_fg_kernel (sl_pop_fg_lowres)', 'achieved': fg_gbs, 'peak': peaks['hbm_gbs'],
+                                'unit': 'GB/s', 'frac': fg_gbs / peaks['hbm_gbs'], 'bytes_per_launch': fg_bytes,
+                                'traffic': traffic.get('pop_fg_kernel', {}).get('base')},
                'algorithmic_bytes_per_tile': C * N_PIX * 2 + 2 * TILE * TILE}
     cpu_tps, cores = cpu_reference_tiles_per_s(args.cpu_tiles) if world == 1 and args.cpu_tiles > 0 else (None, None)
     line = {
