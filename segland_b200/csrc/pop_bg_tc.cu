@@ -43,7 +43,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
-constexpr int STAGING_BYTES = 2 * 16384;                // per 4-warp group: {hi,lo} x [128 rows][64 B]
+constexpr int STAGING_BYTES = 2 * 16384;                // per 4-warp group: two 8 KB [128 rows][64 B] buffers
 constexpr int W3_BYTES = 2048;
 constexpr int MAX_N_TILES = 16;          // C / 32 at C = 512
 constexpr int BAR_BYTES = 256;
@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
     const bool leader = ((warp - 2) & 3) == 0 && lane == 0;                  // issues the group's TMA stores
     auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); };
     int acc = 0; uint32_t acc_phase = 0;
+    int store_ctr = 0;
     float logit = 0.f;
     auto epi_job = [&](bool g2, int s, int nt) {
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -289,29 +290,33 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
               lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
             }
           }
-          // stage the group's 128x32 16-bit chunk (64 B per row, SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3)
-          // and hand it to TMA as ONE 8 KB store per array: the store engine writes full lines and the
-          // TMA unit sees 4x fewer descriptors than with per-warp stores.
-          if (leader) tma_store_wait_read<0>();             // the previous store has drained the buffer
-          group_sync();
-          const uint32_t rbase = sbuf + static_cast<uint32_t>(row) * 64u;
-          const uint32_t sw = static_cast<uint32_t>((row >> 1) & 3);
-          if (!(p.debug & 1))
+          // Stage the group's 128x32 16-bit chunk (64 B per row, SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3)
+          // and hand it to TMA as one 8 KB store: the store engine writes full lines and the LSU only
+          // sees shared memory.  The group's 16 KB staging area is a two-deep ping-pong of 8 KB buffers
+          // (hi and lo alternate), so a buffer is rewritten only after the store issued two stores ago
+          // has read it -- the previous store's latency hides behind the next conversion.
+          const int col = nt * p.NT + c0;
+          auto stage_and_store = [&](const uint32_t (&vals)[16], const CUtensorMap* map) {
+            const uint32_t buf = sbuf + static_cast<uint32_t>((store_ctr & 1) * 8192);
+            ++store_ctr;
+            if (leader) tma_store_wait_read<1>();
+            group_sync();
+            const uint32_t rbase = buf + static_cast<uint32_t>(row) * 64u;
+            const uint32_t sw = static_cast<uint32_t>((row >> 1) & 3);
+            if (!(p.debug & 1))
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t off16 = ((static_cast<uint32_t>(q) ^ sw) << 4);
-            st_shared_v4(rbase + off16, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-            if (!p.h_f16) st_shared_v4(rbase + 8192u + off16, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-          }
-          fence_async_smem();
-          group_sync();
-          if (leader && !(p.debug & 2)) {
-            const int col = nt * p.NT + c0;
-            const int row0 = ws_row0;
-            tma_store_2d(&maps.hh_st, sbuf, col, row0, L2_EVICT_LAST);
-            if (!p.h_f16) tma_store_2d(&maps.hl_st, sbuf + 8192u, col, row0, L2_EVICT_LAST);
-            tma_store_commit();
-          }
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(rbase + ((static_cast<uint32_t>(q) ^ sw) << 4), vals[4 * q], vals[4 * q + 1], vals[4 * q + 2],
+                           vals[4 * q + 3]);
+            fence_async_smem();
+            group_sync();
+            if (leader && !(p.debug & 2)) {
+              tma_store_2d(map, buf, col, ws_row0, L2_EVICT_LAST);
+              tma_store_commit();
+            }
+          };
+          stage_and_store(hi, &maps.hh_st);
+          if (!p.h_f16) stage_and_store(lo, &maps.hl_st);
         }
       } else if (half == 0) {
         if (nt == 0) logit = 0.f;
