@@ -462,3 +462,94 @@ def test_patch_installs_into_reference_shaped_modules(ops, golden):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+# ------------------------------------------------------------------- limits and edge cases
+def test_max_classes_everywhere(ops):
+    """SL_MAX_CLASSES = 32: 31 prototypes (+ background) through the head (three fg passes of <= 12
+    classes), the upsample/argmax/confusion kernel and the label-map confusion kernel."""
+    C, Kb, Kn = 64, 20, 11
+    st = synth.make_head_state(C, Kb, Kn, seed=77)
+    feats = synth.make_random_features(2, C, 16, 16, seed=77)
+    ref = ref_ops.ref_head(feats.float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
+    logits = make_head(ops, st, 'auto')(feats.cuda())
+    assert logits.shape == (2, 32, 16, 16)
+    assert_close_rel(logits.cpu(), ref, RTOL, 'K=31 head')
+    labels = synth.make_labels(2, 64, 64, 32, seed=77, coarse=8)
+    cm = torch.zeros(32, 32, dtype=torch.int64, device='cuda')
+    out = ops.upsample_argmax(logits, (64, 64), label=labels, cm=cm)
+    pred = out['pred'].cpu().numpy()
+    ref_pred = ref_ops.ref_upsample_argmax(ref, (64, 64))
+    assert (pred == ref_pred).mean() >= 0.999
+    cm_ref = sum(ref_ops.ref_confusion(labels[t].numpy(), pred[t], 32) for t in range(2))
+    assert np.array_equal(cm.cpu().numpy().astype(np.float64), cm_ref)
+    assert np.array_equal(ops.get_confusion_matrix(labels.numpy(), pred, 32), cm_ref)
+    with pytest.raises(ValueError):
+        ops.PopHead(torch.randn(25, C), st.cls, torch.randn(8, C), st.cls_n)        # 1 + 33 classes
+
+
+def test_tc_batched_small_and_minimal_shapes(ops):
+    """Tensor-core path with B > 1 images, a single 128-pixel tile per image (N = 128) and more CTAs'
+    worth of tiles than SMs (persistent loop with a ragged tail)."""
+    for C, B, hw in ((64, 5, (8, 16)), (128, 3, (16, 8)), (512, 2, (48, 48))):
+        st = synth.make_head_state(C, 7, 4, seed=C + B)
+        feats = synth.make_random_features(B, C, hw[0], hw[1], seed=C + B)
+        ref = ref_ops.ref_head(feats.float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
+        out = make_head(ops, st, 'tc')(feats.cuda())
+        assert_close_rel(out.cpu(), ref, RTOL, f'tc C={C} B={B} hw={hw}')
+    # 160 tiles of 128 pixels > 148 SMs: every CTA takes one or two tiles
+    st = synth.make_head_state(64, 7, 0, seed=5)
+    feats = synth.make_random_features(10, 64, 32, 64, seed=5)
+    ref = ref_ops.ref_head(feats.float(), st.base_emb, None, st.cls, None)
+    assert_close_rel(make_head(ops, st, 'tc')(feats.cuda()).cpu(), ref, RTOL, 'tc ragged persistent loop')
+
+
+def test_head_is_bit_reproducible(ops):
+    st = synth.make_head_state(512, 7, 4, seed=3)
+    feats = synth.make_random_features(2, 512, 32, 32, seed=3).cuda()
+    for mode in ('tc', 'simt'):
+        head = make_head(ops, st, mode)
+        a = head(feats).clone()
+        for _ in range(3):
+            assert torch.equal(head(feats), a), mode
+
+
+def test_fuse_sixteen_models_and_alignment_errors(ops):
+    mats = synth.make_logit_stacks(16, 8, 16, 16, seed=2)
+    pred = ops.fuse_logits([m.cuda() for m in mats])
+    ref_pred, _ = ref_ops.ref_fuse([m.numpy() for m in mats])
+    assert np.array_equal(pred.cpu().numpy(), ref_pred)
+    from segland_b200 import _cabi
+    with pytest.raises(_cabi.SeglandError):                                   # M > SL_MAX_FUSE
+        ops.fuse_logits([m.cuda() for m in synth.make_logit_stacks(17, 8, 16, 16, seed=2)])
+    with pytest.raises(_cabi.SeglandError):                                   # HW % 4 != 0
+        ops.fuse_logits([torch.randn(8, 3, 3, device='cuda')])
+
+
+def test_upsample_downscale_and_identity(ops):
+    """Output smaller than the input (MAP-style resampling direction) and equal size."""
+    g = torch.Generator().manual_seed(9)
+    lg = torch.randn(2, 6, 40, 36, generator=g)
+    for size in ((40, 36), (20, 12), (7, 8), (1, 4)):
+        ref = ref_ops.ref_upsample(lg, size)
+        out = ops.upsample_argmax(lg.cuda(), size, want_logits=True)
+        assert_close_rel(out['logits'].cpu(), ref, 1e-5, f'resize to {size}')
+        assert (out['pred'].cpu().numpy() == np.argmax(ref.numpy(), axis=1)).mean() >= 0.999
+
+
+def test_inter_union_accumulates_like_validate(ops):
+    """ft_pop.py:312-336: per-batch intersectionAndUnionGPU summed into meters, then IoU."""
+    g = torch.Generator().manual_seed(4)
+    inter_m, union_m = torch.zeros(12, device='cuda'), torch.zeros(12, device='cuda')
+    cm = np.zeros((12, 12))
+    for _ in range(3):
+        tgt = torch.randint(0, 12, (2, 64, 64), generator=g)
+        tgt[torch.rand(2, 64, 64, generator=g) < 0.1] = 255
+        out = torch.randint(0, 12, (2, 64, 64), generator=g)
+        cm += ref_ops.ref_confusion(tgt.numpy(), out.numpy(), 12)
+        i, u, _ = ops.intersectionAndUnionGPU(out.cuda(), tgt.cuda(), 12, 255)
+        inter_m += i
+        union_m += u
+    iou = (inter_m / union_m).cpu().numpy()
+    ref_iou = np.diag(cm) / (cm.sum(0) + cm.sum(1) - np.diag(cm))
+    assert np.allclose(iou, ref_iou, rtol=1e-6)
