@@ -252,6 +252,27 @@ def main():
     print('orth base %.6f ft %.6f ; pseudo-labelled px %d' % (
         float(loss_b['orth_loss']), float(loss_f['orth_loss']), int((mask_b != mask_b_before).sum())))
 
+    # ---- segmentation CE tail: the reference's OrthLoss.forward / CELoss.forward on low-res logits
+    torch.set_grad_enabled(True)
+    gen = torch.Generator().manual_seed(71)
+    ce = {}
+    for i, (B, K, h, w, H, W, scale) in enumerate([(2, 12, 16, 16, 128, 128, 1.0), (1, 8, 9, 13, 70, 101, 3.0),
+                                                   (2, 5, 8, 8, 8, 8, 0.5)]):
+        preds = (torch.randn(B, K, h, w, generator=gen) * scale).requires_grad_(True)
+        target = torch.randint(0, K, (B, H, W), generator=gen)
+        target[torch.rand(B, H, W, generator=gen) < 0.07] = 255
+        sim = torch.eye(4, 11)
+        out = criterion.OrthLoss(ignore_index=255)(preds, target, is_ft=True, proto_sim=sim)
+        out['seg_loss'].backward()
+        ce.update({f'preds{i}': preds.detach().numpy(), f'target{i}': target.numpy(),
+                   f'loss{i}': out['seg_loss'].detach().numpy(), f'grad{i}': preds.grad.numpy(),
+                   f'total{i}': out['total_loss'].detach().numpy()})
+        out2 = criterion.CELoss(ignore_index=255)(preds.detach(), target)
+        assert torch.equal(out2['total_loss'], out['seg_loss'].detach())
+    np.savez_compressed(os.path.join(out_dir, 'ce.npz'), **ce)
+    torch.set_grad_enabled(False)
+    print('ce losses', [float(ce[f'loss{i}']) for i in range(3)])
+
     # ---- fusemat.py: run the script itself on temporary .mat files
     import scipy.io
     from PIL import Image

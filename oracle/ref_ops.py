@@ -190,6 +190,13 @@ def ref_orth_loss(proto_sim):
     return torch.abs(proto_sim[eye_sim == 1]).mean()
 
 
+def ref_seg_ce(preds, target, ignore_index=IGNORE_LABEL):
+    """The segmentation term of OrthLoss.forward / CELoss.forward, loss/criterion.py:17-19,51-52:
+    bilinear align_corners upsample to the label size, then CrossEntropyLoss(ignore_index, mean)."""
+    scale_pre = F.interpolate(input=preds, size=target.shape[1:], mode='bilinear', align_corners=True)
+    return torch.nn.CrossEntropyLoss(ignore_index=ignore_index, reduction='mean')(scale_pre, target)
+
+
 # --------------------------------------------------------------------------- fusion
 def ref_fuse(mats, n_lists=None):
     """fusemat.py:42-48 for ONE tile: sequential += in directory order, / len(fusion_list),

@@ -28,6 +28,8 @@ _SIGNATURES = {
     'sl_map_proto': [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     'sl_orth_loss': [_P, c_int, _P, c_int, c_int, _P, _P, _P, _P],
     'sl_fuse_argmax': [POINTER(_P), c_int, c_int, c_longlong, c_int, _P, _P, _P, c_int, _P, _P],
+    'sl_upsample_ce_fwd': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P],
+    'sl_upsample_ce_bwd': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P],
 }
 
 _lib = None
@@ -58,6 +60,8 @@ def lib():
         handle.sl_pop_bg_tc_ws_bytes.restype = c_size_t
         handle.sl_pop_prepare_ws_bytes.argtypes = [c_int, c_int]
         handle.sl_pop_prepare_ws_bytes.restype = c_size_t
+        handle.sl_upsample_ce_ws_bytes.argtypes = [c_int, c_int, c_int]
+        handle.sl_upsample_ce_ws_bytes.restype = c_size_t
         if handle.sl_abi_version() != 1:
             raise ImportError(f'{LIB_PATH}: ABI version {handle.sl_abi_version()} != 1; rebuild')
         _lib = handle
@@ -65,7 +69,7 @@ def lib():
 
 
 def exported_names():
-    return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes', 'sl_pop_prepare_ws_bytes']
+    return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes', 'sl_pop_prepare_ws_bytes', 'sl_upsample_ce_ws_bytes']
 
 
 def call(name, *args):

@@ -387,6 +387,63 @@ def orth_loss(rows, others=None):
     return _OrthLossFn.apply(rows, others)
 
 
+class _SegCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, preds, target, ignore_index):
+        logits = preds.detach().to(torch.float32).contiguous()
+        B, K, h, w = logits.shape
+        tgt = target.detach().to(torch.int64).contiguous()
+        H, W = tgt.shape[-2:]
+        dev = logits.device
+        ws = torch.empty(_cabi.lib().sl_upsample_ce_ws_bytes(B, H, W), dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        n_valid = torch.empty(1, dtype=torch.int64, device=dev)
+        call('sl_upsample_ce_fwd', ptr(logits), B, K, h, w, H, W, ptr(tgt), int(ignore_index), ptr(ws), ptr(loss),
+             ptr(n_valid), _stream())
+        ctx.save_for_backward(logits, tgt, ws, n_valid)
+        ctx.ignore_index = int(ignore_index)
+        ctx.in_dtype = preds.dtype
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, tgt, ws, n_valid = ctx.saved_tensors
+        B, K, h, w = logits.shape
+        H, W = tgt.shape[-2:]
+        grad = torch.empty_like(logits)
+        g = g.detach().to(torch.float32).reshape(1).contiguous()
+        call('sl_upsample_ce_bwd', ptr(logits), B, K, h, w, H, W, ptr(tgt), ctx.ignore_index, ptr(ws), ptr(n_valid),
+             ptr(g), ptr(grad), _stream())
+        return grad.to(ctx.in_dtype), None, None
+
+
+def seg_cross_entropy(preds, target, ignore_index=IGNORE_LABEL):
+    """The segmentation term of OrthLoss.forward / CELoss.forward (loss/criterion.py:17-19, :51-52):
+    CrossEntropyLoss(ignore_index, 'mean') of the align-corners bilinear up-sampling of `preds`
+    [B,K,h,w] to the size of `target` [B,H,W] (int64), fused: the [B,K,H,W] tensor is never written.
+    Differentiable w.r.t. preds; deterministic."""
+    if not preds.is_cuda or not target.is_cuda:
+        raise ValueError('seg_cross_entropy needs CUDA tensors')
+    if preds.dim() != 4 or target.dim() != 3 or preds.shape[0] != target.shape[0]:
+        raise ValueError('preds must be [B,K,h,w] and target [B,H,W]')
+    return _SegCEFn.apply(preds, target, ignore_index)
+
+
+def orth_loss_forward(preds, target, is_ft=False, proto_sim=None, aux_preds=None, ignore_index=IGNORE_LABEL, w=10.0):
+    """OrthLoss.forward (loss/criterion.py:45-65) with the same arguments and loss-dict keys: the seg /
+    aux cross-entropy terms run fused; the orthogonality term reads the (tiny) proto_sim matrix the
+    model built, exactly as OrthLoss.get_orth_loss does (loss/criterion.py:37-43)."""
+    seg_loss = seg_cross_entropy(preds, target, ignore_index)
+    eye_sim = torch.triu(torch.ones_like(proto_sim), diagonal=1)
+    orth = torch.abs(proto_sim[eye_sim == 1]).mean()
+    if aux_preds is not None:
+        aux_loss = seg_cross_entropy(aux_preds, target, ignore_index)
+        total = seg_loss + orth * w + 0.4 * aux_loss
+        return {'total_loss': total, 'seg_loss': seg_loss, 'aux_loss': aux_loss, 'orth_loss': orth}
+    total = seg_loss + orth * w
+    return {'total_loss': total, 'seg_loss': seg_loss, 'orth_loss': orth}
+
+
 # =================================================================================== fusion
 def fuse_logits(mats, n_lists=None, label=None, cm=None, ignore_label=IGNORE_LABEL, want_fused=False):
     """fusemat.py:42-48 for one tile (or a batch laid out as one long pixel axis): mats is the

@@ -9,7 +9,9 @@ replaces, in place,
     decoder -- `orthogonal_decompose` + `classifier` / `classifier_n` + channel assembly
     (`pspnet_pop.py:143-159`, `:171-182`) -- runs in libsegland_b200.so; backbones and decoders stay
     stock PyTorch.  Training-mode calls (`forward_novel`, loss dicts) fall through to the reference.
-  * `utils.pyt_utils.get_confusion_matrix` and `utils.pyt_utils.intersectionAndUnionGPU`.
+  * `utils.pyt_utils.get_confusion_matrix` and `utils.pyt_utils.intersectionAndUnionGPU`;
+  * `loss.criterion.OrthLoss.forward`: the seg / aux cross-entropy terms run fused with the up-sampling
+    (`loss/criterion.py:51-52,57-58`), differentiable, so training loops keep working.
 The scripts (`eval_base.py`, `eval_ft.py`, `ft_pop.py`, `train_base.py`) need no edits: they look these
 names up at call time.  `unpatch()` restores the originals.
 """
@@ -89,6 +91,20 @@ def patch(verbose=False):
                 _originals.append((pu, fn, getattr(pu, fn)))
                 setattr(pu, fn, getattr(ops, fn))
                 done.append(f'utils.pyt_utils.{fn}')
+    except Exception:                                                  # noqa: BLE001
+        pass
+    try:
+        crit = importlib.import_module('loss.criterion')
+        if not getattr(crit.OrthLoss.forward, '_sl_patched', False):
+            def orth_forward(self, preds, target, is_ft=False, proto_sim=None, aux_preds=None):
+                if not preds.is_cuda:
+                    return _orig_orth(self, preds, target, is_ft, proto_sim, aux_preds)
+                return ops.orth_loss_forward(preds, target, is_ft, proto_sim, aux_preds, self.ignore_index, self.w)
+            _orig_orth = crit.OrthLoss.forward
+            orth_forward._sl_patched = True
+            _originals.append((crit.OrthLoss, 'forward', _orig_orth))
+            crit.OrthLoss.forward = orth_forward
+            done.append('loss.criterion.OrthLoss.forward')
     except Exception:                                                  # noqa: BLE001
         pass
     if verbose:

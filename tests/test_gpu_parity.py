@@ -553,3 +553,52 @@ def test_inter_union_accumulates_like_validate(ops):
     iou = (inter_m / union_m).cpu().numpy()
     ref_iou = np.diag(cm) / (cm.sum(0) + cm.sum(1) - np.diag(cm))
     assert np.allclose(iou, ref_iou, rtol=1e-6)
+
+
+# --------------------------------------------------------------- (f-1) fused upsample + CE
+def test_seg_cross_entropy_vs_golden(ops, golden):
+    """OrthLoss.forward's segmentation term (loss/criterion.py:51-52), forward and gradient, against the
+    reference's own output (tests/golden/ce.npz), plus the whole loss dict."""
+    z = golden('ce')
+    for i in range(3):
+        preds = torch.from_numpy(z[f'preds{i}']).cuda().requires_grad_(True)
+        target = torch.from_numpy(z[f'target{i}']).cuda()
+        loss = ops.seg_cross_entropy(preds, target)
+        assert abs(loss.item() - float(z[f'loss{i}'])) <= 1e-5 * abs(float(z[f'loss{i}']))
+        loss.backward()
+        assert_close_rel(preds.grad.cpu(), torch.from_numpy(z[f'grad{i}']), RTOL, f'ce grad {i}')
+        out = ops.orth_loss_forward(preds.detach(), target, is_ft=True, proto_sim=torch.eye(4, 11).cuda())
+        assert abs(out['total_loss'].item() - float(z[f'total{i}'])) <= 1e-5 * abs(float(z[f'total{i}']))
+        assert set(out) == {'total_loss', 'seg_loss', 'orth_loss'}
+
+
+def test_seg_cross_entropy_properties(ops):
+    g = torch.Generator().manual_seed(5)
+    preds = torch.randn(2, 12, 16, 16, generator=g).cuda()
+    target = torch.randint(0, 12, (2, 128, 128), generator=g).cuda()
+    # all pixels ignored -> NaN like torch, zero gradient
+    all_ign = torch.full_like(target, 255)
+    p = preds.clone().requires_grad_(True)
+    loss = ops.seg_cross_entropy(p, all_ign)
+    assert torch.isnan(loss)
+    # deterministic: two runs are bit-identical, forward and backward
+    grads = []
+    for _ in range(2):
+        p = preds.clone().requires_grad_(True)
+        loss_i = ops.seg_cross_entropy(p, target)
+        (3.0 * loss_i).backward()
+        grads.append((loss_i.item(), p.grad.clone()))
+    assert grads[0][0] == grads[1][0] and torch.equal(grads[0][1], grads[1][1])
+    # against torch's own CUDA ops at full size (1024^2) with the upstream gradient scale
+    big = torch.randn(1, 12, 128, 128, generator=g).cuda().requires_grad_(True)
+    tgt = torch.randint(0, 12, (1, 1024, 1024), generator=g).cuda()
+    tgt[tgt == 3] = 255
+    mine = ops.seg_cross_entropy(big, tgt)
+    (2.5 * mine).backward()
+    gmine = big.grad.clone()
+    big.grad = None
+    ref = torch.nn.functional.cross_entropy(
+        F.interpolate(big, size=(1024, 1024), mode='bilinear', align_corners=True), tgt, ignore_index=255)
+    (2.5 * ref).backward()
+    assert abs(mine.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert_close_rel(gmine.cpu(), big.grad.cpu(), RTOL, 'ce grad 1024^2 vs torch CUDA')

@@ -95,3 +95,14 @@ def test_fuse(golden):
         pred, fused = ref_ops.ref_fuse(mats)
         assert fused.dtype == np.float32
         assert np.array_equal(pred, z[f'{tile}_pred'])
+
+
+def test_seg_ce(golden):
+    z = golden('ce')
+    for i in range(3):
+        preds = torch.from_numpy(z[f'preds{i}']).requires_grad_(True)
+        target = torch.from_numpy(z[f'target{i}'])
+        loss = ref_ops.ref_seg_ce(preds, target)
+        assert loss.item() == float(z[f'loss{i}'])
+        loss.backward()
+        assert np.array_equal(preds.grad.numpy(), z[f'grad{i}'])
