@@ -118,7 +118,7 @@ def cpu_reference_tiles_per_s(n_tiles, repeats=1, seed=1234):
     from segland_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    st = synth.make_head_state(C, KB, 0, seed=seed)
+    st = synth.make_trained_like_state(C, KB, 0, seed=seed)
     labels = synth.make_labels(n_tiles, TILE, TILE, st.n_classes, seed=seed)
     feats = synth.make_features(labels, st, STRIDE, seed=seed).float()       # fp32 copy of the bf16 values
     K = st.n_classes
@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
     from segland_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    st = synth.make_head_state(C, KB, 0, seed=1234)
+    st = synth.make_trained_like_state(C, KB, 0, seed=1234)
     n_distinct = 4
     labels = synth.make_labels(n_distinct, TILE, TILE, st.n_classes, seed=1234)
     feats = synth.make_features(labels, st, STRIDE, seed=1234).float()
@@ -188,7 +188,7 @@ def run_ours(args, rank, world, local_rank):
     ops.check_device()
     peaks = load_peaks()
     T = args.tiles
-    st = synth.make_head_state(C, KB, 0, seed=1234)
+    st = synth.make_trained_like_state(C, KB, 0, seed=1234)     # argmax follows the labels: mIoU is meaningful
     K = st.n_classes
     # distinct tiles per rank (weak scaling): different seeds per rank
     n_gen = min(T, 8)                                # generate 8 distinct tiles on the host, then decorrelate on device

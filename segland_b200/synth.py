@@ -60,6 +60,43 @@ def make_head_state(C, Kb=KB_OEM, Kn=0, seed=1234, proto_scale=1.0):
     return HeadState(base, novel, cls, cls_n)
 
 
+def make_trained_like_state(C, Kb=KB_OEM, Kn=0, seed=1234, n_bg_units=64, bg_gain=5.0, noise=0.02):
+    """A head whose argmax is meaningful on make_features() tiles, so a sweep has a non-trivial mIoU
+    (random-init MLPs give alpha_k of random sign and mIoU ~ chance).  Construction: hidden units
+    0..K-1 of layer 1 are the normalised prototypes, so a foreground vector p*s_k lights exactly unit
+    k (alpha_k ~ 1, beta_k ~ 0); n_bg_units further units are random directions orthogonal to every
+    prototype and see only the background residual, giving class 0 a logit ~ 0.4*bg_gain on pure-noise
+    pixels; layer 2 passes both groups through and w3 sums them.  Everything gets `noise` x default-init
+    jitter so no weight is exactly zero.  In ft mode classifier_n is built the same way (classes Kb..K-1
+    and the background) and classifier handles the base classes."""
+    gen = torch.Generator().manual_seed(seed)
+    base = _orthogonal(gen, Kb, C)
+    novel = _orthogonal(gen, Kn, C) if Kn else None
+    protos = base if novel is None else torch.cat([base, novel], 0)
+    K = protos.shape[0]
+    s_hat = F.normalize(protos, p=2, dim=-1)
+    r = torch.randn(n_bg_units, C, generator=gen)
+    r = r - (r @ s_hat.t()) @ s_hat                                  # orthogonal to every prototype
+    r = F.normalize(r, p=2, dim=-1)
+
+    def build():
+        W1 = noise * _conv1x1_weight(gen, C, C)
+        W2 = noise * _conv1x1_weight(gen, C, C)
+        w3 = noise * _conv1x1_weight(gen, 1, C).reshape(C)
+        W1[:K] += s_hat
+        W1[K:K + n_bg_units] += r
+        idx = torch.arange(K + n_bg_units)
+        W2[idx, idx] += 1.0
+        w3[:K] += 1.0
+        w3[K:K + n_bg_units] += bg_gain / n_bg_units
+        return (W1, W2, w3)
+
+    assert K + n_bg_units <= C
+    if Kn == 0:
+        return HeadState(base, None, build(), None)
+    return HeadState(base, novel, build(), build())
+
+
 def make_labels(T, H, W, n_classes, seed=1234, coarse=32, ignore_frac=0.01):
     """uint8 [T,H,W]: nearest-upsampled coarse random class field, ~1% pixels = 255."""
     gen = torch.Generator().manual_seed(seed + 1)

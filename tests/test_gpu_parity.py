@@ -602,3 +602,26 @@ def test_seg_cross_entropy_properties(ops):
     (2.5 * ref).backward()
     assert abs(mine.item() - ref.item()) <= 1e-5 * abs(ref.item())
     assert_close_rel(gmine.cpu(), big.grad.cpu(), RTOL, 'ce grad 1024^2 vs torch CUDA')
+
+
+def test_trained_like_sweep_matches_reference_miou(ops):
+    """A head whose argmax follows the labels (synth.make_trained_like_state): the sweep's confusion
+    matrix and mIoU equal the CPU oracle's on two full 1024^2 tiles, at a level well above chance --
+    the 'reference-matching mIoU' of the north star, on the benchmark's own workload."""
+    from segland_b200 import sweep
+    st = synth.make_trained_like_state(512, 7, 0, seed=1234)
+    labels = synth.make_labels(2, 1024, 1024, 8, seed=1234)
+    feats = synth.make_features(labels, st, 8, seed=1234)
+    ev = sweep.TileEvaluator(make_head(ops, st, 'auto'), (1024, 1024))
+    ev.step(feats.cuda(), labels.cuda())
+    cm, (base, novel, total, arr) = ev.finalize(base_classes=7)
+    cm_ref = np.zeros((8, 8))
+    for t in range(2):
+        _, c, _ = ref_ops.ref_eval_tile(feats[t:t + 1].float(), labels[t:t + 1].numpy(), st.base_emb, None, st.cls,
+                                        None, (1024, 1024), 8)
+        cm_ref += c
+    mine = cm.cpu().numpy().astype(np.float64)
+    assert mine.sum() == cm_ref.sum()
+    assert np.abs(mine - cm_ref).sum() <= 2 * 1e-4 * cm_ref.sum()           # <= 0.01 % of pixels may differ
+    ref_total = ref_ops.ref_miou(cm_ref, 7)[2]
+    assert total > 0.5 and abs(total - ref_total) < 1e-4
