@@ -204,6 +204,7 @@ def run_ours(args, rank, world, local_rank):
                        tc_precision=args.tc_precision)
     ev = sweep.TileEvaluator(head, (TILE, TILE))
     use_tc = head._use_tc(N_PIX)
+    fused = use_tc and args.fuse and head.fused_ok(N_PIX)
 
     stream = torch.cuda.current_stream()
     ev_k = {k: [] for k in ('prepare', 'fg', 'bg', 'post')}
@@ -217,9 +218,12 @@ def run_ours(args, rank, world, local_rank):
         lg = ev._logits
         if lg is None or lg.shape[0] != T:
             ev._logits = lg = torch.empty(T, K, HW_LR, HW_LR, dtype=torch.float32, device=dev)
-        head(feats, out=lg, fg_only=True)
+        if not fused:
+            head(feats, out=lg, fg_only=True)
         if record: marks[2].record(stream)
-        if use_tc:
+        if fused:
+            head.head_tc(feats, lg)          # fg logits + background MLP in one launch
+        elif use_tc:
             head.bg_tc(feats, lg)
         else:
             head.bg_simt(feats, lg)
@@ -323,13 +327,15 @@ def run_ours(args, rank, world, local_rank):
                    'mode': 'base', 'bg_path': (f'tcgen05 {args.tc_precision} ' + ('(split-bf16, 2+3 passes)' if args.tc_precision == 'precise'
                                                                     else '(split-bf16 L1, fp16 L2, 2+1 passes)'))
                    if use_tc else 'fp32 CUDA cores',
+                   'head_launches': 'one (fg logits fused into the tcgen05 kernel)' if fused else 'two (fg kernel + bg kernel)',
                    'l2_policy': f'inputs larger than L2 ({T * C * N_PIX * 2 / 1e6:.0f} MB features per step)',
                    'parallelism': f'dp{world}'},
         'kernel_ms_per_step': kern_ms,
         'roofline': roofline,
         'stage_s': stage_s,
         'e2e': e2e,
-        'gpu_launches': args.steps * 8,      # per step: 5 (prepare) + fg + bg + upsample/argmax/confusion
+        # per step: 5 (prepare) + head (2 launches fused incl. the prototype transpose, else fg + bg) + upsample/argmax/confusion
+        'gpu_launches': args.steps * 8,
         'clocks': clocks,
         'miou_total': float(mious[2]),
     }
@@ -415,6 +421,7 @@ def main():
     ap.add_argument('--e2e-tiles', type=int, default=8)
     ap.add_argument('--cpu-tiles', type=int, default=8, help='tiles in the bounded CPU-baseline sample (0 = skip)')
     ap.add_argument('--bg-mode', default='auto', choices=['auto', 'tc', 'simt'])
+    ap.add_argument('--fuse', action='store_true', help='single-launch head (sl_pop_head_tc); slower on B200, see DESIGN.md')
     ap.add_argument('--tc-precision', default='precise', choices=['precise', 'balanced'],
                     help="tensor-core background MLP mode; 'precise' is the parity-grade default")
     args = ap.parse_args()

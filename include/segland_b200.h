@@ -128,6 +128,19 @@ SL_API int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
                  const uint16_t *W2_hi, const uint16_t *W2_lo,
                  const uint16_t *W2_f16, const float *w3_bg, int precision, uint16_t *h1_ws, float *logits, int Ktot, int ch, void *stream);
 
+/* The whole POP head in one launch (tensor-core path): sl_pop_bg_tc with the K <= 12 foreground logits of
+ * sl_pop_fg_lowres computed by extra warps from the feature tiles already staged for the MMAs, so the
+ * features are read from HBM once.  Arguments as in the two calls it replaces; ch_map_host[k] is the
+ * output channel of class k, bg_ch the background channel.  Same shape limits and scratch as sl_pop_bg_tc.
+ */
+SL_API int sl_pop_head_tc(const uint16_t *feat, int B, int C, int N,
+                   const uint16_t *W1p_hi, const uint16_t *W1p_lo,
+                   const uint16_t *W2_hi, const uint16_t *W2_lo,
+                   const uint16_t *W2_f16, const float *w3_bg, int precision,
+                   const float *s_hat, const float *alpha, const float *beta, int K,
+                   const int *ch_map_host, uint16_t *h1_ws, float *logits, int Ktot, int bg_ch,
+                   void *stream);
+
 /* Test-time view aggregation at feature resolution (spec: this repo -- the reference
  * has no flip/sliding-window inference): out = scale * sum_v unflip(view_v).
  *   views [V,B,K,h,w] fp32; flip_host[v] bit0 = horizontal flip, bit1 = vertical flip.

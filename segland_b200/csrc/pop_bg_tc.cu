@@ -102,6 +102,12 @@ struct Params {
   int h_f16;            // hidden layer stored as one fp16 tile (layer 2 = 1 pass) instead of bf16 hi/lo (3 passes)
   const float* w3;
   float* logits;
+  // fused foreground projections (KQ > 0): s_hat transposed [C][4*KQ], alpha/beta [K], output channel map
+  const float* s_hat_t;
+  const float* alpha;
+  const float* beta;
+  int K;
+  int fg_ch[12];
   int debug;            // SL_TC_DEBUG experiments (timing only, results invalid): 1 = no st.shared staging,
                         // 2 = no TMA stores, 4 = no LDTM/convert in G1
 };
@@ -113,12 +119,16 @@ struct Maps {           // 9 x 128 B of kernel parameter space
   CUtensorMap hh_st, hl_st;      // same tensors, box 32 ch x 128 rows (SWIZZLE_64B) for the epilogue stores
 };
 
-__global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
+// KQ = ceil(K/4) foreground classes computed by four extra "projection" warps (0 = background only).
+template <int KQ>
+__global__ void __launch_bounds__(THREADS + (KQ > 0 ? 128 : 0), 1)
+bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   if ((base & 1023u) != 0) asm volatile("trap;");                        // SWIZZLE_128B wants 1024-byte tiles
   const uint32_t stage_out = base + STAGES * STAGE_BYTES;                // G1 store staging
-  float* w3s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES);   // [512]
+  // 2 KB: two 768-byte buffers for the projection warps' prototype slices ([16 channels][<=12 classes] fp32)
+  float* sproto = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES + W3_BYTES);
   // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, [2S+4,2S+4+16) h1_ready per
   // layer-1 n-tile; then the TMEM base slot
@@ -143,7 +153,8 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
     tma_prefetch_desc(&maps.x); tma_prefetch_desc(&maps.w1h); tma_prefetch_desc(&maps.w1l);
     tma_prefetch_desc(&maps.w2h); tma_prefetch_desc(&maps.w2l); tma_prefetch_desc(&maps.hh_ld);
     tma_prefetch_desc(&maps.hl_ld); tma_prefetch_desc(&maps.hh_st); tma_prefetch_desc(&maps.hl_st);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // a smem stage is released by the MMA commit and, when the projection warps exist, by their leader too
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), KQ > 0 ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
     for (int s = 0; s < MAX_N_TILES; ++s) mbar_init(h1_bar(s), 2);      // one arrival per epilogue group
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -153,7 +164,6 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
                  "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.C; i += THREADS) w3s[i] = p.w3[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -244,6 +254,106 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
         for (int nt = 0; nt < p.n_tiles; ++nt) mma_job(true);
       }
     }
+  } else if (warp >= 2 + EPI_WARPS) {
+    // ===================================================================== foreground projections (4 warps)
+    // Thread pm owns pixel row pm of the tile.  Every feature k-block passes through the ring
+    // V = n_tiles * l1_passes times per tile; on visit v the warps read channels [64v/V, 64(v+1)/V) of it
+    // straight from the MMA's MN-major SWIZZLE_128B stage, so the CUDA-core work (K FMAs per feature
+    // element) is spread evenly under the tensor-core time and the features are read from HBM once for
+    // both the background MLP and the K foreground logits:  logit_k = p >= 0 ? p*alpha_k : -p*beta_k,
+    // p = s_hat_k . q  (pspnet_pop.py:108-109,114-115 + classifier on the rank-1 vector).
+    if constexpr (KQ > 0) {
+      constexpr int KP = 4 * KQ;
+      const int pm = static_cast<int>(threadIdx.x) - 32 * (2 + EPI_WARPS);      // 0..127
+      const bool pleader = pm == 0;
+      const int V = p.n_tiles * p.l1_passes;
+      const int l2_uses = p.n_tiles * (p.h_f16 ? 1 : 3) * kblocks;
+      // byte offset of (channel 0, pixel pm) inside a stage; channel c adds c*128 and XORs the 16-byte chunk
+      const uint32_t px_blk = static_cast<uint32_t>(pm >> 6) * (A_BYTES / 2);
+      const uint32_t px_chunk = static_cast<uint32_t>((pm & 63) >> 3), px_in = static_cast<uint32_t>(pm & 7) * 2u;
+      int stage = 0; uint32_t phase = 0;
+      auto next_stage = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1u; } };
+      // Prototype slices ([16 channels][KP] fp32, <= 768 B) are staged through a two-buffer shared area:
+      // thread pm carries element pm (and pm+128 when KP = 12) of the NEXT slice in registers, fetched
+      // one stage ahead so the global-load latency is off the critical path.
+      auto slice_addr = [&](int kb, int sl) { return p.s_hat_t + static_cast<size_t>(kb * BLOCK_K + sl * 16) * KP; };
+      auto slice_valid = [&](int kb, int sl) { return kb * BLOCK_K + sl * 16 < p.C; };
+      constexpr int SLICE_ELEMS = 16 * KP;                      // 64, 128 or 192
+      int use = 0;                                             // running count of slices processed (buffer parity)
+      for (int s = 0; s < n_my; ++s) {
+        float acc[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+        int visit = 0;
+        for (int nt = 0; nt < p.n_tiles; ++nt)
+          for (int pass = 0; pass < p.l1_passes; ++pass, ++visit) {
+            // a k-block is four 16-channel slices; visit v of V takes slices [4v/V, 4(v+1)/V)
+            const int sl_lo = 4 * visit / V, sl_hi = 4 * (visit + 1) / V;
+            for (int kb = 0; kb < kblocks; ++kb) {
+              mbar_wait(full_bar(stage), phase);
+              const uint32_t sa = base + stage * STAGE_BYTES + px_blk + px_in;
+              for (int sl = sl_lo; sl < sl_hi; ++sl) {
+                if (!slice_valid(kb, sl)) break;
+                // this slice's prototypes -> shared (buffer use&1); the previous reader of that buffer finished
+                // before the bar.sync of the slice in between
+                float* sb = sproto + (use & 1) * 192;
+                {
+                  const float* src = slice_addr(kb, sl);
+                  if (pm < SLICE_ELEMS) sb[pm] = __ldg(src + pm);
+                  if (SLICE_ELEMS > 128 && pm + 128 < SLICE_ELEMS) sb[pm + 128] = __ldg(src + pm + 128);
+                }
+                float x[16];
+                const int c0 = sl * 16;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {                           // 16 independent shared loads in flight
+                  uint16_t bits;
+                  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(bits)
+                               : "r"(sa + static_cast<uint32_t>(c0 + c) * 128u +
+                                     ((px_chunk ^ static_cast<uint32_t>((c0 + c) & 7)) << 4)));
+                  x[c] = __uint_as_float(static_cast<uint32_t>(bits) << 16);
+                }
+                asm volatile("bar.sync 3, 128;" ::: "memory");            // prototypes visible; x[] held in registers
+                ++use;
+                const float4* srow = reinterpret_cast<const float4*>(sb);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+#pragma unroll
+                  for (int q = 0; q < KQ; ++q) {
+                    const float4 sv = srow[c * KQ + q];                   // broadcast shared load
+                    acc[4 * q + 0] = fmaf(sv.x, x[c], acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(sv.y, x[c], acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(sv.z, x[c], acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(sv.w, x[c], acc[4 * q + 3]);
+                  }
+                }
+              }
+              asm volatile("bar.sync 3, 128;" ::: "memory");              // every reader is done with the stage
+              if (pleader) mbar_arrive(empty_bar(stage));
+              next_stage();
+            }
+          }
+        {  // the tile's K foreground logits
+          const int mt = tile_of(s);
+          const int img = mt / p.tiles_per_image;
+          const int n = (mt - img * p.tiles_per_image) * BLOCK_M + pm;
+#pragma unroll
+          for (int k = 0; k < KP; ++k)
+            if (k < p.K) {
+              const float pr = acc[k];
+              p.logits[(static_cast<size_t>(img) * p.Ktot + p.fg_ch[k]) * p.N + n] =
+                  pr >= 0.f ? pr * __ldg(p.alpha + k) : -pr * __ldg(p.beta + k);
+            }
+        }
+        // layer-2 stages carry no features: the leader just keeps the release protocol in step
+        for (int u = 0; u < l2_uses; ++u) {
+          if (pleader) { mbar_wait(full_bar(stage), phase); mbar_arrive(empty_bar(stage)); }
+          next_stage();
+        }
+        // nobody may run ahead of the leader: a parity wait issued many phases early can be satisfied by a
+        // stale completion of the same parity
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+      }
+    }
   } else {
     // ===================================================================== epilogue (8 warps)
     const int sub = warp & 3;                     // TMEM sub-partition this warp may read
@@ -324,9 +434,15 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
           uint32_t r[32];
           tc_ld32(taddr + c0, r);
           tc_ld_wait();
-          const float* wv = w3s + nt * p.NT + c0;
+          const float4* wv = reinterpret_cast<const float4*>(p.w3 + nt * p.NT + c0);   // warp-uniform, L1-resident
 #pragma unroll
-          for (int j = 0; j < 32; ++j) logit = fmaf(wv[j], fmaxf(__uint_as_float(r[j]), 0.f), logit);
+          for (int j = 0; j < 8; ++j) {
+            const float4 w4 = __ldg(wv + j);
+            logit = fmaf(w4.x, fmaxf(__uint_as_float(r[4 * j + 0]), 0.f), logit);
+            logit = fmaf(w4.y, fmaxf(__uint_as_float(r[4 * j + 1]), 0.f), logit);
+            logit = fmaf(w4.z, fmaxf(__uint_as_float(r[4 * j + 2]), 0.f), logit);
+            logit = fmaf(w4.w, fmaxf(__uint_as_float(r[4 * j + 3]), 0.f), logit);
+          }
         }
       }
       tc_fence_before();
@@ -362,19 +478,21 @@ __global__ void __launch_bounds__(THREADS, 1) bg_fused_kernel(const __grid_const
   }
 }
 
+// s_hat [K][C] -> [C][KP] (zero padded) for the projection warps' 128-bit uniform loads
+__global__ void transpose_protos_kernel(const float* __restrict__ s_hat, int K, int C, int KP, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * KP) return;
+  const int c = idx / KP, k = idx - c * KP;
+  out[idx] = k < K ? s_hat[static_cast<size_t>(k) * C + c] : 0.f;
+}
+
 }  // namespace tc
 }  // namespace sl
 
-extern "C" size_t sl_pop_bg_tc_ws_bytes(int B, int C, int N) {
-  if (B < 1 || C < 1 || N < 1) return 0;
-  // per CTA: 128 rows x C channels x {hi, lo} bf16; sized for a full grid of 148 CTAs
-  return static_cast<size_t>(sl::kNumSMs) * sl::tc::BLOCK_M * C * 2 * sizeof(uint16_t);
-}
-
-extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uint16_t* W1p_hi, const uint16_t* W1p_lo,
-                            const uint16_t* W2_hi, const uint16_t* W2_lo, const uint16_t* W2_f16,
-                            const float* w3_bg, int precision, uint16_t* h1_ws,
-                            float* logits, int Ktot, int ch, void* stream) {
+static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint16_t* W1p_hi, const uint16_t* W1p_lo,
+                          const uint16_t* W2_hi, const uint16_t* W2_lo, const uint16_t* W2_f16, const float* w3_bg,
+                          int precision, uint16_t* h1_ws, float* logits, int Ktot, int ch, const float* s_hat,
+                          const float* alpha, const float* beta, int K, const int* fg_ch_host, void* stream) {
   using namespace sl::tc;
   // (a bf16-feature x fp16-weight single pass for layer 1 was tried: tcgen05 kind::f16 traps on mixed A/B formats)
   SL_CHECK_ARG(precision == SL_TC_PRECISE || precision == SL_TC_BALANCED);
@@ -388,6 +506,11 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
   SL_CHECK_ARG(static_cast<long long>(B) * N / BLOCK_M < (1ll << 30));
   SL_CHECK_ALIGN(feat, 16); SL_CHECK_ALIGN(h1_ws, 128);
   SL_CHECK_ALIGN(W1p_hi, 16); SL_CHECK_ALIGN(W1p_lo, 16); SL_CHECK_ALIGN(W2_hi, 16); SL_CHECK_ALIGN(W2_lo, 16);
+  const int KQ = K > 0 ? (K + 3) / 4 : 0;
+  if (K > 0) {
+    SL_CHECK_PTR(s_hat); SL_CHECK_PTR(alpha); SL_CHECK_PTR(beta); SL_CHECK_PTR(fg_ch_host);
+    SL_CHECK_ARG(K <= 12 && K < Ktot);
+  }
 
   Params p;
   p.C = C;
@@ -412,6 +535,15 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
   const size_t ws_rows = static_cast<size_t>(sl::kNumSMs) * BLOCK_M;
   uint16_t* h_hi = h1_ws;
   uint16_t* h_lo = h1_ws + ws_rows * C;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // transposed, zero-padded prototypes [C][4*KQ] live behind the scratch tiles
+  float* s_hat_t = reinterpret_cast<float*>(h1_ws + 2 * ws_rows * C);
+  p.s_hat_t = s_hat_t; p.alpha = alpha; p.beta = beta; p.K = K;
+  for (int k = 0; k < 12; ++k) p.fg_ch[k] = 0;
+  for (int k = 0; k < K; ++k) {
+    SL_CHECK_ARG(fg_ch_host[k] >= 0 && fg_ch_host[k] < Ktot && fg_ch_host[k] != ch);
+    p.fg_ch[k] = fg_ch_host[k];
+  }
 
   Maps m;
   int rc;
@@ -437,8 +569,46 @@ extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uin
     if ((rc = make_map(&m.hh_st, h_hi, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if ((rc = make_map(&m.hl_st, h_lo, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
-  cudaError_t e = cudaFuncSetAttribute(bg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  bg_fused_kernel<<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(m, p);
+  if (KQ > 0) transpose_protos_kernel<<<(C * 4 * KQ + 255) / 256, 256, 0, st>>>(s_hat, K, C, 4 * KQ, s_hat_t);
+  cudaError_t e = cudaSuccess;
+#define SL_HEAD_LAUNCH(Q)                                                                                         \
+  do {                                                                                                            \
+    e = cudaFuncSetAttribute(bg_fused_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);        \
+    if (e != cudaSuccess) return static_cast<int>(e);                                                             \
+    bg_fused_kernel<Q><<<grid, THREADS + (Q > 0 ? 128 : 0), SMEM_BYTES, st>>>(m, p);                              \
+  } while (0)
+  switch (KQ) {
+    case 0: SL_HEAD_LAUNCH(0); break;
+    case 1: SL_HEAD_LAUNCH(1); break;
+    case 2: SL_HEAD_LAUNCH(2); break;
+    default: SL_HEAD_LAUNCH(3); break;
+  }
+#undef SL_HEAD_LAUNCH
   return SL_LAUNCH_RESULT();
+}
+
+extern "C" size_t sl_pop_bg_tc_ws_bytes(int B, int C, int N) {
+  if (B < 1 || C < 1 || N < 1) return 0;
+  // per CTA: 128 rows x C channels x {hi, lo} bf16, sized for a full grid of 148 CTAs; then [C][12] fp32 for the
+  // transposed prototypes of the fused entry point
+  return static_cast<size_t>(sl::kNumSMs) * sl::tc::BLOCK_M * C * 2 * sizeof(uint16_t) +
+         static_cast<size_t>(C) * 12 * sizeof(float);
+}
+
+extern "C" int sl_pop_bg_tc(const uint16_t* feat, int B, int C, int N, const uint16_t* W1p_hi, const uint16_t* W1p_lo,
+                            const uint16_t* W2_hi, const uint16_t* W2_lo, const uint16_t* W2_f16,
+                            const float* w3_bg, int precision, uint16_t* h1_ws,
+                            float* logits, int Ktot, int ch, void* stream) {
+  return launch_head_tc(feat, B, C, N, W1p_hi, W1p_lo, W2_hi, W2_lo, W2_f16, w3_bg, precision, h1_ws, logits, Ktot, ch,
+                        nullptr, nullptr, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int sl_pop_head_tc(const uint16_t* feat, int B, int C, int N, const uint16_t* W1p_hi,
+                              const uint16_t* W1p_lo, const uint16_t* W2_hi, const uint16_t* W2_lo,
+                              const uint16_t* W2_f16, const float* w3_bg, int precision, const float* s_hat,
+                              const float* alpha, const float* beta, int K, const int* ch_map_host, uint16_t* h1_ws,
+                              float* logits, int Ktot, int bg_ch, void* stream) {
+  SL_CHECK_ARG(K >= 1 && K <= 12);
+  return launch_head_tc(feat, B, C, N, W1p_hi, W1p_lo, W2_hi, W2_lo, W2_f16, w3_bg, precision, h1_ws, logits, Ktot,
+                        bg_ch, s_hat, alpha, beta, K, ch_map_host, stream);
 }

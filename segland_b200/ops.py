@@ -75,7 +75,7 @@ class PopHead:
     TC_PRECISIONS = {'precise': 0, 'balanced': 1}
 
     def __init__(self, base_emb, classifier, novel_emb=None, classifier_n=None, device=None, bg_mode='auto',
-                 tc_precision='precise'):
+                 tc_precision='precise', fuse=False):
         check_device()
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
@@ -100,6 +100,10 @@ class PopHead:
         if tc_precision not in self.TC_PRECISIONS:
             raise ValueError(tc_precision)
         self.tc_precision = tc_precision
+        # fuse=True: one-launch head (sl_pop_head_tc: fg logits computed inside the tensor-core kernel, K <= 12).
+        # Measured on B200 at configs[1]: 1.22 ms vs 0.10 + 1.03 ms for the two-launch path -- the projection
+        # warps' shared-memory reads compete with the MMA operand reads -- so it is off by default.
+        self.fuse = bool(fuse)
         self._plan = None
         self._h1_ws = None
         self.refresh()
@@ -178,6 +182,22 @@ class PopHead:
              ptr(p.split[3]), ptr(p.f16[1]), ptr(p.w3_bg), self.TC_PRECISIONS[self.tc_precision],
              ptr(self._h1_ws), ptr(out), out.shape[1], 0, _stream())
 
+    def head_tc(self, feats, out):
+        """One launch for the whole head (K <= 12): background MLP on tcgen05 + foreground logits from the
+        same shared-memory feature tiles."""
+        B, C, h, w = feats.shape
+        N = h * w
+        need = _cabi.lib().sl_pop_bg_tc_ws_bytes(B, C, N)
+        if self._h1_ws is None or self._h1_ws.numel() * 2 < need or self._h1_ws.device != feats.device:
+            self._h1_ws = torch.empty(need // 2, dtype=torch.int16, device=feats.device)
+        p = self._plan
+        call('sl_pop_head_tc', ptr(feats), B, C, N, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
+             ptr(p.split[3]), ptr(p.f16[1]), ptr(p.w3_bg), self.TC_PRECISIONS[self.tc_precision], ptr(p.s_hat),
+             ptr(p.alpha), ptr(p.beta), self.K, self._ch_map, ptr(self._h1_ws), ptr(out), out.shape[1], 0, _stream())
+
+    def fused_ok(self, N):
+        return self.K <= 12 and self._use_tc(N)
+
     def bg_simt(self, feats, out):
         B, C, h, w = feats.shape
         p = self._plan
@@ -201,6 +221,9 @@ class PopHead:
             out = torch.empty(B, Ktot, h, w, dtype=torch.float32, device=feats.device)
         p = self._plan
         st = _stream()
+        if not fg_only and self.fuse and self.fused_ok(N):
+            self.head_tc(feats, out)
+            return out
         call('sl_pop_fg_lowres', ptr(feats), B, C, N, ptr(p.s_hat), ptr(p.alpha), ptr(p.beta), self.K,
              ptr(out), Ktot, self._ch_map, st)
         if not fg_only:
