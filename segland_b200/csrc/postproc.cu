@@ -195,11 +195,15 @@ __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const flo
   return d;
 }
 
-template <int THREADS, bool EXTRA>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8) upsample_rows_kernel(
+// KP == 0: predictions / confusion only (the eval hot path).  KP > 0: also soft outputs (conf, probs,
+// up-sampled logits) for K <= KP classes, whose interpolated values stay in registers so the softmax
+// costs one interpolation and one exp per value.
+template <int THREADS, int KP>
+__global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (THREADS == 256 ? 3 : 8)) upsample_rows_kernel(
     const float* __restrict__ logits_lr, int K, int h, int w, int H, int W, int rows_per_band, float sy, float sx,
     const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred, float* __restrict__ conf,
     float* __restrict__ probs, float* __restrict__ logits_hr, unsigned long long* __restrict__ cm) {
+  constexpr bool EXTRA = KP > 0;
   extern __shared__ __align__(16) float hrow[];                 // [2][K][THREADS] float4
   __shared__ unsigned int hist[SL_MAX_CLASSES * SL_MAX_CLASSES];
   const bool do_cm = cm != nullptr;
@@ -275,51 +279,61 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8) upsample_rows
       const float l0 = cy.l0, l1 = cy.l1;
       float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       const bool bad = ((cy.i0 & 1) ? bad_odd : bad_even) | ((r1 & 1) ? bad_odd : bad_even);
-      if (!bad) {
+      if constexpr (!EXTRA) {
+        if (!bad) {
 #pragma unroll 4
-        for (int k = 0; k < K; ++k) {
-          const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-          // l0*a + l1*c on packed fp32 pairs (FMUL2 + FFMA2): same products and sums as the scalar form
-          float2 t01 = mul2(make_float2(l0, l0), make_float2(a.x, a.y)), t23 = mul2(make_float2(l0, l0), make_float2(a.z, a.w));
-          t01 = fma2(make_float2(l1, l1), make_float2(c.x, c.y), t01);
-          t23 = fma2(make_float2(l1, l1), make_float2(c.z, c.w), t23);
-          const float v[4] = {t01.x, t01.y, t23.x, t23.y};
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; }
-          if (EXTRA && logits_hr)
-            *reinterpret_cast<float4*>(logits_hr + (static_cast<size_t>(b) * K + k) * HW + (pix - static_cast<size_t>(b) * HW)) =
-                make_float4(v[0], v[1], v[2], v[3]);
-        }
-      } else {
-        for (int k = 0; k < K; ++k) {
-          const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-          const float v[4] = {l0 * a.x + l1 * c.x, l0 * a.y + l1 * c.y, l0 * a.z + l1 * c.z, l0 * a.w + l1 * c.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) argmax_step(v[j], k, best[j], idx[j]);
-          if (EXTRA && logits_hr)
-            *reinterpret_cast<float4*>(logits_hr + (static_cast<size_t>(b) * K + k) * HW + (pix - static_cast<size_t>(b) * HW)) =
-                make_float4(v[0], v[1], v[2], v[3]);
-        }
-      }
-      if (EXTRA && (conf || probs)) {                           // softmax: recompute instead of keeping K values
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < K; ++k) {
-          const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-          s[0] += __expf(l0 * a.x + l1 * c.x - best[0]);
-          s[1] += __expf(l0 * a.y + l1 * c.y - best[1]);
-          s[2] += __expf(l0 * a.z + l1 * c.z - best[2]);
-          s[3] += __expf(l0 * a.w + l1 * c.w - best[3]);
-        }
-        const float inv[4] = {1.f / s[0], 1.f / s[1], 1.f / s[2], 1.f / s[3]};
-        if (conf) *reinterpret_cast<float4*>(conf + pix) = make_float4(inv[0], inv[1], inv[2], inv[3]);
-        if (probs)
           for (int k = 0; k < K; ++k) {
             const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-            *reinterpret_cast<float4*>(probs + (static_cast<size_t>(b) * K + k) * HW + (pix - static_cast<size_t>(b) * HW)) =
-                make_float4(__expf(l0 * a.x + l1 * c.x - best[0]) * inv[0], __expf(l0 * a.y + l1 * c.y - best[1]) * inv[1],
-                            __expf(l0 * a.z + l1 * c.z - best[2]) * inv[2], __expf(l0 * a.w + l1 * c.w - best[3]) * inv[3]);
+            // l0*a + l1*c on packed fp32 pairs (FMUL2 + FFMA2): same products and sums as the scalar form
+            float2 t01 = mul2(make_float2(l0, l0), make_float2(a.x, a.y)), t23 = mul2(make_float2(l0, l0), make_float2(a.z, a.w));
+            t01 = fma2(make_float2(l1, l1), make_float2(c.x, c.y), t01);
+            t23 = fma2(make_float2(l1, l1), make_float2(c.z, c.w), t23);
+            const float v[4] = {t01.x, t01.y, t23.x, t23.y};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; }
           }
+        } else {
+          for (int k = 0; k < K; ++k) {
+            const float4 a = h0[k * THREADS], c = h1[k * THREADS];
+            const float v[4] = {l0 * a.x + l1 * c.x, l0 * a.y + l1 * c.y, l0 * a.z + l1 * c.z, l0 * a.w + l1 * c.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) argmax_step(v[j], k, best[j], idx[j]);
+          }
+        }
+      } else {
+        float vals[4][KP > 0 ? KP : 1];
+        const size_t plane_off = pix - static_cast<size_t>(b) * HW;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          if (k < K) {
+            const float4 a = h0[k * THREADS], c = h1[k * THREADS];
+            const float v[4] = {l0 * a.x + l1 * c.x, l0 * a.y + l1 * c.y, l0 * a.z + l1 * c.z, l0 * a.w + l1 * c.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { argmax_step(v[j], k, best[j], idx[j]); vals[j][k] = v[j]; }
+            if (logits_hr)
+              __stcs(reinterpret_cast<float4*>(logits_hr + (static_cast<size_t>(b) * K + k) * HW + plane_off),
+                     make_float4(v[0], v[1], v[2], v[3]));
+          }
+        }
+        if (conf || probs) {
+          float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < KP; ++k)
+            if (k < K) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { vals[j][k] = __expf(vals[j][k] - best[j]); s[j] += vals[j][k]; }
+            }
+          const float inv[4] = {1.f / s[0], 1.f / s[1], 1.f / s[2], 1.f / s[3]};
+          if (conf) *reinterpret_cast<float4*>(conf + pix) = make_float4(inv[0], inv[1], inv[2], inv[3]);
+          if (probs) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+              if (k < K)
+                __stcs(reinterpret_cast<float4*>(probs + (static_cast<size_t>(b) * K + k) * HW + plane_off),   // streaming:
+                       make_float4(vals[0][k] * inv[0], vals[1][k] * inv[1], vals[2][k] * inv[2], vals[3][k] * inv[3]));  // written once
+          }
+        }
       }
       if (pred) *reinterpret_cast<uchar4*>(pred + pix) = make_uchar4(idx[0], idx[1], idx[2], idx[3]);
     }
@@ -363,7 +377,10 @@ static int launch_rows(const float* logits_lr, int B, int K, int h, int w, int H
                        float* logits_hr, unsigned long long* cm, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(2) * K * THREADS * sizeof(float4);
   const bool extra = conf || probs || logits_hr;
-  auto kern = extra ? upsample_rows_kernel<THREADS, true> : upsample_rows_kernel<THREADS, false>;
+  auto kern = !extra ? upsample_rows_kernel<THREADS, 0>
+              : K <= 8 ? upsample_rows_kernel<THREADS, 8>
+              : K <= 12 ? upsample_rows_kernel<THREADS, 12>
+              : K <= 16 ? upsample_rows_kernel<THREADS, 16> : upsample_rows_kernel<THREADS, 32>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid((W / 4 + THREADS - 1) / THREADS, (H + rows_per_band - 1) / rows_per_band, B);
