@@ -497,6 +497,324 @@ bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
   }
 }
 
+
+// ===========================================================================================
+// cta_group::2 variant of the background-MLP kernel (no fused foreground warps).  Two CTAs on an SM
+// pair form a cluster and run ONE 256-row MMA per instruction: CTA rank r owns pixel tile 2i+r (its
+// own A operand, TMEM accumulator rows, epilogue and scratch tile) and loads only HALF of every weight
+// tile (B operand rows [r*NT/2, (r+1)*NT/2)); the tensor cores of both SMs read both halves.  That
+// halves the weight traffic L2->smem and the B bytes each SM's MMA must stream, which is what limits
+// the single-CTA kernel (tensor pipe 77 % active).  Protocol differences from bg_fused_kernel:
+//   * only the leader (rank 0) issues tcgen05.mma.cta_group::2 and owns the `full` / `tmem_empty` waits;
+//   * both CTAs' TMA loads signal the LEADER's full barrier (peer bit of the barrier address cleared);
+//   * tcgen05.commit is multicast to the `empty` / `tmem_full` barriers of both CTAs;
+//   * both CTAs' epilogue warps arrive on the leader's `tmem_empty` barrier (count 16);
+//   * TMEM is allocated with cta_group::2 by the same warp of both CTAs; cluster barriers fence
+//     set-up and tear-down.  Scratch tiles, readiness barriers and schedules are per CTA as before.
+constexpr int P_STAGES = 6;                          // 32 KB stages: 16 KB A + 16 KB half-B
+constexpr int P_STAGE_BYTES = A_BYTES + B_BYTES_MAX / 2;
+constexpr int P_BAR_BYTES = 8 * (2 * P_STAGES + 4 + 2 * MAX_N_TILES) + 16;   // barriers + the TMEM base word
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + STAGING_BYTES + W3_BYTES + P_BAR_BYTES;
+static_assert(P_SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;          // clears the CTA-pair peer bit of a shared::cluster address
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {     // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  if ((base & 1023u) != 0) asm volatile("trap;");
+  const uint32_t stage_out = base + P_STAGES * P_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES + STAGING_BYTES + W3_BYTES);
+  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then h1_ready[slot][n-tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P_STAGES + 4 + 2 * MAX_N_TILES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (P_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * P_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * P_STAGES + 2 + s); };
+  auto h1_bar = [&](int slot, int nt) { return bar0 + 8u * (2 * P_STAGES + 4 + slot * MAX_N_TILES + nt); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool leader_cta = rank == 0;
+  const int pair = static_cast<int>(blockIdx.x) >> 1, n_pairs = static_cast<int>(gridDim.x) >> 1;
+  const int kblocks = (p.C + BLOCK_K - 1) / BLOCK_K;
+  const int half_nt = p.NT / 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(half_nt) * BLOCK_K * 2;
+  const int pair_tiles = (p.m_tiles + 1) / 2;
+  const int n_my = (pair_tiles - pair + n_pairs - 1) / n_pairs;          // identical in both CTAs of the pair
+  auto tile_raw = [&](int s) { return (pair + s * n_pairs) * 2 + static_cast<int>(rank); };
+  auto tile_of = [&](int s) { return min(tile_raw(s), p.m_tiles - 1); };  // odd tail: rank 1 redoes a valid tile
+  const int L = p.lookahead;
+  auto slot_of = [&](int s) { return s & L; };
+  auto ws_row0_of = [&](int s) { return (static_cast<int>(blockIdx.x) * (1 + L) + (s & L)) * BLOCK_M; };
+  auto h1_parity = [&](int s) { return static_cast<uint32_t>((L ? (s >> 1) : s) & 1); };
+  auto dep_of_kb = [&](int kb) { return min(p.n_tiles - 1, (kb * BLOCK_K + BLOCK_K - 1) / p.NT); };
+  auto for_each_phase = [&](auto&& g1, auto&& g2) {
+    if (L == 0) {
+      for (int s = 0; s < n_my; ++s) { g1(s); g2(s); }
+    } else {
+      for (int s = 0; s <= n_my; ++s) {
+        if (s < n_my) g1(s);
+        if (s >= 1) g2(s - 1);
+      }
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.x); tma_prefetch_desc(&maps.w1h); tma_prefetch_desc(&maps.w1l);
+    tma_prefetch_desc(&maps.w2h); tma_prefetch_desc(&maps.w2l); tma_prefetch_desc(&maps.hh_ld);
+    tma_prefetch_desc(&maps.hl_ld); tma_prefetch_desc(&maps.hh_st); tma_prefetch_desc(&maps.hl_st);
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * EPI_WARPS); }
+    for (int s = 0; s < 2 * MAX_N_TILES; ++s) mbar_init(h1_bar(0, s), 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // both CTAs' barriers are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      auto stage_wait = [&]() {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        // the leader arms its full barrier with the bytes of BOTH CTAs' loads for this stage
+        if (leader_cta) mbar_expect_tx(full_bar(stage), 2u * (A_BYTES + b_bytes));
+      };
+      auto stage_next = [&]() { if (++stage == P_STAGES) { stage = 0; phase ^= 1u; } };
+      auto load_g1 = [&](int s) {
+        const int mt = tile_of(s);
+        const int img = mt / p.tiles_per_image, n0 = (mt - img * p.tiles_per_image) * BLOCK_M;
+        for (int nt = 0; nt < p.n_tiles; ++nt)
+          for (int pass = 0; pass < p.l1_passes; ++pass)
+            for (int kb = 0; kb < kblocks; ++kb) {
+              stage_wait();
+              const uint32_t sa = base + stage * P_STAGE_BYTES, sb = sa + A_BYTES;
+              tma_load_3d_pair(sa, &maps.x, full_bar(stage), n0, kb * BLOCK_K, img, L2_EVICT_FIRST);
+              tma_load_3d_pair(sa + A_BYTES / 2, &maps.x, full_bar(stage), n0 + 64, kb * BLOCK_K, img, L2_EVICT_FIRST);
+              tma_load_2d_pair(sb, pass == 1 ? &maps.w1l : &maps.w1h, full_bar(stage), kb * BLOCK_K,
+                               nt * p.NT + static_cast<int>(rank) * half_nt, L2_EVICT_LAST);
+              stage_next();
+            }
+      };
+      auto load_g2 = [&](int s) {
+        const int l2_passes = p.h_f16 ? 1 : 3;
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
+          int ready = -1;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            if (nt == 0)
+              for (const int need = dep_of_kb(kb); ready < need;) {
+                ++ready;
+                mbar_wait(h1_bar(slot_of(s), ready), h1_parity(s));
+                fence_proxy_async_all();
+              }
+            for (int pass = 0; pass < l2_passes; ++pass) {
+              stage_wait();
+              const uint32_t sa = base + stage * P_STAGE_BYTES, sb = sa + A_BYTES;
+              tma_load_2d_pair(sa, pass == 1 ? &maps.hl_ld : &maps.hh_ld, full_bar(stage), kb * BLOCK_K, ws_row0_of(s),
+                               L2_EVICT_LAST);
+              tma_load_2d_pair(sb, pass == 2 ? &maps.w2l : &maps.w2h, full_bar(stage), kb * BLOCK_K,
+                               nt * p.NT + static_cast<int>(rank) * half_nt, L2_EVICT_LAST);
+              stage_next();
+            }
+          }
+        }
+      };
+      for_each_phase(load_g1, load_g2);
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && leader_cta) {
+      const uint32_t idesc_g1 = make_idesc(2 * BLOCK_M, p.NT, true, 1u, 1u);
+      const uint32_t idesc_g2 = make_idesc(2 * BLOCK_M, p.NT, false, p.h_f16 ? 0u : 1u, p.h_f16 ? 0u : 1u);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      auto mma_job = [&](bool g2) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MAX_NT);
+        const uint32_t idesc = g2 ? idesc_g2 : idesc_g1;
+        uint32_t accumulate = 0;
+        const int iters = (g2 ? (p.h_f16 ? 1 : 3) : p.l1_passes) * kblocks;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * P_STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = g2 ? make_desc(sa + k * (UMMA_K * 2), 16, 1024)
+                                   : make_desc(sa + k * (UMMA_K * 128), A_BYTES / 2, 1024);
+            const uint64_t db = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            tc_mma_pair(d_tmem, da, db, idesc, accumulate);
+            accumulate = 1;
+          }
+          tc_commit_pair(empty_bar(stage));       // frees the stage in both CTAs once these MMAs retire
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_pair(tfull_bar(acc));           // accumulators complete -> both CTAs' epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      };
+      for_each_phase([&](int) { for (int nt = 0; nt < p.n_tiles; ++nt) mma_job(false); },
+                     [&](int) { for (int nt = 0; nt < p.n_tiles; ++nt) mma_job(true); });
+    }
+  } else {
+    // ===================================================================== epilogue (8 warps, both CTAs)
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;
+    const int half = (warp - 2) >> 2;
+    const int n_chunks = p.NT / 32;
+    const int c_split = (n_chunks + 1) / 2;
+    const uint32_t sbuf = stage_out + static_cast<uint32_t>(half * 16384);
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); };
+    int acc = 0; uint32_t acc_phase = 0;
+    int store_ctr = 0;
+    float logit = 0.f;
+    auto epi_job = [&](bool g2, int s, int nt) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(acc * MAX_NT);
+      if (!g2) {
+        const int c_begin = half == 0 ? 0 : c_split, c_end = half == 0 ? c_split : n_chunks;
+        for (int ch = c_begin; ch < c_end; ++ch) {
+          const int c0 = ch * 32;
+          uint32_t r[32];
+          tc_ld32(taddr + c0, r);
+          tc_ld_wait();
+          uint32_t hi[16], lo[16];
+          if (p.h_f16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __half2 h2 = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * j]), 0.f),
+                                                   fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
+              hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              lo[j] = 0u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = fmaxf(__uint_as_float(r[2 * j]), 0.f), b = fmaxf(__uint_as_float(r[2 * j + 1]), 0.f);
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+              const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hb << 16),
+                                                              b - __uint_as_float(hb & 0xffff0000u));
+              hi[j] = hb;
+              lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+          }
+          const int col = nt * p.NT + c0;
+          auto stage_and_store = [&](const uint32_t (&vals)[16], const CUtensorMap* map) {
+            const uint32_t buf = sbuf + static_cast<uint32_t>((store_ctr & 1) * 8192);
+            ++store_ctr;
+            if (leader) tma_store_wait_read<1>();
+            group_sync();
+            const uint32_t rbase = buf + static_cast<uint32_t>(row) * 64u;
+            const uint32_t sw = static_cast<uint32_t>((row >> 1) & 3);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(rbase + ((static_cast<uint32_t>(q) ^ sw) << 4), vals[4 * q], vals[4 * q + 1], vals[4 * q + 2],
+                           vals[4 * q + 3]);
+            fence_async_smem();
+            group_sync();
+            if (leader) {
+              tma_store_2d(map, buf, col, ws_row0_of(s), L2_EVICT_LAST);
+              tma_store_commit();
+            }
+          };
+          stage_and_store(hi, &maps.hh_st);
+          if (!p.h_f16) stage_and_store(lo, &maps.hl_st);
+        }
+      } else if (half == 0) {
+        if (nt == 0) logit = 0.f;
+        for (int c0 = 0; c0 < p.NT; c0 += 32) {
+          uint32_t r[32];
+          tc_ld32(taddr + c0, r);
+          tc_ld_wait();
+          const float4* wv = reinterpret_cast<const float4*>(p.w3 + nt * p.NT + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w4 = __ldg(wv + j);
+            logit = fmaf(w4.x, fmaxf(__uint_as_float(r[4 * j + 0]), 0.f), logit);
+            logit = fmaf(w4.y, fmaxf(__uint_as_float(r[4 * j + 1]), 0.f), logit);
+            logit = fmaf(w4.z, fmaxf(__uint_as_float(r[4 * j + 2]), 0.f), logit);
+            logit = fmaf(w4.w, fmaxf(__uint_as_float(r[4 * j + 3]), 0.f), logit);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));   // 16 arrivals (8 warps x 2 CTAs) on the leader's barrier
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (!g2) {
+        if (leader) {
+          tma_store_wait_all();
+          fence_proxy_async_all();
+          mbar_arrive(h1_bar(slot_of(s), nt));
+        }
+        __syncwarp();
+      }
+      if (g2 && half == 0 && nt == p.n_tiles - 1 && tile_raw(s) < p.m_tiles) {
+        const int mt = tile_raw(s);
+        const int img = mt / p.tiles_per_image;
+        const int n = (mt - img * p.tiles_per_image) * BLOCK_M + row;
+        p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
+      }
+    };
+    for_each_phase([&](int s) { for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(false, s, nt); },
+                   [&](int s) { for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(true, s, nt); });
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // the peer's shared memory and TMEM stay alive until both CTAs are done
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 // s_hat [K][C] -> [C][KP] (zero padded) for the projection warps' 128-bit uniform loads
 __global__ void transpose_protos_kernel(const float* __restrict__ s_hat, int K, int C, int KP, float* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -595,6 +913,26 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
     cuuint32_t sbox[2] = {32, BLOCK_M};
     if ((rc = make_map(&m.hh_st, h_hi, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if ((rc = make_map(&m.hl_st, h_lo, 2, dims, sbox, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  }
+  // cta_group::2 variant for the background-only launch: a CTA pair shares every weight tile
+  {
+    const char* pe = getenv("SL_TC_PAIR");
+    const bool use_pair = KQ == 0 && p.m_tiles >= 2 && (pe == nullptr || atoi(pe) != 0);
+    if (use_pair) {
+      // each CTA loads half of B: box rows = NT/2
+      cuuint64_t wdims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(C)};
+      cuuint32_t wbox[2] = {BLOCK_K, static_cast<cuuint32_t>(p.NT / 2)};
+      if ((rc = make_map(&m.w1h, W1p_hi, 2, wdims, wbox))) return rc;
+      if ((rc = make_map(&m.w1l, W1p_lo, 2, wdims, wbox))) return rc;
+      if ((rc = make_map(&m.w2h, W2_hi, 2, wdims, wbox))) return rc;
+      if ((rc = make_map(&m.w2l, W2_lo, 2, wdims, wbox))) return rc;
+      const int pair_tiles = (p.m_tiles + 1) / 2;
+      int pgrid = 2 * (pair_tiles < sl::kNumSMs / 2 ? pair_tiles : sl::kNumSMs / 2);
+      cudaError_t pe2 = cudaFuncSetAttribute(bg_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+      if (pe2 != cudaSuccess) return static_cast<int>(pe2);
+      bg_pair_kernel<<<pgrid, THREADS, P_SMEM_BYTES, st>>>(m, p);
+      return SL_LAUNCH_RESULT();
+    }
   }
   if (KQ > 0) transpose_protos_kernel<<<(C * 4 * KQ + 255) / 256, 256, 0, st>>>(s_hat, K, C, 4 * KQ, s_hat_t);
   cudaError_t e = cudaSuccess;
