@@ -128,6 +128,25 @@ SL_API int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
                  const uint16_t *W2_hi, const uint16_t *W2_lo,
                  const uint16_t *W2_f16, const float *w3_bg, int precision, uint16_t *h1_ws, float *logits, int Ktot, int ch, void *stream);
 
+/* Backward of the POP head for training: the per-pixel part of autograd through
+ * forward_novel / forward_base (networks/pspnet_pop.py:191-219, :161-189), i.e. through
+ * orthogonal_decompose (:95-121) and classifier / classifier_n (:46-63), in exact fp32 on the CUDA cores.
+ * Inputs are the forward's operands -- features, s_hat [K,C], alpha / beta [K], the FOLDED first layer
+ * W1p = W1 (I - S_hat^T S_hat) [C_out][C_in] row-major, W2 [C,C], w3 [C] of the background MLP -- and
+ * g_logits [B,Ktot,N] = dL/dlogits in the forward's channel layout (fg_ch[k] = channel of class k, bg_ch).
+ * Outputs (overwritten): d_s_hat [K,C] (through the projections p_k = s_hat_k . q only; the dependence of
+ * W1p on s_hat is differentiated by the caller from dW1p), d_alpha, d_beta [K], dW1p, dW2 [C,C], dw3 [C] and,
+ * when d_feat != NULL, dL/dfeatures [B,C,N] fp32.  Activations are recomputed; ws holds them
+ * (sl_pop_head_bwd_ws_bytes, 16-byte aligned).  C % 8 == 0, C <= 512, N % 8 == 0, B*N < 2^31.
+ */
+SL_API size_t sl_pop_head_bwd_ws_bytes(int B, int C, int N, int K);
+SL_API int sl_pop_head_bwd(const uint16_t *feat, int B, int C, int N,
+                    const float *s_hat, const float *alpha, const float *beta, int K, const int *fg_ch_host,
+                    const float *W1p, const float *W2, const float *w3,
+                    const float *g_logits, int Ktot, int bg_ch,
+                    float *d_s_hat, float *d_alpha, float *d_beta, float *dW1p, float *dW2, float *dw3,
+                    float *d_feat, void *ws, void *stream);
+
 /* The whole POP head in one launch (tensor-core path): sl_pop_bg_tc with the K <= 12 foreground logits of
  * sl_pop_fg_lowres computed by extra warps from the feature tiles already staged for the MMAs, so the
  * features are read from HBM once.  Arguments as in the two calls it replaces; ch_map_host[k] is the

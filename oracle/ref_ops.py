@@ -197,6 +197,31 @@ def ref_seg_ce(preds, target, ignore_index=IGNORE_LABEL):
     return torch.nn.CrossEntropyLoss(ignore_index=ignore_index, reduction='mean')(scale_pre, target)
 
 
+def ref_orth_loss_forward(preds, target, proto_sim, w=10.0, ignore_index=IGNORE_LABEL):
+    """OrthLoss.forward without aux head, loss/criterion.py:45-65 (self.w = 10.0, :35)."""
+    seg_loss = ref_seg_ce(preds, target, ignore_index)
+    orth_loss = ref_orth_loss(proto_sim)
+    return {'total_loss': seg_loss + orth_loss * w, 'seg_loss': seg_loss, 'orth_loss': orth_loss}
+
+
+def ref_forward_novel(features_full, mask, mask_b, base_emb, novel_emb, cls, cls_n):
+    """forward_novel after the decoder with its criterion, pspnet_pop.py:199-243, differentiable by
+    autograd in the reference's materialising formulation.  features_full [B,C,h,w] = [novel images;
+    base images]; mask [B/2,H,W] int64; mask_b [B/2,H,W] int64 is pseudo-labelled IN PLACE (:221-231)."""
+    preds = ref_head_all(features_full, base_emb, novel_emb, cls, cls_n)
+    B, n_base = preds.shape[0], base_emb.shape[0]
+    preds2 = torch.cat([preds[:, :1], preds[:, 1 + n_base:]], dim=1)
+    mask_new = ref_pseudo_label(preds2[B // 2:].detach(), mask_b, n_base)
+    mask_all = torch.cat([mask, mask_new], dim=0)
+    return ref_orth_loss_forward(preds, mask_all, ref_proto_sim_ft(novel_emb, base_emb)), preds
+
+
+def ref_forward_base_loss(features, mask, base_emb, cls):
+    """forward_base with a criterion, pspnet_pop.py:169-187."""
+    preds = ref_head_base(features, base_emb, cls)
+    return ref_orth_loss_forward(preds, mask, ref_proto_sim_base(base_emb)), preds
+
+
 # --------------------------------------------------------------------------- fusion
 def ref_fuse(mats, n_lists=None):
     """fusemat.py:42-48 for ONE tile: sequential += in directory order, / len(fusion_list),

@@ -22,6 +22,7 @@ _SIGNATURES = {
     'sl_pop_bg_tc': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, _P],
     'sl_pop_head_tc': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_int, POINTER(c_int), _P, _P,
                        c_int, c_int, _P],
+    'sl_pop_head_bwd': [_P, c_int, c_int, c_int, _P, _P, _P, c_int, POINTER(c_int), _P, _P, _P, _P, c_int, c_int] + [_P] * 9,
     'sl_views_reduce': [_P, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_float, _P, _P],
     'sl_upsample_argmax': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P],
     'sl_pseudo_label': [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
@@ -60,6 +61,8 @@ def lib():
         handle.sl_error_string.restype = c_char_p
         handle.sl_pop_bg_tc_ws_bytes.argtypes = [c_int, c_int, c_int]
         handle.sl_pop_bg_tc_ws_bytes.restype = c_size_t
+        handle.sl_pop_head_bwd_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        handle.sl_pop_head_bwd_ws_bytes.restype = c_size_t
         handle.sl_pop_prepare_ws_bytes.argtypes = [c_int, c_int]
         handle.sl_pop_prepare_ws_bytes.restype = c_size_t
         handle.sl_upsample_ce_ws_bytes.argtypes = [c_int, c_int, c_int]
@@ -71,7 +74,8 @@ def lib():
 
 
 def exported_names():
-    return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes', 'sl_pop_prepare_ws_bytes', 'sl_upsample_ce_ws_bytes']
+    return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes', 'sl_pop_prepare_ws_bytes', 'sl_upsample_ce_ws_bytes',
+                                     'sl_pop_head_bwd_ws_bytes']
 
 
 def call(name, *args):

@@ -236,6 +236,129 @@ class PopHead:
     forward = __call__
 
 
+# ==================================================================== POP head, training mode
+def _split_bf16(W):
+    """fp32 -> (hi, lo) bf16 bit patterns with hi + lo ~ W to 16 mantissa bits (round-to-nearest both)."""
+    hi = W.to(torch.bfloat16)
+    lo = (W - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi.view(torch.int16), lo.view(torch.int16)
+
+
+class _PopHeadFn(torch.autograd.Function):
+    """logits = head(features) with the forward's operands as explicit (differentiable) inputs; the backward is
+    sl_pop_head_bwd.  Forward kernels are the eval ones (sl_pop_fg_lowres + sl_pop_bg_tc / sl_pop_bg_simt)."""
+
+    @staticmethod
+    def forward(ctx, features, s_hat, alpha, beta, W1p, W2, w3, bg_mode):
+        feats = features.detach().to(torch.bfloat16).contiguous()
+        B, C, h, w = feats.shape
+        N, K = h * w, s_hat.shape[0]
+        Ktot = 1 + K
+        dev = feats.device
+        s_hat, alpha, beta = (t.detach().to(torch.float32).contiguous() for t in (s_hat, alpha, beta))
+        W1p, W2, w3 = (t.detach().to(torch.float32).contiguous() for t in (W1p, W2, w3))
+        out = torch.empty(B, Ktot, h, w, dtype=torch.float32, device=dev)
+        ch_map = int_array([1 + k for k in range(K)])
+        st = _stream()
+        call('sl_pop_fg_lowres', ptr(feats), B, C, N, ptr(s_hat), ptr(alpha), ptr(beta), K, ptr(out), Ktot, ch_map, st)
+        use_tc = bg_mode != 'simt' and C % 32 == 0 and 32 <= C <= 512 and N % 128 == 0
+        if bg_mode == 'tc' and not use_tc:
+            raise ValueError(f'bg_mode="tc" needs C % 32 == 0, C <= 512, N % 128 == 0 (C={C}, N={N})')
+        if use_tc:
+            w1h, w1l = _split_bf16(W1p)
+            w2h, w2l = _split_bf16(W2)
+            ws = torch.empty(_cabi.lib().sl_pop_bg_tc_ws_bytes(B, C, N) // 2, dtype=torch.int16, device=dev)
+            call('sl_pop_bg_tc', ptr(feats), B, C, N, ptr(w1h), ptr(w1l), ptr(w2h), ptr(w2l), ptr(w2h), ptr(w3), 0,
+                 ptr(ws), ptr(out), Ktot, 0, st)
+        else:
+            W1t, W2t = W1p.t().contiguous(), W2.t().contiguous()     # [C_in][C_out]; both alive until the launch
+            call('sl_pop_bg_simt', ptr(feats), B, C, N, ptr(W1t), ptr(W2t), ptr(w3), ptr(out), Ktot, 0, st)
+        ctx.save_for_backward(feats, s_hat, alpha, beta, W1p, W2, w3)
+        ctx.feat_dtype = features.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, s_hat, alpha, beta, W1p, W2, w3 = ctx.saved_tensors
+        B, C, h, w = feats.shape
+        N, K = h * w, s_hat.shape[0]
+        dev = feats.device
+        g = g.to(torch.float32).contiguous()
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        d_s, d_a, d_b, dW1p, dW2, dw3 = new(K, C), new(K), new(K), new(C, C), new(C, C), new(C)
+        d_feat = new(B, C, h, w) if ctx.needs_input_grad[0] else None
+        ws = torch.empty(_cabi.lib().sl_pop_head_bwd_ws_bytes(B, C, N, K) // 4, dtype=torch.float32, device=dev)
+        call('sl_pop_head_bwd', ptr(feats), B, C, N, ptr(s_hat), ptr(alpha), ptr(beta), K,
+             int_array([1 + k for k in range(K)]), ptr(W1p), ptr(W2), ptr(w3), ptr(g), 1 + K, 0,
+             ptr(d_s), ptr(d_a), ptr(d_b), ptr(dW1p), ptr(dW2), ptr(dw3), ptr(d_feat), ptr(ws), _stream())
+        if d_feat is not None and ctx.feat_dtype != torch.float32:
+            d_feat = d_feat.to(ctx.feat_dtype)
+        return d_feat, d_s, d_a, d_b, dW1p, dW2, dw3, None
+
+
+def _mlp3(x, W1, W2, w3):
+    return torch.relu(torch.relu(x @ W1.t()) @ W2.t()) @ w3
+
+
+def pop_head_train(features, base_emb, classifier, novel_emb=None, classifier_n=None, bg_mode='auto'):
+    """The head of forward_novel / forward_base with autograd (networks/pspnet_pop.py:199-219, :169-182):
+    features [B,C,h,w] (any float dtype; cast to bf16 for the kernels, gradients flow back if it requires
+    grad), base_emb [Kb,C], classifier = (W1, W2, w3) conv weights, and for ft mode novel_emb [Kn,C] +
+    classifier_n.  Returns preds [B,1+Kb(+Kn),h,w] fp32 in the reference's channel order.  Every per-pixel
+    operation, forward and backward, runs in libsegland_b200.so; the parameter-side chain -- F.normalize of
+    the prototypes (pspnet_pop.py:106,111), alpha/beta = MLP(+-s_hat) and the fold W1 (I - S^T S), all
+    O(K C^2) on [K,C] / [C,C] tensors -- is differentiated by PyTorch."""
+    check_device()
+    C = base_emb.shape[1]
+    Kb = base_emb.shape[0]
+    ft = novel_emb is not None and novel_emb.shape[0] > 0
+    mats = lambda ws: (ws[0].reshape(C, C).float(), ws[1].reshape(C, C).float(), ws[2].reshape(C).float())
+    with torch.autocast('cuda', enabled=False):
+        protos = torch.cat([base_emb, novel_emb], 0) if ft else base_emb
+        s_hat = torch.nn.functional.normalize(protos.to(torch.float32), p=2, dim=-1)
+        fg = mats(classifier)
+        bg = mats(classifier_n) if ft else fg
+        alpha, beta = _mlp3(s_hat[:Kb], *fg), _mlp3(-s_hat[:Kb], *fg)
+        if ft:
+            alpha = torch.cat([alpha, _mlp3(s_hat[Kb:], *bg)])
+            beta = torch.cat([beta, _mlp3(-s_hat[Kb:], *bg)])
+        W1p = bg[0] - (bg[0] @ s_hat.t()) @ s_hat
+        return _PopHeadFn.apply(features, s_hat, alpha, beta, W1p, bg[1], bg[2], bg_mode)
+
+
+def forward_novel_train(features_full, mask, mask_b, base_emb, novel_emb, classifier, classifier_n, criterion=None,
+                        bg_mode='auto'):
+    """forward_novel after the decoder (networks/pspnet_pop.py:199-245): head on [novel; base] images,
+    pseudo-labelling of the base images' background with classifier_n's argmax (IN PLACE on mask_b, :221-231),
+    then criterion(preds, cat(mask, mask_b), is_ft=True, proto_sim) or preds when there is no criterion/mask."""
+    Kb = base_emb.shape[0]
+    preds = pop_head_train(features_full, base_emb, classifier, novel_emb, classifier_n, bg_mode)
+    B = preds.shape[0]
+    with torch.no_grad():
+        preds2_base = torch.cat([preds[B // 2:, :1], preds[B // 2:, 1 + Kb:]], dim=1).contiguous()
+        if mask_b.shape[0] != B // 2:
+            raise ValueError('mask_b must hold one mask per base image (the second half of the batch)')
+        mask_new = pseudo_label(preds2_base, mask_b, Kb)
+    if criterion is None or mask is None:
+        return preds
+    with torch.autocast('cuda', enabled=False):
+        C = base_emb.shape[1]
+        mask_all = torch.cat([mask, mask_new], dim=0)
+        n_hat = torch.nn.functional.normalize(novel_emb.to(torch.float32), p=2, dim=-1).reshape(-1, C)
+        all_emb = torch.cat([n_hat, torch.nn.functional.normalize(base_emb.to(torch.float32), p=2, dim=-1)], dim=0)
+        proto_sim = torch.matmul(n_hat, all_emb.t())
+        return criterion(preds.to(torch.float32), mask_all, is_ft=True, proto_sim=proto_sim)
+
+
+def forward_base_train(features, mask, base_emb, classifier, criterion=None, bg_mode='auto'):
+    """forward_base after the decoder with autograd (networks/pspnet_pop.py:169-189)."""
+    preds = pop_head_train(features, base_emb, classifier, None, None, bg_mode)
+    if criterion is None or mask is None:
+        return preds
+    cls_emb = torch.nn.functional.normalize(base_emb, p=2, dim=-1)
+    return criterion(preds, mask, proto_sim=torch.matmul(cls_emb, cls_emb.t()))
+
+
 def aggregate_views(views, flips, scale=None):
     """Test-time view aggregation (spec: this repo; the reference has none).
     views [V,B,K,h,w] fp32 logits of V views of the same tiles; flips[v] in {0,1,2,3}

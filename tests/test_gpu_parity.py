@@ -642,3 +642,109 @@ def test_fused_head_matches_two_launch_path(ops):
         assert_close_rel(one[:, 1:].cpu(), two[:, 1:].cpu(), 1e-5, f'fused fg C={C}')
         ref = ref_ops.ref_head(feats.cpu().float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
         assert_close_rel(one.cpu(), ref, RTOL, f'fused head C={C}')
+
+
+# ------------------------------------------------------------------- training mode
+GRAD_RTOL = 1e-3          # gradients: within 1e-3 of the reference's autograd, relative to each tensor's max / rms
+
+
+def _crit(ops):
+    return lambda preds, target, is_ft=False, proto_sim=None: ops.orth_loss_forward(preds, target, is_ft, proto_sim)
+
+
+@pytest.mark.parametrize('name', ['ft_c64', 'ft_c64b', 'ft_c96'])
+@pytest.mark.parametrize('bg_mode', ['auto', 'simt'])
+def test_forward_novel_train_vs_golden(ops, golden, name, bg_mode):
+    """forward_novel + OrthLoss + backward on the CUDA path == the reference's autograd (golden)."""
+    z = golden('train_grads')
+    st = state_from_npz(z, name + '_').to('cuda')
+    req = lambda t: t.clone().requires_grad_(True)
+    novel, cls, cls_n = req(st.novel_emb), tuple(req(t) for t in st.cls), tuple(req(t) for t in st.cls_n)
+    img_n = req(bf16_from_bits(z[name + '_img_n_bits']).float().cuda())
+    img_b = req(bf16_from_bits(z[name + '_img_b_bits']).float().cuda())
+    mask_n = torch.from_numpy(z[name + '_mask_n']).cuda()
+    mask_b = torch.from_numpy(z[name + '_mask_b_before'].copy()).cuda()
+    # (1) the whole forward_novel: pseudo-labels (in place) and the loss dict.  The pseudo-labels are an argmax of
+    # OUR logits, so a near-tie pixel may legitimately flip: >= 99.9 % agreement, losses within 1e-3.
+    loss = ops.forward_novel_train(torch.cat([img_n, img_b], 0), mask_n, mask_b, st.base_emb, novel, cls, cls_n,
+                                   criterion=_crit(ops), bg_mode=bg_mode)
+    after = torch.from_numpy(z[name + '_mask_b_after'])
+    agree = (mask_b.cpu() == after).float().mean().item()
+    assert agree >= 0.999, f'pseudo-label agreement {agree}'
+    untouched = torch.from_numpy(z[name + '_mask_b_before']) != 0
+    assert torch.equal(mask_b.cpu()[untouched], after[untouched])                   # labelled pixels never change
+    for key in ('total', 'seg', 'orth'):
+        assert abs(loss[key + '_loss'].item() - float(z[f'{name}_{key}'])) <= 1e-3 * abs(float(z[f'{name}_{key}'])), key
+    # (2) gradients with the reference's own pseudo-labels, so that every pixel sees the same target
+    for t in (novel, *cls, *cls_n, img_n, img_b):
+        t.grad = None
+    preds = ops.pop_head_train(torch.cat([img_n, img_b], 0), st.base_emb, cls, novel, cls_n, bg_mode=bg_mode)
+    n_hat = F.normalize(novel, p=2, dim=-1)
+    sim = n_hat @ torch.cat([n_hat, F.normalize(st.base_emb, p=2, dim=-1)], 0).t()
+    loss = ops.orth_loss_forward(preds, torch.cat([mask_n, after.cuda()], 0), True, sim)
+    for key in ('total', 'seg', 'orth'):
+        assert abs(loss[key + '_loss'].item() - float(z[f'{name}_{key}'])) <= 1e-4 * abs(float(z[f'{name}_{key}'])), key
+    loss['total_loss'].backward()
+    got = [novel, *cls, *cls_n, img_n, img_b]
+    want = ['g_novel_emb', 'g_W1', 'g_W2', 'g_w3', 'g_W1n', 'g_W2n', 'g_w3n', 'g_img_n', 'g_img_b']
+    for t, key in zip(got, want):
+        ref = torch.from_numpy(z[f'{name}_{key}']).reshape(t.shape)
+        assert_close_rel(t.grad.cpu(), ref, GRAD_RTOL, f'{name}/{bg_mode} {key}')
+
+
+def test_forward_base_train_vs_golden(ops, golden):
+    z = golden('train_grads')
+    st = state_from_npz(z, 'base_c64_').to('cuda')
+    req = lambda t: t.clone().requires_grad_(True)
+    base, cls = req(st.base_emb), tuple(req(t) for t in st.cls)
+    img = req(bf16_from_bits(z['base_c64_img_bits']).float().cuda())
+    loss = ops.forward_base_train(img, torch.from_numpy(z['base_c64_mask']).long().cuda(), base, cls, criterion=_crit(ops))
+    for key in ('total', 'seg', 'orth'):
+        assert abs(loss[key + '_loss'].item() - float(z[f'base_c64_{key}'])) <= 1e-4 * abs(float(z[f'base_c64_{key}'])), key
+    loss['total_loss'].backward()
+    for t, key in zip([base, *cls, img], ['g_base_emb', 'g_W1', 'g_W2', 'g_w3', 'g_img']):
+        ref = torch.from_numpy(z[f'base_c64_{key}']).reshape(t.shape)
+        assert_close_rel(t.grad.cpu(), ref, GRAD_RTOL, f'base_c64 {key}')
+
+
+@pytest.mark.parametrize('C,Kb,Kn,hw', [(512, 7, 4, (32, 32)), (192, 7, 4, (24, 40)), (480, 5, 2, (16, 16))])
+def test_head_backward_vs_oracle_autograd(ops, C, Kb, Kn, hw):
+    """Head forward + backward at real widths against autograd through the oracle's materialising head,
+    with a random upstream gradient (no loss in between)."""
+    st = synth.make_head_state(C, Kb, Kn, seed=7 + C)
+    gen = torch.Generator().manual_seed(C)
+    h, w = hw
+    feats = synth.make_random_features(2, C, h, w, seed=C).float()
+    g_out = torch.randn(2, 1 + Kb + Kn, h, w, generator=gen)
+    req = lambda t: t.clone().requires_grad_(True)
+
+    def run(dev, fn):
+        novel = req(st.novel_emb.to(dev))
+        cls, cls_n = tuple(req(t.to(dev)) for t in st.cls), tuple(req(t.to(dev)) for t in st.cls_n)
+        f = req(feats.to(dev))
+        out = fn(f, st.base_emb.to(dev), novel, cls, cls_n)
+        out.backward(g_out.to(dev))
+        return out.detach().cpu(), [t.grad.cpu() for t in (novel, *cls, *cls_n, f)]
+
+    out_ref, g_ref = run('cpu', lambda f, b, n, c, cn: ref_ops.ref_head_all(f, b, n, c, cn))
+    out, g = run('cuda', lambda f, b, n, c, cn: ops.pop_head_train(f, b, c, n, cn))
+    assert_close_rel(out, out_ref, RTOL, 'train forward logits')
+    for a, b, key in zip(g, g_ref, ['novel_emb', 'W1', 'W2', 'w3', 'W1n', 'W2n', 'w3n', 'features']):
+        assert_close_rel(a, b, GRAD_RTOL, f'C={C} grad {key}')
+
+
+def test_head_backward_skips_feature_grad_and_is_deterministic_in_structure(ops):
+    """needs_input_grad[0] == False -> no d_feat buffer; parameter grads unchanged."""
+    st = synth.make_head_state(64, 7, 4, seed=3).to('cuda')
+    feats = synth.make_random_features(2, 64, 16, 16, seed=3).cuda()
+    g_out = torch.randn(2, 12, 16, 16, device='cuda')
+    grads = []
+    for need in (False, True):
+        novel = st.novel_emb.clone().requires_grad_(True)
+        cls_n = tuple(t.clone().requires_grad_(True) for t in st.cls_n)
+        f = feats.float().requires_grad_(need)
+        ops.pop_head_train(f, st.base_emb, st.cls, novel, cls_n).backward(g_out)
+        assert (f.grad is not None) == need
+        grads.append([novel.grad.clone()] + [t.grad.clone() for t in cls_n])
+    for a, b in zip(*grads):
+        assert_close_rel(a.cpu(), b.cpu(), 1e-5, 'param grads independent of d_feat')

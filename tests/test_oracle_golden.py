@@ -106,3 +106,44 @@ def test_seg_ce(golden):
         assert loss.item() == float(z[f'loss{i}'])
         loss.backward()
         assert np.array_equal(preds.grad.numpy(), z[f'grad{i}'])
+
+
+def _grads_of(loss, tensors):
+    gs = torch.autograd.grad(loss, tensors, allow_unused=True)
+    return [None if g is None else g.detach() for g in gs]
+
+
+@pytest.mark.parametrize('name', ['ft_c64', 'ft_c64b', 'ft_c96'])
+def test_forward_novel_gradients(golden, name):
+    """Oracle forward_novel + OrthLoss + autograd == the reference's (train mode, identity backbone)."""
+    z = golden('train_grads')
+    st = state_from_npz(z, name + '_')
+    req = lambda t: t.clone().requires_grad_(True)
+    novel, cls, cls_n = req(st.novel_emb), tuple(req(t) for t in st.cls), tuple(req(t) for t in st.cls_n)
+    img_n, img_b = req(bf16_from_bits(z[name + '_img_n_bits']).float()), req(bf16_from_bits(z[name + '_img_b_bits']).float())
+    mask_b = torch.from_numpy(z[name + '_mask_b_before'].copy())
+    loss, _ = ref_ops.ref_forward_novel(torch.cat([img_n, img_b], 0), torch.from_numpy(z[name + '_mask_n']), mask_b,
+                                        st.base_emb, novel, cls, cls_n)
+    assert np.array_equal(mask_b.numpy(), z[name + '_mask_b_after'])
+    for key in ('total', 'seg', 'orth'):
+        assert abs(loss[key + '_loss'].item() - float(z[f'{name}_{key}'])) < 2e-6, key
+    got = _grads_of(loss['total_loss'], [novel, *cls, *cls_n, img_n, img_b])
+    want = ['g_novel_emb', 'g_W1', 'g_W2', 'g_w3', 'g_W1n', 'g_W2n', 'g_w3n', 'g_img_n', 'g_img_b']
+    for g, key in zip(got, want):
+        ref = torch.from_numpy(z[f'{name}_{key}']).reshape(g.shape)
+        assert (g - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-9, key
+
+
+def test_forward_base_gradients(golden):
+    z = golden('train_grads')
+    st = state_from_npz(z, 'base_c64_')
+    req = lambda t: t.clone().requires_grad_(True)
+    base, cls = req(st.base_emb), tuple(req(t) for t in st.cls)
+    img = req(bf16_from_bits(z['base_c64_img_bits']).float())
+    loss, _ = ref_ops.ref_forward_base_loss(img, torch.from_numpy(z['base_c64_mask']).long(), base, cls)
+    for key in ('total', 'seg', 'orth'):
+        assert abs(loss[key + '_loss'].item() - float(z[f'base_c64_{key}'])) < 2e-6, key
+    got = _grads_of(loss['total_loss'], [base, *cls, img])
+    for g, key in zip(got, ['g_base_emb', 'g_W1', 'g_W2', 'g_w3', 'g_img']):
+        ref = torch.from_numpy(z[f'base_c64_{key}']).reshape(g.shape)
+        assert (g - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-9, key
