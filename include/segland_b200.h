@@ -137,15 +137,20 @@ SL_API int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
  * Outputs (overwritten): d_s_hat [K,C] (through the projections p_k = s_hat_k . q only; the dependence of
  * W1p on s_hat is differentiated by the caller from dW1p), d_alpha, d_beta [K], dW1p, dW2 [C,C], dw3 [C] and,
  * when d_feat != NULL, dL/dfeatures [B,C,N] fp32.  Activations are recomputed; ws holds them
- * (sl_pop_head_bwd_ws_bytes, 16-byte aligned).  C % 8 == 0, C <= 512, N % 8 == 0, B*N < 2^31.
+ * (sl_pop_head_bwd_ws_bytes, 128-byte aligned).  C % 8 == 0, C <= 512, N % 8 == 0, B*N < 2^31.
+ * mode: SL_BWD_AUTO runs the GEMMs on tcgen05 as split-bf16 products (2-3 passes, fp32 accumulation, ~1e-5 of
+ *       fp32; C >= 32) and falls back to the exact CUDA-core SGEMMs for narrower heads; SL_BWD_SIMT forces
+ *       the exact fp32 path.
  */
+#define SL_BWD_AUTO 0
+#define SL_BWD_SIMT 1
 SL_API size_t sl_pop_head_bwd_ws_bytes(int B, int C, int N, int K);
 SL_API int sl_pop_head_bwd(const uint16_t *feat, int B, int C, int N,
                     const float *s_hat, const float *alpha, const float *beta, int K, const int *fg_ch_host,
                     const float *W1p, const float *W2, const float *w3,
                     const float *g_logits, int Ktot, int bg_ch,
                     float *d_s_hat, float *d_alpha, float *d_beta, float *dW1p, float *dW2, float *dw3,
-                    float *d_feat, void *ws, void *stream);
+                    float *d_feat, int mode, void *ws, void *stream);
 
 /* The whole POP head in one launch (tensor-core path): sl_pop_bg_tc with the K <= 12 foreground logits of
  * sl_pop_fg_lowres computed by extra warps from the feature tiles already staged for the MMAs, so the

@@ -22,7 +22,8 @@ _SIGNATURES = {
     'sl_pop_bg_tc': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, _P],
     'sl_pop_head_tc': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_int, POINTER(c_int), _P, _P,
                        c_int, c_int, _P],
-    'sl_pop_head_bwd': [_P, c_int, c_int, c_int, _P, _P, _P, c_int, POINTER(c_int), _P, _P, _P, _P, c_int, c_int] + [_P] * 9,
+    'sl_pop_head_bwd': [_P, c_int, c_int, c_int, _P, _P, _P, c_int, POINTER(c_int), _P, _P, _P, _P, c_int, c_int] + [_P] * 7
+                       + [c_int, _P, _P],
     'sl_views_reduce': [_P, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_float, _P, _P],
     'sl_upsample_argmax': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P],
     'sl_pseudo_label': [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],

@@ -237,18 +237,28 @@ __global__ void __launch_bounds__(256) dw3_kernel(const float* __restrict__ h2, 
 }  // namespace bwd
 }  // namespace sl
 
+// tensor-core GEMM chain (pop_bwd_tc.cu)
+int sl_pop_bwd_flag_cap(long long px, int C);
+int sl_pop_bwd_tc_run(const uint16_t* feat, int B, int C, int N, const float* s_hat, int K, const float* W1p, const float* W2,
+                      const float* w3, const float* g_logits, int Ktot, int bg_ch, const float* gp, float* dW1p,
+                      float* dW2, float* dw3, float* d_feat, uint16_t* act, uint16_t* wsplit, cudaStream_t st);
+
 extern "C" size_t sl_pop_head_bwd_ws_bytes(int B, int C, int N, int K) {
   if (B < 1 || C < 1 || N < 1 || K < 1) return 0;
   const size_t px = static_cast<size_t>(B) * N;
-  // p, gp [B,K,N]; h1, dz2, dz1 [B*N, C]; +-1 coefficient vectors
-  return (2 * px * K + 3 * px * C + 2 * SL_MAX_CLASSES) * sizeof(float) + 256;
+  // p, gp [B,K,N] fp32; h1, dz2, dz1 [B*N, C] (fp32 each, or bf16 hi/lo pairs on the tensor-core path);
+  // +-1 coefficient vectors; bf16 hi/lo of W1', W2 and their transposes
+  // tensor-core path: 7 bf16 activation planes (h1 x3, dz2 x2, dz1 x2), 9 bf16 weight planes, the sign-fix-up queue
+  const size_t act = (3 * px * C * 4 > 7 * px * C * 2 ? 3 * px * C * 4 : 7 * px * C * 2);
+  return (2 * px * K + 2 * SL_MAX_CLASSES) * sizeof(float) + act + 9 * static_cast<size_t>(C) * C * 2 +
+         (static_cast<size_t>(sl_pop_bwd_flag_cap(static_cast<long long>(px), C)) + 4) * sizeof(int) + 256;
 }
 
 extern "C" int sl_pop_head_bwd(const uint16_t* feat, int B, int C, int N, const float* s_hat, const float* alpha,
                                const float* beta, int K, const int* fg_ch_host, const float* W1p, const float* W2,
                                const float* w3, const float* g_logits, int Ktot, int bg_ch, float* d_s_hat,
                                float* d_alpha, float* d_beta, float* dW1p, float* dW2, float* dw3, float* d_feat,
-                               void* ws, void* stream) {
+                               int mode, void* ws, void* stream) {
   using namespace sl::bwd;
   SL_CHECK_PTR(feat); SL_CHECK_PTR(s_hat); SL_CHECK_PTR(alpha); SL_CHECK_PTR(beta); SL_CHECK_PTR(fg_ch_host);
   SL_CHECK_PTR(W1p); SL_CHECK_PTR(W2); SL_CHECK_PTR(w3); SL_CHECK_PTR(g_logits); SL_CHECK_PTR(d_s_hat);
@@ -256,8 +266,9 @@ extern "C" int sl_pop_head_bwd(const uint16_t* feat, int B, int C, int N, const 
   SL_CHECK_ARG(B >= 1 && K >= 1 && K < SL_MAX_CLASSES && Ktot > K && Ktot <= SL_MAX_CLASSES);
   SL_CHECK_ARG(C >= 8 && C <= 512 && C % 8 == 0 && N >= 8 && N % 8 == 0);
   SL_CHECK_ARG(bg_ch >= 0 && bg_ch < Ktot);
+  SL_CHECK_ARG(mode == SL_BWD_AUTO || mode == SL_BWD_SIMT);
   SL_CHECK_ARG(static_cast<long long>(B) * N < (1ll << 31));
-  SL_CHECK_ALIGN(feat, 16); SL_CHECK_ALIGN(ws, 16);
+  SL_CHECK_ALIGN(feat, 16); SL_CHECK_ALIGN(ws, 128);
   FgChannels chs;
   for (int k = 0; k < SL_MAX_CLASSES; ++k) chs.ch[k] = 0;
   for (int k = 0; k < K; ++k) {
@@ -272,8 +283,10 @@ extern "C" int sl_pop_head_bwd(const uint16_t* feat, int B, int C, int N, const 
   float* h1 = gp + px * K;
   float* dz2 = h1 + px * C;
   float* dz1 = dz2 + px * C;          // holds h2 = relu(z2) until dw3 has been reduced
-  float* one = dz1 + px * C;
+  // +-1 vectors and the bf16 weight planes sit behind the larger (tensor-core) activation region
+  float* one = h1 + (7 * px * C * 2 + 3) / 4;
   float* neg = one + SL_MAX_CLASSES;
+  uint16_t* wsplit = reinterpret_cast<uint16_t*>(neg + SL_MAX_CLASSES);
 
   cudaMemsetAsync(d_s_hat, 0, sizeof(float) * K * C, st);
   cudaMemsetAsync(d_alpha, 0, sizeof(float) * K, st);
@@ -295,6 +308,13 @@ extern "C" int sl_pop_head_bwd(const uint16_t* feat, int B, int C, int N, const 
     fg_coef_grad_kernel<<<dim3(chunks, K, B), 256, 0, st>>>(p, g_logits, alpha, beta, K, N, Ktot, chs, gp, d_alpha, d_beta);
   }
   const FeatPxCh fq{feat, C, N};
+  if (mode == SL_BWD_AUTO && C >= 32) {
+    // d_s_hat[k][c] = sum_px gp[k][px] q[px][c]  (K rows only: stays on the CUDA cores)
+    sgemm<false, false>(K, C, BNpx, max(1, min(BNpx / 512, 2 * sl::kNumSMs / ((C + BN - 1) / BN))), ProjKPx{gp, K, N},
+                        fq, EpiAtomic{d_s_hat, C}, st);
+    return sl_pop_bwd_tc_run(feat, B, C, N, s_hat, K, W1p, W2, w3, g_logits, Ktot, bg_ch, gp, dW1p, dW2, dw3, d_feat,
+                             reinterpret_cast<uint16_t*>(h1), wsplit, st);
+  }
   const int px_splits = max(1, min(BNpx / 512, 2 * sl::kNumSMs / (((C + BM - 1) / BM) * ((C + BN - 1) / BN))));
   // d_s_hat[k][c] = sum_px gp[k][px] q[px][c]
   sgemm<false, false>(K, C, BNpx, max(1, min(BNpx / 512, 2 * sl::kNumSMs / ((C + BN - 1) / BN))), ProjKPx{gp, K, N},

@@ -275,6 +275,7 @@ class _PopHeadFn(torch.autograd.Function):
             call('sl_pop_bg_simt', ptr(feats), B, C, N, ptr(W1t), ptr(W2t), ptr(w3), ptr(out), Ktot, 0, st)
         ctx.save_for_backward(feats, s_hat, alpha, beta, W1p, W2, w3)
         ctx.feat_dtype = features.dtype
+        ctx.bg_mode = bg_mode
         return out
 
     @staticmethod
@@ -290,7 +291,8 @@ class _PopHeadFn(torch.autograd.Function):
         ws = torch.empty(_cabi.lib().sl_pop_head_bwd_ws_bytes(B, C, N, K) // 4, dtype=torch.float32, device=dev)
         call('sl_pop_head_bwd', ptr(feats), B, C, N, ptr(s_hat), ptr(alpha), ptr(beta), K,
              int_array([1 + k for k in range(K)]), ptr(W1p), ptr(W2), ptr(w3), ptr(g), 1 + K, 0,
-             ptr(d_s), ptr(d_a), ptr(d_b), ptr(dW1p), ptr(dW2), ptr(dw3), ptr(d_feat), ptr(ws), _stream())
+             ptr(d_s), ptr(d_a), ptr(d_b), ptr(dW1p), ptr(dW2), ptr(dw3), ptr(d_feat),
+             1 if ctx.bg_mode == 'simt' else 0, ptr(ws), _stream())
         if d_feat is not None and ctx.feat_dtype != torch.float32:
             d_feat = d_feat.to(ctx.feat_dtype)
         return d_feat, d_s, d_a, d_b, dW1p, dW2, dw3, None

@@ -8,7 +8,11 @@ replaces, in place,
     (`eval_base.py:167`, `eval_ft.py:167`, `ft_pop.py:327`, `train_base.py:331`) the head after the
     decoder -- `orthogonal_decompose` + `classifier` / `classifier_n` + channel assembly
     (`pspnet_pop.py:143-159`, `:171-182`) -- runs in libsegland_b200.so; backbones and decoders stay
-    stock PyTorch.  Training-mode calls (`forward_novel`, loss dicts) fall through to the reference.
+    stock PyTorch.  Training-mode calls on CUDA tensors -- `forward_novel` (`ft_pop.py:252`,
+    `pspnet_pop.py:191-245`) and `forward_base` with a criterion (`train_base.py:259`, `:161-189`) -- run
+    the same head with autograd (`ops.forward_novel_train` / `ops.forward_base_train`: forward kernels +
+    `sl_pop_head_bwd`), so gradients reach `novel_emb`, `classifier_n`, `classifier`, `base_emb` and the
+    decoder exactly as in the reference; `patch(train=False)` keeps training on the reference's forward.
   * `utils.pyt_utils.get_confusion_matrix` and `utils.pyt_utils.intersectionAndUnionGPU`;
   * `loss.criterion.OrthLoss.forward`: the seg / aux cross-entropy terms run fused with the up-sampling
     (`loss/criterion.py:51-52,57-58`), differentiable, so training loops keep working.
@@ -57,21 +61,43 @@ def head_for(model, **kw):
     return cached[1]
 
 
+def _mlp_weights(seq):
+    return (seq[0].weight, seq[2].weight, seq[4].weight)
+
+
 def _make_forward(orig_forward):
     def forward(self, img, mask=None, img_b=None, mask_b=None):
-        wants_loss = self.criterion is not None and mask is not None
-        if self.training or (wants_loss and not self.is_ft) or not img.is_cuda:
+        if not img.is_cuda:
             return orig_forward(self, img, mask, img_b, mask_b)
-        with torch.no_grad():
+        is_ft = bool(getattr(self, 'is_ft', False))
+        if is_ft and self.training:                                   # forward_novel (pspnet_pop.py:191-245)
+            if not _train_enabled[0] or img_b is None or mask_b is None:
+                return orig_forward(self, img, mask, img_b, mask_b)
+            feats = _features(self, torch.cat([img, img_b], dim=0))
+            return ops.forward_novel_train(feats, mask, mask_b, self.base_emb, self.novel_emb,
+                                           _mlp_weights(self.classifier), _mlp_weights(self.classifier_n),
+                                           criterion=self.criterion)
+        wants_loss = self.criterion is not None and mask is not None
+        if not is_ft and (wants_loss or torch.is_grad_enabled() and self.training):   # forward_base, train_base.py:259
+            if not _train_enabled[0]:
+                return orig_forward(self, img, mask, img_b, mask_b)
+            return ops.forward_base_train(_features(self, img), mask, self.base_emb, _mlp_weights(self.classifier),
+                                          criterion=self.criterion)
+        with torch.no_grad():                                         # forward_all / forward_base, inference
             feats = _features(self, img)
             return head_for(self)(feats)
     forward._sl_patched = True
     return forward
 
 
-def patch(verbose=False):
-    """Install the B200 path into every importable reference module.  Returns the list of patched names."""
+_train_enabled = [True]
+
+
+def patch(verbose=False, train=True):
+    """Install the B200 path into every importable reference module.  Returns the list of patched names.
+    train=False leaves training-mode forwards (forward_novel, forward_base with a criterion) on the reference."""
     ops.check_device()
+    _train_enabled[0] = bool(train)
     done = []
     for name in MODEL_MODULES:
         try:

@@ -400,7 +400,7 @@ def test_full_size_properties(ops):
 def test_patch_installs_into_reference_shaped_modules(ops, golden):
     """segland_b200.patch against stand-ins with the reference's module/attribute names (the real tree
     is not on the GPU box): eval-mode forward goes through the CUDA head and matches the golden logits
-    the real GFSS_Model produced; training mode falls through to the original forward."""
+    the real GFSS_Model produced; train-mode forward_novel runs the CUDA head with autograd."""
     import sys
     import types
     import torch.nn as nn
@@ -449,7 +449,35 @@ def test_patch_installs_into_reference_shaped_modules(ops, golden):
         assert_close_rel(out.cpu(), torch.from_numpy(z['logits']), RTOL, 'patched forward')
         assert model(feats.cpu()) == 'reference path'                    # CPU tensors are not ours to take
         model.train()
-        assert model(feats) == 'reference path'                          # training falls through
+        assert model(feats) == 'reference path'                          # ft training without base images: not ours
+        # forward_novel (ft_pop.py:252) through the patched forward == ops.forward_novel_train on the same inputs
+        zt = golden('train_grads')
+        stt = state_from_npz(zt, 'ft_c64b_')
+        tm = GFSS_Model().cuda().train()
+        with torch.no_grad():
+            tm.novel_emb.copy_(stt.novel_emb); tm.base_emb.copy_(stt.base_emb)
+            for seq, ws in ((tm.classifier, stt.cls), (tm.classifier_n, stt.cls_n)):
+                seq[0].weight.copy_(ws[0].view(C, C, 1, 1)); seq[2].weight.copy_(ws[1].view(C, C, 1, 1))
+                seq[4].weight.copy_(ws[2].view(1, C, 1, 1))
+        tm.criterion = lambda preds, target, is_ft=False, proto_sim=None: ops.orth_loss_forward(preds, target, is_ft, proto_sim)
+        img_n = bf16_from_bits(zt['ft_c64b_img_n_bits']).float().cuda()
+        img_b = bf16_from_bits(zt['ft_c64b_img_b_bits']).float().cuda()
+        mask_n = torch.from_numpy(zt['ft_c64b_mask_n']).cuda()
+        mb1, mb2 = (torch.from_numpy(zt['ft_c64b_mask_b_before'].copy()).cuda() for _ in range(2))
+        loss = tm(img_n, mask_n, img_b, mb1)
+        loss['total_loss'].backward()
+        assert abs(loss['total_loss'].item() - float(zt['ft_c64b_total'])) <= 1e-3 * float(zt['ft_c64b_total'])
+        assert tm.base_emb.grad is None and tm.novel_emb.grad is not None
+        novel = stt.novel_emb.clone().cuda().requires_grad_(True)
+        cls_n = tuple(t.clone().cuda().requires_grad_(True) for t in stt.cls_n)
+        direct = ops.forward_novel_train(torch.cat([img_n, img_b]), mask_n, mb2, stt.base_emb.cuda(), novel,
+                                         tuple(t.cuda() for t in stt.cls), cls_n, criterion=tm.criterion)
+        direct['total_loss'].backward()
+        assert torch.equal(mb1, mb2)
+        assert_close_rel(tm.novel_emb.grad.cpu(), novel.grad.cpu(), 1e-5, 'patched novel_emb grad')
+        assert_close_rel(tm.classifier_n[2].weight.grad.view(C, C).cpu(), cls_n[1].grad.cpu(), 1e-5, 'patched W2n grad')
+        assert_close_rel(tm.classifier[0].weight.grad.view(C, C).cpu(), torch.from_numpy(zt['ft_c64b_g_W1']), 2e-3,
+                         'patched classifier grad vs reference autograd')
         model.eval()
         with torch.no_grad():
             model.novel_emb.mul_(2.0)                                    # in-place update -> head rebuilt
@@ -748,3 +776,57 @@ def test_head_backward_skips_feature_grad_and_is_deterministic_in_structure(ops)
         grads.append([novel.grad.clone()] + [t.grad.clone() for t in cls_n])
     for a, b in zip(*grads):
         assert_close_rel(a.cpu(), b.cpu(), 1e-5, 'param grads independent of d_feat')
+
+
+@pytest.mark.parametrize('mode', [0, 1])               # SL_BWD_AUTO (tcgen05 split-bf16) / SL_BWD_SIMT (fp32 CUDA cores)
+@pytest.mark.parametrize('C,B,h,w', [(512, 2, 32, 32), (192, 1, 24, 40), (96, 3, 16, 24), (64, 1, 8, 8)])
+def test_head_bwd_integer_inputs_are_exact(ops, mode, C, B, h, w):
+    """sl_pop_head_bwd on small-integer operands: every product and partial sum is exactly representable, so no
+    ReLU mask can flip and both implementations must reproduce the float64 formulas (pop_bwd.cu header) to fp32
+    rounding of the final pixel sums.  This pins the GEMM plumbing (operand layouts, majorness, split-K, ragged
+    tiles) independently of rounding noise."""
+    from segland_b200 import _cabi
+    from segland_b200._cabi import call, ptr, int_array
+    gen = torch.Generator().manual_seed(C + mode)
+    K, Ktot, N = 5, 7, h * w
+    ri = lambda lo, hi, *s: torch.randint(lo, hi + 1, s, generator=gen).float()
+    feats = ri(-3, 3, B, C, h, w)
+    s_hat, alpha, beta = ri(-1, 1, K, C), ri(-2, 2, K), ri(-2, 2, K)
+    sp = lambda t, p: t * (torch.rand(t.shape, generator=gen) < p)                  # sparsify: keeps sums small
+    W1p, W2, w3 = sp(ri(-2, 2, C, C), 0.2), sp(ri(-2, 2, C, C), 0.2), ri(-2, 2, C)
+    g = ri(-2, 2, B, Ktot, h, w)
+    fg_ch, bg_ch = [1, 2, 4, 5, 6], 3
+    dev = lambda t: t.cuda().contiguous()
+    outs = [torch.empty(*s, device='cuda') for s in ((K, C), (K,), (K,), (C, C), (C, C), (C,), (B, C, h, w))]
+    ws = torch.empty(_cabi.lib().sl_pop_head_bwd_ws_bytes(B, C, N, K) // 4 + 32, device='cuda')
+    f16 = dev(feats.to(torch.bfloat16))
+    args = [dev(t) for t in (s_hat, alpha, beta, W1p, W2, w3, g)]
+    call('sl_pop_head_bwd', ptr(f16), B, C, N, ptr(args[0]), ptr(args[1]), ptr(args[2]), K, int_array(fg_ch),
+         ptr(args[3]), ptr(args[4]), ptr(args[5]), ptr(args[6]), Ktot, bg_ch, *[ptr(o) for o in outs], mode, ptr(ws),
+         torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    # float64 formulas
+    d = lambda t: t.double()
+    q = d(feats).flatten(2)                                                         # [B,C,N]
+    p = torch.einsum('kc,bcn->bkn', d(s_hat), q)
+    gk = d(g).flatten(2)[:, fg_ch]                                                  # [B,K,N]
+    pos = p >= 0
+    d_alpha = (gk * p * pos).sum((0, 2))
+    d_beta = -(gk * p * ~pos).sum((0, 2))
+    gp = gk * torch.where(pos, d(alpha).view(1, K, 1), -d(beta).view(1, K, 1))
+    d_s = torch.einsum('bkn,bcn->kc', gp, q)
+    z1 = torch.einsum('oc,bcn->bon', d(W1p), q)
+    h1 = z1.clamp_min(0)
+    z2 = torch.einsum('oc,bcn->bon', d(W2), h1)
+    g0 = d(g).flatten(2)[:, bg_ch].unsqueeze(1)                                     # [B,1,N]
+    dw3 = (g0 * z2.clamp_min(0)).sum((0, 2))
+    dz2 = g0 * d(w3).view(1, C, 1) * (z2 > 0)
+    dW2 = torch.einsum('bin,bjn->ij', dz2, h1)
+    dz1 = torch.einsum('ij,bin->bjn', d(W2), dz2) * (z1 > 0)
+    dW1p = torch.einsum('bin,bjn->ij', dz1, q)
+    d_feat = torch.einsum('ij,bin->bjn', d(W1p), dz1) + torch.einsum('bkn,kc->bcn', gp, d(s_hat))
+    want = [d_s, d_alpha, d_beta, dW1p, dW2, dw3, d_feat.view(B, C, h, w)]
+    assert z2.abs().max() < 2 ** 24 and (z2 == 0).any(), 'test data must be exactly representable and hit z == 0'
+    for o, r, name in zip(outs, want, ['d_s_hat', 'd_alpha', 'd_beta', 'dW1p', 'dW2', 'dw3', 'd_feat']):
+        err = (o.double().cpu() - r).abs().max().item()
+        assert err <= 2e-6 * r.abs().max().item(), f'{name} mode {mode}: {err} vs max {r.abs().max().item()}'
