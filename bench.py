@@ -296,9 +296,9 @@ def run_ours(args, rank, world, local_rank):
         ach = bg_flops / (kern_ms['bg'] * 1e-3) / 1e12
         roofline = {'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
                     'frac': ach / peaks['tflops_sustained'],
-                    'traffic': traffic.get('bg_fused_kernel', {}).get(args.tc_precision) if use_tc else None,
+                    'traffic': traffic.get('bg_pair_kernel', {}).get(args.tc_precision) if use_tc else None,
                     'traffic_note': 'dram read+write bytes per 32-tile launch from profiles/r1_traffic.json (ncu --set full)',
-                    'kernel': 'bg_fused_kernel (sl_pop_bg_tc)' if use_tc else 'pop_bg_simt_kernel',
+                    'kernel': 'bg_pair_kernel (sl_pop_bg_tc, cta_group::2)' if use_tc else 'pop_bg_simt_kernel',
                     'mma_passes': passes,
                     'achieved_executed': bg_exec_flops / (kern_ms['bg'] * 1e-3) / 1e12,
                     'frac_executed_of_burst': bg_exec_flops / (kern_ms['bg'] * 1e-3) / 1e12 / peaks['tflops_burst'],

@@ -234,6 +234,94 @@ __global__ void __launch_bounds__(256) dw3_kernel(const float* __restrict__ h2, 
   }
 }
 
+// d_s_hat[k][c] += sum_px gp[b][k][px] * q[b][c][px]: HBM-bound stream over the features.
+// grid (ceil(C/8), px-chunks, B), 256 threads; a thread owns 8 consecutive pixels of 8 channels per iteration and
+// KG <= 12 classes of accumulators; classes beyond KG are handled by further passes over the (L2-resident) chunk.
+constexpr int PG_CH = 8, PG_KG = 12, PG_ITERS = 4;
+__global__ void __launch_bounds__(256) proto_grad_kernel(const uint16_t* __restrict__ feat, const float* __restrict__ gp,
+                                                         int C, int N, int K, float* __restrict__ d_s_hat) {
+  const int c0 = blockIdx.x * PG_CH, b = blockIdx.z;
+  const int chunk = 256 * 8 * PG_ITERS;
+  const int n_begin = blockIdx.y * chunk, n_end = min(N, n_begin + chunk);
+  __shared__ float red[8][PG_KG * PG_CH];
+  for (int k0 = 0; k0 < K; k0 += PG_KG) {
+    const int kn = min(PG_KG, K - k0);
+    float acc[PG_KG][PG_CH];
+#pragma unroll
+    for (int k = 0; k < PG_KG; ++k)
+#pragma unroll
+      for (int c = 0; c < PG_CH; ++c) acc[k][c] = 0.f;
+    for (int n = n_begin + threadIdx.x * 8; n < n_end; n += 256 * 8) {
+      float q[PG_CH][8];
+#pragma unroll
+      for (int c = 0; c < PG_CH; ++c) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (c0 + c < C) u = ld_stream_u4(feat + (static_cast<long long>(b) * C + c0 + c) * N + n);
+        q[c][0] = bf16lo(u.x); q[c][1] = bf16hi(u.x); q[c][2] = bf16lo(u.y); q[c][3] = bf16hi(u.y);
+        q[c][4] = bf16lo(u.z); q[c][5] = bf16hi(u.z); q[c][6] = bf16lo(u.w); q[c][7] = bf16hi(u.w);
+      }
+#pragma unroll
+      for (int k = 0; k < PG_KG; ++k) {
+        if (k < kn) {
+          const float4* g4 = reinterpret_cast<const float4*>(gp + (static_cast<long long>(b) * K + k0 + k) * N + n);
+          const float4 ga = __ldg(g4), gb = __ldg(g4 + 1);
+          const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+          for (int c = 0; c < PG_CH; ++c)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[k][c] = fmaf(gv[e], q[c][e], acc[k][c]);
+        }
+      }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < PG_KG; ++k)
+#pragma unroll
+      for (int c = 0; c < PG_CH; ++c) {
+        const float v = warp_sum(acc[k][c]);
+        if (lane == 0) red[warp][k * PG_CH + c] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < PG_KG * PG_CH) {
+      const int k = threadIdx.x / PG_CH, c = threadIdx.x - k * PG_CH;
+      if (k < kn && c0 + c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        atomicAdd(d_s_hat + (k0 + k) * C + c0 + c, t);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// d_feat[b][c][n] += sum_k gp[b][k][n] * s_hat[k][c]  (the projection term of d_q; the GEMM wrote W1'^T dz1).
+// grid (px-chunks of 1024, ceil(C/64), B), 256 threads; a thread keeps gp of its 4 pixels in registers.
+__global__ void __launch_bounds__(256) dfeat_proj_kernel(const float* __restrict__ gp, const float* __restrict__ s_hat, int C,
+                                                         int N, int K, float* __restrict__ d_feat) {
+  const int n = blockIdx.x * 1024 + threadIdx.x * 4, b = blockIdx.z;
+  const int c_begin = blockIdx.y * 64, c_end = min(C, c_begin + 64);
+  if (n >= N) return;
+  for (int k0 = 0; k0 < K; k0 += PG_KG) {
+    const int kn = min(PG_KG, K - k0);
+    float4 g[PG_KG];
+#pragma unroll
+    for (int k = 0; k < PG_KG; ++k)
+      g[k] = k < kn ? __ldg(reinterpret_cast<const float4*>(gp + (static_cast<long long>(b) * K + k0 + k) * N + n))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = c_begin; c < c_end; ++c) {
+      float4* o = reinterpret_cast<float4*>(d_feat + (static_cast<long long>(b) * C + c) * N + n);
+      float4 v = *o;
+#pragma unroll
+      for (int k = 0; k < PG_KG; ++k) {
+        const float s = k < kn ? __ldg(s_hat + (k0 + k) * C + c) : 0.f;
+        v.x = fmaf(g[k].x, s, v.x); v.y = fmaf(g[k].y, s, v.y); v.z = fmaf(g[k].z, s, v.z); v.w = fmaf(g[k].w, s, v.w);
+      }
+      *o = v;
+    }
+  }
+}
+
 }  // namespace bwd
 }  // namespace sl
 
@@ -308,17 +396,18 @@ extern "C" int sl_pop_head_bwd(const uint16_t* feat, int B, int C, int N, const 
     fg_coef_grad_kernel<<<dim3(chunks, K, B), 256, 0, st>>>(p, g_logits, alpha, beta, K, N, Ktot, chs, gp, d_alpha, d_beta);
   }
   const FeatPxCh fq{feat, C, N};
+  // d_s_hat[k][c] = sum_px gp[k][px] q[px][c]
+  proto_grad_kernel<<<dim3((C + PG_CH - 1) / PG_CH, (N + 256 * 8 * PG_ITERS - 1) / (256 * 8 * PG_ITERS), B), 256, 0, st>>>(
+      feat, gp, C, N, K, d_s_hat);
   if (mode == SL_BWD_AUTO && C >= 32) {
-    // d_s_hat[k][c] = sum_px gp[k][px] q[px][c]  (K rows only: stays on the CUDA cores)
-    sgemm<false, false>(K, C, BNpx, max(1, min(BNpx / 512, 2 * sl::kNumSMs / ((C + BN - 1) / BN))), ProjKPx{gp, K, N},
-                        fq, EpiAtomic{d_s_hat, C}, st);
-    return sl_pop_bwd_tc_run(feat, B, C, N, s_hat, K, W1p, W2, w3, g_logits, Ktot, bg_ch, gp, dW1p, dW2, dw3, d_feat,
-                             reinterpret_cast<uint16_t*>(h1), wsplit, st);
+    const int rc = sl_pop_bwd_tc_run(feat, B, C, N, s_hat, K, W1p, W2, w3, g_logits, Ktot, bg_ch, gp, dW1p, dW2, dw3, d_feat,
+                                     reinterpret_cast<uint16_t*>(h1), wsplit, st);
+    if (rc != 0) return rc;
+    if (d_feat != nullptr)
+      dfeat_proj_kernel<<<dim3((N + 1023) / 1024, (C + 63) / 64, B), 256, 0, st>>>(gp, s_hat, C, N, K, d_feat);
+    return SL_LAUNCH_RESULT();
   }
   const int px_splits = max(1, min(BNpx / 512, 2 * sl::kNumSMs / (((C + BM - 1) / BM) * ((C + BN - 1) / BN))));
-  // d_s_hat[k][c] = sum_px gp[k][px] q[px][c]
-  sgemm<false, false>(K, C, BNpx, max(1, min(BNpx / 512, 2 * sl::kNumSMs / ((C + BN - 1) / BN))), ProjKPx{gp, K, N},
-                      fq, EpiAtomic{d_s_hat, C}, st);
   // h1 = relu(W1' q)
   sgemm<true, false>(BNpx, C, C, 1, fq, ColMajor{W1p, C}, EpiRelu{h1, C}, st);
   // z2 = W2 h1 -> dz2, h2
