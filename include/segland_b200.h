@@ -152,6 +152,23 @@ SL_API int sl_pop_head_bwd(const uint16_t *feat, int B, int C, int N,
                     float *d_s_hat, float *d_alpha, float *d_beta, float *dW1p, float *dW2, float *dw3,
                     float *d_feat, int mode, void *ws, void *stream);
 
+/* Backward of sl_pop_prepare (training): the parameter-side chain s_hat = normalize(protos), alpha/beta =
+ * MLP(+-s_hat), W1' = W1_bg (I - S_hat^T S_hat) (pspnet_pop.py:106,113; :46-63; :112,118), given the
+ * outputs of sl_pop_head_bwd: d_s_hat [K,C], d_alpha, d_beta [K], dW1p [C,C] and the background MLP's direct
+ * gradients dW2_direct [C,C], dw3_direct [C].  Outputs (overwritten): d_protos [K,C] (rows [0,Kb) = base_emb,
+ * [Kb,K) = novel_emb), dW1/dW2/dw3 of the background MLP (classifier_n in ft mode) and, unless NULL, of the
+ * foreground MLP (classifier; pass NULL when it is frozen).  When both MLPs are the same tensors (base mode)
+ * pass NULL for the *_fg outputs: everything accumulates into *_bg.  ws: sl_pop_prepare_bwd_ws_bytes(K, C).
+ */
+SL_API size_t sl_pop_prepare_bwd_ws_bytes(int K, int C);
+SL_API int sl_pop_prepare_bwd(const float *protos, int K, int Kb, int C,
+                       const float *W1_fg, const float *W2_fg, const float *w3_fg,
+                       const float *W1_bg, const float *W2_bg, const float *w3_bg,
+                       const float *d_s_hat, const float *d_alpha, const float *d_beta, const float *dW1p,
+                       const float *dW2_direct, const float *dw3_direct,
+                       float *d_protos, float *dW1_fg, float *dW2_fg, float *dw3_fg,
+                       float *dW1_bg, float *dW2_bg, float *dw3_bg, float *ws, void *stream);
+
 /* The whole POP head in one launch (tensor-core path): sl_pop_bg_tc with the K <= 12 foreground logits of
  * sl_pop_fg_lowres computed by extra warps from the feature tiles already staged for the MMAs, so the
  * features are read from HBM once.  Arguments as in the two calls it replaces; ch_map_host[k] is the

@@ -20,8 +20,10 @@ def eager_head(f, base, novel, cls, cls_n):
     return torch.cat([p2[:, :1], p1, p2[:, 1:]], 1)
 
 
-def timeit(fn, n=10):
-    fn(); torch.cuda.synchronize()
+def timeit(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
     for _ in range(n):

@@ -24,6 +24,7 @@ _SIGNATURES = {
                        c_int, c_int, _P],
     'sl_pop_head_bwd': [_P, c_int, c_int, c_int, _P, _P, _P, c_int, POINTER(c_int), _P, _P, _P, _P, c_int, c_int] + [_P] * 7
                        + [c_int, _P, _P],
+    'sl_pop_prepare_bwd': [_P, c_int, c_int, c_int] + [_P] * 21,
     'sl_views_reduce': [_P, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_float, _P, _P],
     'sl_upsample_argmax': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P],
     'sl_pseudo_label': [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
@@ -64,6 +65,8 @@ def lib():
         handle.sl_pop_bg_tc_ws_bytes.restype = c_size_t
         handle.sl_pop_head_bwd_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
         handle.sl_pop_head_bwd_ws_bytes.restype = c_size_t
+        handle.sl_pop_prepare_bwd_ws_bytes.argtypes = [c_int, c_int]
+        handle.sl_pop_prepare_bwd_ws_bytes.restype = c_size_t
         handle.sl_pop_prepare_ws_bytes.argtypes = [c_int, c_int]
         handle.sl_pop_prepare_ws_bytes.restype = c_size_t
         handle.sl_upsample_ce_ws_bytes.argtypes = [c_int, c_int, c_int]
@@ -76,7 +79,7 @@ def lib():
 
 def exported_names():
     return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes', 'sl_pop_prepare_ws_bytes', 'sl_upsample_ce_ws_bytes',
-                                     'sl_pop_head_bwd_ws_bytes']
+                                     'sl_pop_head_bwd_ws_bytes', 'sl_pop_prepare_bwd_ws_bytes']
 
 
 def call(name, *args):

@@ -170,6 +170,134 @@ __global__ void __launch_bounds__(128) fold_weights_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Backward of sl_pop_prepare (training): the O(K C^2) parameter-side chain
+//   s_hat = normalize(protos);  alpha/beta = MLP(+-s_hat);  W1' = W1_bg (I - S_hat^T S_hat)
+// given dL/d{s_hat (through the projections), alpha, beta, W1', W2_bg, w3_bg} from sl_pop_head_bwd.
+// All kernels are tiny (K <= 31 vectors of C <= 1024); clarity over speed.
+
+// da2[v] = dy_v w3 [h2[v] > 0];  dw3_target += dy_v h2[v].       grid 2K, 128 threads
+__global__ void __launch_bounds__(128) pb_dlayer3_kernel(const float* __restrict__ h2, const float* __restrict__ d_alpha,
+                                                         const float* __restrict__ d_beta, int Kb, int C,
+                                                         const float* __restrict__ w3f, const float* __restrict__ w3g,
+                                                         float* __restrict__ da2, float* dw3f, float* dw3g) {
+  const int v = blockIdx.x, k = v >> 1;
+  const float dy = (v & 1) ? d_beta[k] : d_alpha[k];
+  const float* w3 = k < Kb ? w3f : w3g;
+  float* dw3 = k < Kb ? dw3f : dw3g;
+  for (int i = threadIdx.x; i < C; i += 128) {
+    const float h = h2[static_cast<size_t>(v) * C + i];
+    da2[static_cast<size_t>(v) * C + i] = h > 0.f ? dy * w3[i] : 0.f;
+    if (dw3 != nullptr) atomicAdd(dw3 + i, dy * h);
+  }
+}
+
+// out[v][i] = [mask[v][i] > 0] * sum_o W_sel[o][i] d[v][o]   (transposed mat-vec).   grid (ceil(C/128), V), 128 threads
+__global__ void __launch_bounds__(128) pb_matvec_t_kernel(const float* __restrict__ d, int Kb, int C,
+                                                          const float* __restrict__ Wf, const float* __restrict__ Wg,
+                                                          const float* __restrict__ mask, float* __restrict__ out) {
+  extern __shared__ float dv[];                       // [C]
+  const int v = blockIdx.y, k = v >> 1;
+  const float* W = k < Kb ? Wf : Wg;
+  for (int o = threadIdx.x; o < C; o += 128) dv[o] = d[static_cast<size_t>(v) * C + o];
+  __syncthreads();
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= C) return;
+  float acc = 0.f;
+  for (int o = 0; o < C; ++o) acc = fmaf(__ldg(W + static_cast<size_t>(o) * C + i), dv[o], acc);
+  if (mask != nullptr && !(mask[static_cast<size_t>(v) * C + i] > 0.f)) acc = 0.f;
+  out[static_cast<size_t>(v) * C + i] = acc;
+}
+
+// dW_target[o][i] += sum_{v of that target} a[v][o] * b[v][i];  b = h1, or +-s_hat when b_is_shat.   grid C, 128 threads
+__global__ void __launch_bounds__(128) pb_outer_kernel(const float* __restrict__ a, const float* __restrict__ b, int b_is_shat,
+                                                       int K, int Kb, int C, float* dWf, float* dWg) {
+  const int o = blockIdx.x;
+  for (int i = threadIdx.x; i < C; i += 128) {
+    float sf = 0.f, sg = 0.f;
+    for (int v = 0; v < 2 * K; ++v) {
+      const int k = v >> 1;
+      const float bv = b_is_shat ? ((v & 1) ? -b[static_cast<size_t>(k) * C + i] : b[static_cast<size_t>(k) * C + i])
+                                 : b[static_cast<size_t>(v) * C + i];
+      const float t = a[static_cast<size_t>(v) * C + o] * bv;
+      if (k < Kb) sf += t; else sg += t;
+    }
+    if (dWf == dWg) { if (dWf != nullptr) dWf[static_cast<size_t>(o) * C + i] += sf + sg; }
+    else {
+      if (dWf != nullptr) dWf[static_cast<size_t>(o) * C + i] += sf;
+      if (dWg != nullptr) dWg[static_cast<size_t>(o) * C + i] += sg;
+    }
+  }
+}
+
+// out[k][o] = M[o] . s_hat[k]                                                     grid C, 128 threads
+__global__ void __launch_bounds__(128) pb_rowdot_kernel(const float* __restrict__ M, const float* __restrict__ s_hat, int K,
+                                                        int C, float* __restrict__ out) {
+  const int o = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* row = M + static_cast<size_t>(o) * C;
+  for (int k = warp; k < K; k += 4) {
+    float acc = 0.f;
+    for (int i = lane; i < C; i += 32) acc = fmaf(row[i], s_hat[static_cast<size_t>(k) * C + i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[static_cast<size_t>(k) * C + o] = acc;
+  }
+}
+
+// dW1_bg[o][i] += D[o][i] - sum_k V[k][o] s_hat[k][i]                            grid C, 128 threads
+__global__ void __launch_bounds__(128) pb_fold_dw_kernel(const float* __restrict__ D, const float* __restrict__ V,
+                                                         const float* __restrict__ s_hat, int K, int C, float* dW1) {
+  const int o = blockIdx.x;
+  for (int i = threadIdx.x; i < C; i += 128) {
+    float corr = 0.f;
+    for (int k = 0; k < K; ++k) corr = fmaf(V[static_cast<size_t>(k) * C + o], s_hat[static_cast<size_t>(k) * C + i], corr);
+    dW1[static_cast<size_t>(o) * C + i] += D[static_cast<size_t>(o) * C + i] - corr;
+  }
+}
+
+// ds_fold[k][i] = - sum_o (U[k][o] D[o][i] + V[k][o] W1[o][i])                  grid (ceil(C/128), K), 128 threads
+__global__ void __launch_bounds__(128) pb_fold_ds_kernel(const float* __restrict__ U, const float* __restrict__ V,
+                                                         const float* __restrict__ D, const float* __restrict__ W1, int C,
+                                                         float* __restrict__ out) {
+  extern __shared__ float uv[];                       // U[k][:], V[k][:]
+  const int k = blockIdx.y;
+  for (int o = threadIdx.x; o < C; o += 128) {
+    uv[o] = U[static_cast<size_t>(k) * C + o];
+    uv[C + o] = V[static_cast<size_t>(k) * C + o];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= C) return;
+  float acc = 0.f;
+  for (int o = 0; o < C; ++o)
+    acc = fmaf(uv[o], __ldg(D + static_cast<size_t>(o) * C + i), fmaf(uv[C + o], __ldg(W1 + static_cast<size_t>(o) * C + i), acc));
+  out[static_cast<size_t>(k) * C + i] = -acc;
+}
+
+// d_protos[k] = (g - s_hat_k (s_hat_k . g)) / max(||protos_k||, 1e-12),  g = d_s_in + dx[+] - dx[-] + ds_fold
+__global__ void __launch_bounds__(128) pb_finalize_kernel(const float* __restrict__ protos, const float* __restrict__ s_hat,
+                                                          const float* __restrict__ d_s_in, const float* __restrict__ dx,
+                                                          const float* __restrict__ ds_fold, int C, float* __restrict__ d_protos) {
+  __shared__ float red[2][4];
+  const int k = blockIdx.x;
+  const size_t r = static_cast<size_t>(k) * C;
+  float ss = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < C; i += 128) {
+    const float g = d_s_in[r + i] + dx[2 * r + i] - dx[2 * r + C + i] + ds_fold[r + i];
+    const float pv = protos[r + i];
+    ss = fmaf(pv, pv, ss);
+    dot = fmaf(s_hat[r + i], g, dot);
+  }
+  ss = warp_sum(ss); dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ss; red[1][threadIdx.x >> 5] = dot; }
+  __syncthreads();
+  const float nrm = fmaxf(sqrtf(red[0][0] + red[0][1] + red[0][2] + red[0][3]), 1e-12f);
+  const float d = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  for (int i = threadIdx.x; i < C; i += 128) {
+    const float g = d_s_in[r + i] + dx[2 * r + i] - dx[2 * r + C + i] + ds_fold[r + i];
+    d_protos[r + i] = (g - s_hat[r + i] * d) / nrm;
+  }
+}
+
 }  // namespace sl
 
 extern "C" size_t sl_pop_prepare_ws_bytes(int K, int C) {
@@ -201,5 +329,72 @@ extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const f
   if (W1p_t || W2_t || n_split || W1p_f16)
     sl::fold_weights_kernel<<<C, 128, 0, st>>>(s_hat, K, C, W1_bg, W2_bg, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo,
                                                W1p_f16, W2_f16);
+  return SL_LAUNCH_RESULT();
+}
+
+extern "C" size_t sl_pop_prepare_bwd_ws_bytes(int K, int C) {
+  if (K < 1 || C < 1) return 0;
+  return static_cast<size_t>(14) * K * C * sizeof(float);
+}
+
+extern "C" int sl_pop_prepare_bwd(const float* protos, int K, int Kb, int C, const float* W1_fg, const float* W2_fg,
+                                  const float* w3_fg, const float* W1_bg, const float* W2_bg, const float* w3_bg,
+                                  const float* d_s_hat, const float* d_alpha, const float* d_beta, const float* dW1p,
+                                  const float* dW2_direct, const float* dw3_direct, float* d_protos, float* dW1_fg,
+                                  float* dW2_fg, float* dw3_fg, float* dW1_bg, float* dW2_bg, float* dw3_bg, float* ws,
+                                  void* stream) {
+  SL_CHECK_ARG(K >= 1 && K < SL_MAX_CLASSES && Kb >= 0 && Kb <= K);
+  SL_CHECK_ARG(C >= 8 && C <= 1024 && C % 8 == 0);
+  SL_CHECK_PTR(protos); SL_CHECK_PTR(W1_fg); SL_CHECK_PTR(W2_fg); SL_CHECK_PTR(w3_fg);
+  SL_CHECK_PTR(W1_bg); SL_CHECK_PTR(W2_bg); SL_CHECK_PTR(w3_bg);
+  SL_CHECK_PTR(d_s_hat); SL_CHECK_PTR(d_alpha); SL_CHECK_PTR(d_beta); SL_CHECK_PTR(dW1p); SL_CHECK_PTR(dW2_direct);
+  SL_CHECK_PTR(dw3_direct); SL_CHECK_PTR(d_protos); SL_CHECK_PTR(dW1_bg); SL_CHECK_PTR(dW2_bg); SL_CHECK_PTR(dw3_bg);
+  SL_CHECK_PTR(ws);
+  const bool shared = W1_fg == W1_bg && W2_fg == W2_bg && w3_fg == w3_bg;      // base mode: one MLP for every class
+  const int n_fg = (dW1_fg != nullptr) + (dW2_fg != nullptr) + (dw3_fg != nullptr);
+  SL_CHECK_ARG(n_fg == 0 || n_fg == 3);
+  SL_CHECK_ARG(!(shared && n_fg != 0));                                        // shared weights accumulate into the *_bg outputs
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t KC = static_cast<size_t>(K) * C;
+  float* s_hat = ws;                 // [K][C]
+  float* h1 = s_hat + KC;            // [2K][C]
+  float* h2 = h1 + 2 * KC;
+  float* da2 = h2 + 2 * KC;
+  float* da1 = da2 + 2 * KC;
+  float* dx = da1 + 2 * KC;
+  float* U = dx + 2 * KC;            // [K][C]
+  float* V = U + KC;
+  float* dsf = V + KC;
+  // outputs: background MLP starts from its direct gradients, everything else from zero
+  cudaMemcpyAsync(dW2_bg, dW2_direct, sizeof(float) * C * C, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(dw3_bg, dw3_direct, sizeof(float) * C, cudaMemcpyDeviceToDevice, st);
+  cudaMemsetAsync(dW1_bg, 0, sizeof(float) * C * C, st);
+  if (n_fg) {
+    cudaMemsetAsync(dW1_fg, 0, sizeof(float) * C * C, st);
+    cudaMemsetAsync(dW2_fg, 0, sizeof(float) * C * C, st);
+    cudaMemsetAsync(dw3_fg, 0, sizeof(float) * C, st);
+  }
+  float* t1 = shared ? dW1_bg : dW1_fg;   // targets of the classes [0, Kb)
+  float* t2 = shared ? dW2_bg : dW2_fg;
+  float* t3 = shared ? dw3_bg : dw3_fg;
+  // recompute the forward activations of the 2K coefficient vectors
+  sl::normalize_protos_kernel<<<K, 128, 0, st>>>(protos, C, s_hat);
+  const size_t xs_bytes = static_cast<size_t>(sl::VCHUNK) * C * sizeof(float);
+  sl::mlp1_kernel<<<(C + 7) / 8, 256, xs_bytes, st>>>(s_hat, K, Kb, C, W1_fg, W1_bg, h1);
+  sl::mlp2_kernel<<<(C + 7) / 8, 256, xs_bytes, st>>>(h1, K, Kb, C, W2_fg, W2_bg, h2);
+  // alpha / beta -> MLP weights and s_hat
+  const dim3 gv((C + 127) / 128, 2 * K);
+  sl::pb_dlayer3_kernel<<<2 * K, 128, 0, st>>>(h2, d_alpha, d_beta, Kb, C, w3_fg, w3_bg, da2, t3, dw3_bg);
+  sl::pb_outer_kernel<<<C, 128, 0, st>>>(da2, h1, 0, K, Kb, C, t2, dW2_bg);
+  sl::pb_matvec_t_kernel<<<gv, 128, C * sizeof(float), st>>>(da2, Kb, C, W2_fg, W2_bg, h1, da1);
+  sl::pb_outer_kernel<<<C, 128, 0, st>>>(da1, s_hat, 1, K, Kb, C, t1, dW1_bg);
+  sl::pb_matvec_t_kernel<<<gv, 128, C * sizeof(float), st>>>(da1, Kb, C, W1_fg, W1_bg, nullptr, dx);
+  // the fold W1' = W1_bg (I - S^T S)
+  sl::pb_rowdot_kernel<<<C, 128, 0, st>>>(W1_bg, s_hat, K, C, U);
+  sl::pb_rowdot_kernel<<<C, 128, 0, st>>>(dW1p, s_hat, K, C, V);
+  sl::pb_fold_dw_kernel<<<C, 128, 0, st>>>(dW1p, V, s_hat, K, C, dW1_bg);
+  sl::pb_fold_ds_kernel<<<dim3((C + 127) / 128, K), 128, 2 * C * sizeof(float), st>>>(U, V, dW1p, W1_bg, C, dsf);
+  // through the normalisation
+  sl::pb_finalize_kernel<<<K, 128, 0, st>>>(protos, s_hat, d_s_hat, dx, dsf, C, d_protos);
   return SL_LAUNCH_RESULT();
 }

@@ -237,95 +237,99 @@ class PopHead:
 
 
 # ==================================================================== POP head, training mode
-def _split_bf16(W):
-    """fp32 -> (hi, lo) bf16 bit patterns with hi + lo ~ W to 16 mantissa bits (round-to-nearest both)."""
-    hi = W.to(torch.bfloat16)
-    lo = (W - hi.to(torch.float32)).to(torch.bfloat16)
-    return hi.view(torch.int16), lo.view(torch.int16)
-
-
-class _PopHeadFn(torch.autograd.Function):
-    """logits = head(features) with the forward's operands as explicit (differentiable) inputs; the backward is
-    sl_pop_head_bwd.  Forward kernels are the eval ones (sl_pop_fg_lowres + sl_pop_bg_tc / sl_pop_bg_simt)."""
+class _PopHeadTrainFn(torch.autograd.Function):
+    """preds = head(features; prototypes, classifier, classifier_n) with every step in libsegland_b200.so:
+    forward = sl_pop_prepare + sl_pop_fg_lowres + sl_pop_bg_tc / sl_pop_bg_simt (the eval kernels),
+    backward = sl_pop_head_bwd (per-pixel part) + sl_pop_prepare_bwd (parameter-side chain)."""
 
     @staticmethod
-    def forward(ctx, features, s_hat, alpha, beta, W1p, W2, w3, bg_mode):
+    def forward(ctx, features, protos, Kb, W1, W2, w3, W1n, W2n, w3n, bg_mode):
         feats = features.detach().to(torch.bfloat16).contiguous()
         B, C, h, w = feats.shape
-        N, K = h * w, s_hat.shape[0]
+        N, K = h * w, protos.shape[0]
         Ktot = 1 + K
         dev = feats.device
-        s_hat, alpha, beta = (t.detach().to(torch.float32).contiguous() for t in (s_hat, alpha, beta))
-        W1p, W2, w3 = (t.detach().to(torch.float32).contiguous() for t in (W1p, W2, w3))
-        out = torch.empty(B, Ktot, h, w, dtype=torch.float32, device=dev)
-        ch_map = int_array([1 + k for k in range(K)])
-        st = _stream()
-        call('sl_pop_fg_lowres', ptr(feats), B, C, N, ptr(s_hat), ptr(alpha), ptr(beta), K, ptr(out), Ktot, ch_map, st)
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        protos = f32(protos)
+        fg = (f32(W1).view(C, C), f32(W2).view(C, C), f32(w3).view(C))
+        bg = fg if W1n is None else (f32(W1n).view(C, C), f32(W2n).view(C, C), f32(w3n).view(C))
+        new = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
         use_tc = bg_mode != 'simt' and C % 32 == 0 and 32 <= C <= 512 and N % 128 == 0
         if bg_mode == 'tc' and not use_tc:
             raise ValueError(f'bg_mode="tc" needs C % 32 == 0, C <= 512, N % 128 == 0 (C={C}, N={N})')
+        s_hat, alpha, beta, W1p_t, W2_t = new(K, C), new(K), new(K), new(C, C), new(C, C)
+        split = tuple(new(C, C, dtype=torch.int16) for _ in range(4)) if use_tc else (None,) * 4
+        ws = new(_cabi.lib().sl_pop_prepare_ws_bytes(K, C) // 4)
+        st = _stream()
+        call('sl_pop_prepare', ptr(protos), K, Kb, C, ptr(fg[0]), ptr(fg[1]), ptr(fg[2]), ptr(bg[0]), ptr(bg[1]),
+             ptr(bg[2]), ptr(s_hat), ptr(alpha), ptr(beta), ptr(W1p_t), ptr(W2_t), ptr(split[0]), ptr(split[1]),
+             ptr(split[2]), ptr(split[3]), None, None, ptr(ws), st)
+        out = new(B, Ktot, h, w)
+        call('sl_pop_fg_lowres', ptr(feats), B, C, N, ptr(s_hat), ptr(alpha), ptr(beta), K, ptr(out), Ktot,
+             int_array([1 + k for k in range(K)]), st)
         if use_tc:
-            w1h, w1l = _split_bf16(W1p)
-            w2h, w2l = _split_bf16(W2)
-            ws = torch.empty(_cabi.lib().sl_pop_bg_tc_ws_bytes(B, C, N) // 2, dtype=torch.int16, device=dev)
-            call('sl_pop_bg_tc', ptr(feats), B, C, N, ptr(w1h), ptr(w1l), ptr(w2h), ptr(w2l), ptr(w2h), ptr(w3), 0,
-                 ptr(ws), ptr(out), Ktot, 0, st)
+            h1_ws = torch.empty(_cabi.lib().sl_pop_bg_tc_ws_bytes(B, C, N) // 2, dtype=torch.int16, device=dev)
+            call('sl_pop_bg_tc', ptr(feats), B, C, N, ptr(split[0]), ptr(split[1]), ptr(split[2]), ptr(split[3]),
+                 ptr(split[2]), ptr(bg[2]), 0, ptr(h1_ws), ptr(out), Ktot, 0, st)
         else:
-            W1t, W2t = W1p.t().contiguous(), W2.t().contiguous()     # [C_in][C_out]; both alive until the launch
-            call('sl_pop_bg_simt', ptr(feats), B, C, N, ptr(W1t), ptr(W2t), ptr(w3), ptr(out), Ktot, 0, st)
-        ctx.save_for_backward(feats, s_hat, alpha, beta, W1p, W2, w3)
-        ctx.feat_dtype = features.dtype
-        ctx.bg_mode = bg_mode
+            call('sl_pop_bg_simt', ptr(feats), B, C, N, ptr(W1p_t), ptr(W2_t), ptr(bg[2]), ptr(out), Ktot, 0, st)
+        ctx.save_for_backward(feats, protos, s_hat, alpha, beta, W1p_t, *fg, *(() if W1n is None else bg))
+        ctx.meta = (Kb, W1n is None, bg_mode, features.dtype, tuple(W1.shape), tuple(W2.shape), tuple(w3.shape))
         return out
 
     @staticmethod
     def backward(ctx, g):
-        feats, s_hat, alpha, beta, W1p, W2, w3 = ctx.saved_tensors
+        feats, protos, s_hat, alpha, beta, W1p_t, *ws_ = ctx.saved_tensors
+        Kb, shared, bg_mode, feat_dtype, s1, s2, s3 = ctx.meta
+        fg = tuple(ws_[:3])
+        bg = fg if shared else tuple(ws_[3:])
         B, C, h, w = feats.shape
         N, K = h * w, s_hat.shape[0]
         dev = feats.device
         g = g.to(torch.float32).contiguous()
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        d_s, d_a, d_b, dW1p, dW2, dw3 = new(K, C), new(K), new(K), new(C, C), new(C, C), new(C)
-        d_feat = new(B, C, h, w) if ctx.needs_input_grad[0] else None
+        need = ctx.needs_input_grad            # features, protos, Kb, W1, W2, w3, W1n, W2n, w3n, bg_mode
+        d_s, d_a, d_b, dW1p, dW2d, dw3d = new(K, C), new(K), new(K), new(C, C), new(C, C), new(C)
+        d_feat = new(B, C, h, w) if need[0] else None
+        W1p = W1p_t.t().contiguous()
         ws = torch.empty(_cabi.lib().sl_pop_head_bwd_ws_bytes(B, C, N, K) // 4, dtype=torch.float32, device=dev)
+        st = _stream()
         call('sl_pop_head_bwd', ptr(feats), B, C, N, ptr(s_hat), ptr(alpha), ptr(beta), K,
-             int_array([1 + k for k in range(K)]), ptr(W1p), ptr(W2), ptr(w3), ptr(g), 1 + K, 0,
-             ptr(d_s), ptr(d_a), ptr(d_b), ptr(dW1p), ptr(dW2), ptr(dw3), ptr(d_feat),
-             1 if ctx.bg_mode == 'simt' else 0, ptr(ws), _stream())
-        if d_feat is not None and ctx.feat_dtype != torch.float32:
-            d_feat = d_feat.to(ctx.feat_dtype)
-        return d_feat, d_s, d_a, d_b, dW1p, dW2, dw3, None
-
-
-def _mlp3(x, W1, W2, w3):
-    return torch.relu(torch.relu(x @ W1.t()) @ W2.t()) @ w3
+             int_array([1 + k for k in range(K)]), ptr(W1p), ptr(bg[1]), ptr(bg[2]), ptr(g), 1 + K, 0,
+             ptr(d_s), ptr(d_a), ptr(d_b), ptr(dW1p), ptr(dW2d), ptr(dw3d), ptr(d_feat),
+             1 if bg_mode == 'simt' else 0, ptr(ws), st)
+        want_fg = (not shared) and (need[3] or need[4] or need[5])
+        d_protos = new(K, C)
+        gfg = (new(C, C), new(C, C), new(C)) if want_fg else (None, None, None)
+        gbg = (new(C, C), new(C, C), new(C))
+        ws2 = new(_cabi.lib().sl_pop_prepare_bwd_ws_bytes(K, C) // 4)
+        call('sl_pop_prepare_bwd', ptr(protos), K, Kb, C, ptr(fg[0]), ptr(fg[1]), ptr(fg[2]), ptr(bg[0]), ptr(bg[1]),
+             ptr(bg[2]), ptr(d_s), ptr(d_a), ptr(d_b), ptr(dW1p), ptr(dW2d), ptr(dw3d), ptr(d_protos),
+             ptr(gfg[0]), ptr(gfg[1]), ptr(gfg[2]), ptr(gbg[0]), ptr(gbg[1]), ptr(gbg[2]), ptr(ws2), st)
+        if d_feat is not None and feat_dtype != torch.float32:
+            d_feat = d_feat.to(feat_dtype)
+        if shared:
+            gfg, gbg = gbg, (None, None, None)
+        shp = lambda t, s: None if t is None else t.view(s)
+        return (d_feat, d_protos if need[1] else None, None, shp(gfg[0], s1), shp(gfg[1], s2), shp(gfg[2], s3),
+                shp(gbg[0], s1), shp(gbg[1], s2), shp(gbg[2], s3), None)
 
 
 def pop_head_train(features, base_emb, classifier, novel_emb=None, classifier_n=None, bg_mode='auto'):
     """The head of forward_novel / forward_base with autograd (networks/pspnet_pop.py:199-219, :169-182):
     features [B,C,h,w] (any float dtype; cast to bf16 for the kernels, gradients flow back if it requires
     grad), base_emb [Kb,C], classifier = (W1, W2, w3) conv weights, and for ft mode novel_emb [Kn,C] +
-    classifier_n.  Returns preds [B,1+Kb(+Kn),h,w] fp32 in the reference's channel order.  Every per-pixel
-    operation, forward and backward, runs in libsegland_b200.so; the parameter-side chain -- F.normalize of
-    the prototypes (pspnet_pop.py:106,111), alpha/beta = MLP(+-s_hat) and the fold W1 (I - S^T S), all
-    O(K C^2) on [K,C] / [C,C] tensors -- is differentiated by PyTorch."""
+    classifier_n.  Returns preds [B,1+Kb(+Kn),h,w] fp32 in the reference's channel order.  Forward and
+    backward run in libsegland_b200.so (see _PopHeadTrainFn); PyTorch only concatenates the prototypes and
+    routes the gradients.  bg_mode='simt' selects the exact-fp32 CUDA-core kernels for both directions."""
     check_device()
-    C = base_emb.shape[1]
-    Kb = base_emb.shape[0]
     ft = novel_emb is not None and novel_emb.shape[0] > 0
-    mats = lambda ws: (ws[0].reshape(C, C).float(), ws[1].reshape(C, C).float(), ws[2].reshape(C).float())
+    Kb = base_emb.shape[0]
+    protos = torch.cat([base_emb, novel_emb], 0) if ft else base_emb
+    cn = tuple(classifier_n) if ft else (None, None, None)
     with torch.autocast('cuda', enabled=False):
-        protos = torch.cat([base_emb, novel_emb], 0) if ft else base_emb
-        s_hat = torch.nn.functional.normalize(protos.to(torch.float32), p=2, dim=-1)
-        fg = mats(classifier)
-        bg = mats(classifier_n) if ft else fg
-        alpha, beta = _mlp3(s_hat[:Kb], *fg), _mlp3(-s_hat[:Kb], *fg)
-        if ft:
-            alpha = torch.cat([alpha, _mlp3(s_hat[Kb:], *bg)])
-            beta = torch.cat([beta, _mlp3(-s_hat[Kb:], *bg)])
-        W1p = bg[0] - (bg[0] @ s_hat.t()) @ s_hat
-        return _PopHeadFn.apply(features, s_hat, alpha, beta, W1p, bg[1], bg[2], bg_mode)
+        return _PopHeadTrainFn.apply(features, protos, Kb, classifier[0], classifier[1], classifier[2],
+                                     cn[0], cn[1], cn[2], bg_mode)
 
 
 def forward_novel_train(features_full, mask, mask_b, base_emb, novel_emb, classifier, classifier_n, criterion=None,
