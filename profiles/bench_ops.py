@@ -59,7 +59,7 @@ def main():
     # ---- C4: ft-mode heads with probability-map output
     for name, C, hw in (('ConvNeXt-T C=192', 192, 256), ('Swin-T/S C=96', 96, 256), ('PSPNet ft C=512', 512, 128)):
         stc = synth.make_head_state(C, 7, 4, seed=2)
-        Tc = 8
+        Tc = 32 if C * hw * hw * 2 * 32 <= (1 << 30) else 16      # >= 2 x L2 of features, enough tiles to fill 148 SMs
         f = torch.randn(Tc, C, hw, hw, device=dev, generator=g).to(torch.bfloat16)
         head = ops.PopHead(stc.base_emb, stc.cls, stc.novel_emb, stc.cls_n)
         lg = torch.empty(Tc, 12, hw, hw, device=dev)
@@ -73,6 +73,26 @@ def main():
         report(f'C4 upsample+softmax prob-map out K=12 {name}', t, Tc * (12 * hw * hw * 4 + 12 * 1024 * 1024 * 4 + 1024 * 1024), Tc)
         t = timeit(lambda: ops.upsample_argmax(lg, (1024, 1024)), iters=10)
         report(f'C4 upsample+argmax (pred only) K=12 {name}', t, Tc * (12 * hw * hw * 4 + 1024 * 1024), Tc)
+    # ---- training mode: head forward + backward at the ft_pop shapes (batch 1 novel + 1 base image,
+    # 1024^2 crops, scripts/ft_oem.sh), device time of every launch of one autograd step
+    for name, C, hw in (('PSPNet C=512', 512, 128), ('Swin-T/S C=96', 96, 256), ('ConvNeXt-T C=192', 192, 256)):
+        stc = synth.make_head_state(C, 7, 4, seed=3).to(dev)
+        f = synth.make_random_features(2, C, hw, hw, seed=3).to(dev)
+        gout = torch.randn(2, 12, hw, hw, device=dev, generator=g)
+        novel = stc.novel_emb.clone().requires_grad_(True)
+        cls_n = tuple(w.clone().requires_grad_(True) for w in stc.cls_n)
+
+        def step(mode='auto', need_dfeat=False):
+            for w in (novel, *cls_n):
+                w.grad = None
+            x = f.float().requires_grad_(need_dfeat)
+            ops.pop_head_train(x, stc.base_emb, stc.cls, novel, cls_n, bg_mode=mode).backward(gout)
+
+        flops = 10 * C * C * 2 * hw * hw
+        for label_, kw in (('tcgen05', {}), ('tcgen05 + d_feat', {'need_dfeat': True}), ('exact fp32', {'mode': 'simt'})):
+            t = timeit(lambda: step(**kw), iters=10)
+            print(f'{"train head fwd+bwd " + name + " (" + label_ + ")":58s} {t * 1e3:9.3f} ms/step '
+                  f'{flops / t / 1e12:7.1f} TFLOP/s fp32-equivalent (10 C^2 N)')
     # ---- metric kernels on 1024^2 label maps (32 tiles)
     gt = torch.randint(0, 12, (32, 1024, 1024), device=dev, dtype=torch.uint8, generator=g)
     pr = torch.randint(0, 12, (32, 1024, 1024), device=dev, dtype=torch.uint8, generator=g)

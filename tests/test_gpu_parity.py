@@ -830,3 +830,22 @@ def test_head_bwd_integer_inputs_are_exact(ops, mode, C, B, h, w):
     for o, r, name in zip(outs, want, ['d_s_hat', 'd_alpha', 'd_beta', 'dW1p', 'dW2', 'dw3', 'd_feat']):
         err = (o.double().cpu() - r).abs().max().item()
         assert err <= 2e-6 * r.abs().max().item(), f'{name} mode {mode}: {err} vs max {r.abs().max().item()}'
+
+
+def test_head_train_frozen_classifier_and_many_classes(ops):
+    """ft_freeze (networks/*_pop.py): classifier and base_emb frozen -> no gradient buffers for them; and a head
+    with 20 foreground classes (prototype-gradient kernel loops over class groups) against the exact-fp32 path."""
+    st = synth.make_head_state(64, 12, 8, seed=11).to('cuda')
+    feats = synth.make_random_features(2, 64, 16, 16, seed=11).cuda()
+    g_out = torch.randn(2, 21, 16, 16, device='cuda')
+    res = {}
+    for mode in ('auto', 'simt'):
+        novel = st.novel_emb.clone().requires_grad_(True)
+        cls_n = tuple(t.clone().requires_grad_(True) for t in st.cls_n)
+        base = st.base_emb.clone()                                   # requires_grad False, like ft mode
+        cls = tuple(t.clone() for t in st.cls)
+        ops.pop_head_train(feats, base, cls, novel, cls_n, bg_mode=mode).backward(g_out)
+        assert base.grad is None and all(t.grad is None for t in cls)
+        res[mode] = [novel.grad, *[t.grad for t in cls_n]]
+    for a, b in zip(res['auto'], res['simt']):
+        assert_close_rel(a.cpu(), b.cpu(), GRAD_RTOL, 'K=20 tensor-core vs exact gradients')
