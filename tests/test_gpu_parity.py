@@ -849,3 +849,45 @@ def test_head_train_frozen_classifier_and_many_classes(ops):
         res[mode] = [novel.grad, *[t.grad for t in cls_n]]
     for a, b in zip(res['auto'], res['simt']):
         assert_close_rel(a.cpu(), b.cpu(), GRAD_RTOL, 'K=20 tensor-core vs exact gradients')
+
+
+# ------------------------------------------------------------------- f-3: on-device fusion, async writer
+def test_logit_bank_fusion_matches_fusemat_order(ops):
+    """LogitBank.fuse (mean of low-res logits -> one fused upsample+argmax) against the reference's
+    order of operations (upsample each model, sum in order, / M, argmax: oracle ref_fuse)."""
+    from segland_b200 import sweep
+    M, K, T, h, H = 3, 12, 4, 32, 128
+    gen = torch.Generator().manual_seed(5)
+    stacks = [torch.randn(T, K, h, h, generator=gen) for _ in range(M)]
+    labels = synth.make_labels(T, H, H, K, seed=9, coarse=8)
+    bank = sweep.LogitBank(T, K, (h, h))
+    for m in range(M):
+        i = bank.new_model()
+        bank.deposit(i, 0, stacks[m][:2].cuda())
+        bank.deposit(i, 2, stacks[m][2:].cuda())
+    cm = torch.zeros(K, K, dtype=torch.int64, device='cuda')
+    pred = bank.fuse((H, H), labels=labels.cuda(), cm=cm).cpu().numpy()
+    ups = [ref_ops.ref_upsample(s, (H, H)).numpy() for s in stacks]
+    agree_px = 0
+    cm_ref = np.zeros((K, K))
+    for t in range(T):
+        ref_pred, fused = ref_ops.ref_fuse([u[t] for u in ups])
+        agree_px += argmax_agreement(pred[t][None], ref_pred[None], fused[None]) * H * H
+        cm_ref += ref_ops.ref_confusion(labels[t].numpy(), pred[t], K)
+    assert agree_px / (T * H * H) >= 0.9999
+    assert np.array_equal(cm.cpu().numpy().astype(np.float64), cm_ref)
+
+
+def test_async_map_writer_roundtrip(ops, tmp_path):
+    from PIL import Image
+    from segland_b200 import sweep
+    maps = torch.randint(0, 12, (6, 64, 96), dtype=torch.uint8, device='cuda')
+    palette = [v for k in range(12) for v in (20 * k, 255 - 20 * k, 10 * k)]
+    wr = sweep.AsyncMapWriter(str(tmp_path), (64, 96), palette=palette, slots=2, workers=2)
+    for i in range(6):
+        wr.submit(f'tile_{i}', maps[i])
+    wr.close()
+    for i in range(6):
+        img = Image.open(tmp_path / f'tile_{i}.png')
+        assert img.mode == 'P' and np.array_equal(np.array(img), maps[i].cpu().numpy())
+        assert img.getpalette()[:36] == palette
