@@ -29,6 +29,10 @@
 #include <cstdlib>
 #include "tma.cuh"
 
+int sl_pop_bg_small_launch(const uint16_t* feat, int B, int C, int N, const uint16_t* W1p_hi, const uint16_t* W1p_lo,
+                           const uint16_t* W2_hi, const uint16_t* W2_lo, const float* w3_bg, float* logits, int Ktot, int ch,
+                           cudaStream_t st);
+
 namespace sl {
 namespace tc {
 
@@ -813,6 +817,14 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
   if (K > 0) {
     SL_CHECK_PTR(s_hat); SL_CHECK_PTR(alpha); SL_CHECK_PTR(beta); SL_CHECK_PTR(fg_ch_host);
     SL_CHECK_ARG(K <= 12 && K < Ktot);
+  }
+
+  // narrow heads (Swin: C = 96 / 128): weights-resident kernel, hidden tile in shared memory (pop_bg_small.cu)
+  if (K == 0 && precision == SL_TC_PRECISE && C <= 128 && C % 32 == 0) {
+    const char* se = getenv("SL_TC_SMALL");
+    if (se == nullptr || atoi(se) != 0)
+      return sl_pop_bg_small_launch(feat, B, C, N, W1p_hi, W1p_lo, W2_hi, W2_lo, w3_bg, logits, Ktot, ch,
+                                    static_cast<cudaStream_t>(stream));
   }
 
   Params p;

@@ -660,13 +660,16 @@ def test_trained_like_sweep_matches_reference_miou(ops):
 
 def test_fused_head_matches_two_launch_path(ops):
     """sl_pop_head_tc (fg logits computed inside the tensor-core kernel) against sl_pop_fg_lowres +
-    sl_pop_bg_tc: same background channel bit for bit, foreground within fp32 summation-order noise."""
+    sl_pop_bg_tc: same background channel bit for bit (C > 128), foreground within fp32 summation-order noise."""
     for C, Kn, hw in ((512, 0, (32, 32)), (512, 4, (16, 24)), (96, 4, (16, 16)), (480, 4, (8, 16)), (192, 1, (16, 16))):
         st = synth.make_head_state(C, 7, Kn, seed=C + Kn)
         feats = synth.make_random_features(2, C, hw[0], hw[1], seed=C).cuda()
         one = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n, bg_mode='tc', fuse=True)(feats)
         two = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n, bg_mode='tc', fuse=False)(feats)
-        assert torch.equal(one[:, 0], two[:, 0])
+        if C > 128:
+            assert torch.equal(one[:, 0], two[:, 0])
+        else:          # narrow heads take the weights-resident kernel (pop_bg_small.cu): same products, other summation order
+            assert_close_rel(one[:, 0].cpu(), two[:, 0].cpu(), 1e-5, f'fused bg C={C}')
         assert_close_rel(one[:, 1:].cpu(), two[:, 1:].cpu(), 1e-5, f'fused fg C={C}')
         ref = ref_ops.ref_head(feats.cpu().float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
         assert_close_rel(one.cpu(), ref, RTOL, f'fused head C={C}')
