@@ -66,3 +66,126 @@ def test_oracle_collapse_identity():
     W1p = st.cls_n[0] - (st.cls_n[0] @ s.t()) @ s
     out[0] = mlp((W1p, st.cls_n[1], st.cls_n[2]), q)
     assert torch.allclose(out.view(1, 12, 8, 8), ref, rtol=0, atol=2e-6)
+
+
+def test_collapsed_backward_formulas_match_autograd():
+    """The per-pixel backward the CUDA kernels implement (pop_bwd.cu header) and the parameter-side chain
+    (sl_pop_prepare_bwd), restated here in float64 torch, against autograd through the oracle's materialising
+    head.  Pins the algebra on CPU, independent of any kernel."""
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    C, Kb, Kn, B, h, w = 24, 3, 2, 2, 5, 4
+    K, N = Kb + Kn, h * w
+    d = torch.float64
+    base = torch.randn(Kb, C, dtype=d)
+    novel = torch.randn(Kn, C, dtype=d, requires_grad=True)
+    cls = tuple(torch.randn(*s, dtype=d) / 4 for s in ((C, C), (C, C), (C,)))
+    cls_n = tuple((torch.randn(*s, dtype=d) / 4).requires_grad_(True) for s in ((C, C), (C, C), (C,)))
+    feats = torch.randn(B, C, h, w, dtype=d, requires_grad=True)
+    g = torch.randn(B, 1 + K, h, w, dtype=d)
+    def materialising_head(f):
+        # the reference's formulation (pspnet_pop.py:95-121,143-159) in float64: rank-1 tensors through the MLPs
+        qq = f.flatten(2)
+        s1, s2 = F.normalize(base, dim=-1), F.normalize(novel, dim=-1)
+        fg1 = (s1 @ qq).unsqueeze(2) * s1.unsqueeze(-1)                   # [B,Kb,C,N]
+        fg2 = (s2 @ qq).unsqueeze(2) * s2.unsqueeze(-1)
+        bg = (qq - fg1.sum(1) - fg2.sum(1)).unsqueeze(1)
+        run = lambda x, ws: torch.einsum('c,bkcn->bkn', ws[2], torch.relu(torch.einsum(
+            'oc,bkcn->bkon', ws[1], torch.relu(torch.einsum('oc,bkcn->bkon', ws[0], x)))))
+        p1, p2 = run(fg1, cls), run(torch.cat([bg, fg2], 1), cls_n)
+        return torch.cat([p2[:, :1], p1, p2[:, 1:]], 1).view(B, 1 + K, h, w)
+
+    out = materialising_head(feats)
+    out.backward(g)
+    # ---- collapsed forward quantities
+    with torch.no_grad():
+        protos = torch.cat([base, novel.detach()])
+        nrm = protos.norm(dim=-1, keepdim=True)
+        S = protos / nrm
+        W1, W2, w3 = (t.detach() for t in cls_n)
+        mlp = lambda x, ws: torch.relu(torch.relu(x @ ws[0].t()) @ ws[1].t()) @ ws[2]
+        alpha = torch.cat([mlp(S[:Kb], cls), mlp(S[Kb:], (W1, W2, w3))])
+        beta = torch.cat([mlp(-S[:Kb], cls), mlp(-S[Kb:], (W1, W2, w3))])
+        W1p = W1 - (W1 @ S.t()) @ S
+        q = feats.detach().flatten(2)                                     # [B,C,N]
+        p = torch.einsum('kc,bcn->bkn', S, q)
+        logits = torch.cat([(torch.relu(torch.relu(torch.einsum('oc,bcn->bon', W1p, q)).transpose(1, 2) @ W2.t()) @ w3).unsqueeze(1),
+                            torch.where(p >= 0, p * alpha.view(1, K, 1), -p * beta.view(1, K, 1))], 1)
+        assert torch.allclose(logits.view_as(out), out.detach(), atol=1e-10)
+        # ---- per-pixel backward (sl_pop_head_bwd)
+        gk, g0 = g.flatten(2)[:, 1:], g.flatten(2)[:, :1]
+        pos = p >= 0
+        d_alpha, d_beta = (gk * p * pos).sum((0, 2)), -(gk * p * ~pos).sum((0, 2))
+        gp = gk * torch.where(pos, alpha.view(1, K, 1), -beta.view(1, K, 1))
+        d_s = torch.einsum('bkn,bcn->kc', gp, q)
+        z1 = torch.einsum('oc,bcn->bon', W1p, q)
+        h1 = z1.clamp_min(0)
+        z2 = torch.einsum('oc,bcn->bon', W2, h1)
+        dw3 = (g0 * z2.clamp_min(0)).sum((0, 2))
+        dz2 = g0 * w3.view(1, C, 1) * (z2 > 0)
+        dW2 = torch.einsum('bin,bjn->ij', dz2, h1)
+        dz1 = torch.einsum('ij,bin->bjn', W2, dz2) * (z1 > 0)
+        D = torch.einsum('bin,bjn->ij', dz1, q)
+        d_feat = torch.einsum('ij,bin->bjn', W1p, dz1) + torch.einsum('bkn,kc->bcn', gp, S)
+        # ---- parameter side (sl_pop_prepare_bwd), novel classes + background use classifier_n
+        V = D @ S.t()
+        U = W1 @ S.t()
+        gW1 = D - V @ S
+        gS = d_s - (U.t() @ D + V.t() @ W1)
+        gW2, gw3 = dW2.clone(), dw3.clone()
+        for k in range(Kb, K):
+            for sign, dy in ((1.0, d_alpha[k]), (-1.0, d_beta[k])):
+                x = sign * S[k]
+                a1 = W1 @ x; hh1 = a1.clamp_min(0); a2 = W2 @ hh1; hh2 = a2.clamp_min(0)
+                gw3 += dy * hh2
+                da2 = dy * w3 * (a2 > 0)
+                gW2 += torch.outer(da2, hh1)
+                da1 = (W2.t() @ da2) * (a1 > 0)
+                gW1 += torch.outer(da1, x)
+                gS[k] += sign * (W1.t() @ da1)
+        for k in range(Kb):                                               # base classes: coefficients from `classifier`
+            for sign, dy in ((1.0, d_alpha[k]), (-1.0, d_beta[k])):
+                x = sign * S[k]
+                a1 = cls[0] @ x; a2 = cls[1] @ a1.clamp_min(0)
+                da1 = (cls[1].t() @ (dy * cls[2] * (a2 > 0))) * (a1 > 0)
+                gS[k] += sign * (cls[0].t() @ da1)
+        g_protos = (gS - S * (S * gS).sum(-1, keepdim=True)) / nrm
+    close = lambda a, b: torch.allclose(a, b, rtol=1e-9, atol=1e-11)
+    assert close(d_feat.view_as(feats), feats.grad)
+    assert close(g_protos[Kb:], novel.grad)
+    assert close(gW1, cls_n[0].grad) and close(gW2, cls_n[1].grad) and close(gw3, cls_n[2].grad)
+
+
+def test_patch_installs_into_the_real_reference_when_present(monkeypatch):
+    """Where the reference tree is mounted (authoring container), patch() must find every *_pop model, the metric
+    functions and OrthLoss under the names it expects, and leave CPU calls on the reference's own forward."""
+    import os
+    import sys
+    ref = os.environ.get('SEGLAND_REFERENCE', '/root/reference')
+    if not os.path.isdir(ref):
+        pytest.skip('reference tree not mounted')
+    from oracle import gen_golden
+    from segland_b200 import ops, patch as slp
+    gen_golden.import_reference()
+    monkeypatch.setattr(ops, 'check_device', lambda: None)
+    try:
+        done = slp.patch()
+        for name in slp.MODEL_MODULES:
+            assert f'networks.{name}.GFSS_Model.forward' in done, name
+        for name in ('utils.pyt_utils.get_confusion_matrix', 'utils.pyt_utils.intersectionAndUnionGPU',
+                     'loss.criterion.OrthLoss.forward'):
+            assert name in done
+        import networks.pspnet_pop as pp
+        st = synth.make_head_state(64, 7, 4, seed=1)
+        model = gen_golden.build_ref_model(pp, st).eval()
+        x = synth.make_random_features(1, 64, 8, 8).float()
+        out = model(x)                                                # CPU tensor -> the reference's own forward_all
+        want = ref_ops.ref_head(x, st.base_emb, st.novel_emb, st.cls, st.cls_n)
+        assert torch.equal(out.detach(), want)
+        assert {'base_emb', 'novel_emb'} <= set(dict(model.named_parameters()))
+        assert [type(m).__name__ for m in model.classifier_n] == ['Conv2d', 'ReLU', 'Conv2d', 'ReLU', 'Conv2d']
+    finally:
+        slp.unpatch()
+        sys.path[:] = [p for p in sys.path if p != ref]
+        for k in [k for k in sys.modules if k.split('.')[0] in ('networks', 'loss', 'utils', 'timm', 'engine', 'dataset')]:
+            sys.modules.pop(k, None)
