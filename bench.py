@@ -280,7 +280,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the public API with HOST buffers (double-buffered H2D, D2H of preds)
     Te = min(T, args.e2e_tiles)
-    e2e = run_e2e(ev, head, feats_h, labels_h, Te, args.steps, dev, world, dist if world > 1 else None)
+    # --e2e-tiles 0 (profiler runs only) skips the host-buffer leg; the driver's default run always measures it
+    e2e = run_e2e(ev, head, feats_h, labels_h, Te, args.steps, dev, world, dist if world > 1 else None) if Te > 0 else None
 
     if rank != 0:
         return

@@ -235,15 +235,16 @@ __global__ void __launch_bounds__(256) dw3_kernel(const float* __restrict__ h2, 
 }
 
 // d_s_hat[k][c] += sum_px gp[b][k][px] * q[b][c][px]: HBM-bound stream over the features.
-// grid (ceil(C/8), px-chunks, B), 256 threads; a thread owns 8 consecutive pixels of 8 channels per iteration and
-// KG <= 12 classes of accumulators; classes beyond KG are handled by further passes over the (L2-resident) chunk.
-constexpr int PG_CH = 8, PG_KG = 12, PG_ITERS = 4;
+// grid (ceil(C/32), px-chunks of 2048, B), 256 threads: warp w owns channels c0 + 4w .. + 3, a lane owns 8 consecutive
+// pixels per iteration; the eight warps read the same gp values (L1 hits), so gp costs C/32 passes over 4KN bytes
+// instead of C/8.  KG <= 12 classes of accumulators per pass over the chunk (it stays in L1/L2 for further passes).
+constexpr int PG_CH = 4, PG_KG = 12, PG_CHUNK = 2048;
 __global__ void __launch_bounds__(256) proto_grad_kernel(const uint16_t* __restrict__ feat, const float* __restrict__ gp,
                                                          int C, int N, int K, float* __restrict__ d_s_hat) {
-  const int c0 = blockIdx.x * PG_CH, b = blockIdx.z;
-  const int chunk = 256 * 8 * PG_ITERS;
-  const int n_begin = blockIdx.y * chunk, n_end = min(N, n_begin + chunk);
-  __shared__ float red[8][PG_KG * PG_CH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 32 + warp * PG_CH, b = blockIdx.z;
+  const int n_begin = blockIdx.y * PG_CHUNK, n_end = min(N, n_begin + PG_CHUNK);
+  if (c0 >= C) return;
   for (int k0 = 0; k0 < K; k0 += PG_KG) {
     const int kn = min(PG_KG, K - k0);
     float acc[PG_KG][PG_CH];
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(256) proto_grad_kernel(const uint16_t* __restr
     for (int k = 0; k < PG_KG; ++k)
 #pragma unroll
       for (int c = 0; c < PG_CH; ++c) acc[k][c] = 0.f;
-    for (int n = n_begin + threadIdx.x * 8; n < n_end; n += 256 * 8) {
+    for (int n = n_begin + lane * 8; n < n_end; n += 256) {
       float q[PG_CH][8];
 #pragma unroll
       for (int c = 0; c < PG_CH; ++c) {
@@ -273,25 +274,13 @@ __global__ void __launch_bounds__(256) proto_grad_kernel(const uint16_t* __restr
         }
       }
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < PG_KG; ++k)
 #pragma unroll
       for (int c = 0; c < PG_CH; ++c) {
         const float v = warp_sum(acc[k][c]);
-        if (lane == 0) red[warp][k * PG_CH + c] = v;
+        if (lane == 0 && k < kn && c0 + c < C) atomicAdd(d_s_hat + (k0 + k) * C + c0 + c, v);
       }
-    __syncthreads();
-    if (threadIdx.x < PG_KG * PG_CH) {
-      const int k = threadIdx.x / PG_CH, c = threadIdx.x - k * PG_CH;
-      if (k < kn && c0 + c < C) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-        atomicAdd(d_s_hat + (k0 + k) * C + c0 + c, t);
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -309,15 +298,24 @@ __global__ void __launch_bounds__(256) dfeat_proj_kernel(const float* __restrict
     for (int k = 0; k < PG_KG; ++k)
       g[k] = k < kn ? __ldg(reinterpret_cast<const float4*>(gp + (static_cast<long long>(b) * K + k0 + k) * N + n))
                     : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = c_begin; c < c_end; ++c) {
-      float4* o = reinterpret_cast<float4*>(d_feat + (static_cast<long long>(b) * C + c) * N + n);
-      float4 v = *o;
+    for (int cb = c_begin; cb < c_end; cb += 4) {          // four channels per step: four 16-byte loads in flight
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = cb + u < c_end ? *reinterpret_cast<const float4*>(d_feat + (static_cast<long long>(b) * C + cb + u) * N + n)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < PG_KG; ++k) {
-        const float s = k < kn ? __ldg(s_hat + (k0 + k) * C + c) : 0.f;
-        v.x = fmaf(g[k].x, s, v.x); v.y = fmaf(g[k].y, s, v.y); v.z = fmaf(g[k].z, s, v.z); v.w = fmaf(g[k].w, s, v.w);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float s = (k < kn && cb + u < c_end) ? __ldg(s_hat + (k0 + k) * C + cb + u) : 0.f;
+          v[u].x = fmaf(g[k].x, s, v[u].x); v[u].y = fmaf(g[k].y, s, v[u].y);
+          v[u].z = fmaf(g[k].z, s, v[u].z); v[u].w = fmaf(g[k].w, s, v[u].w);
+        }
       }
-      *o = v;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (cb + u < c_end) *reinterpret_cast<float4*>(d_feat + (static_cast<long long>(b) * C + cb + u) * N + n) = v[u];
     }
   }
 }
@@ -397,8 +395,7 @@ extern "C" int sl_pop_head_bwd(const uint16_t* feat, int B, int C, int N, const 
   }
   const FeatPxCh fq{feat, C, N};
   // d_s_hat[k][c] = sum_px gp[k][px] q[px][c]
-  proto_grad_kernel<<<dim3((C + PG_CH - 1) / PG_CH, (N + 256 * 8 * PG_ITERS - 1) / (256 * 8 * PG_ITERS), B), 256, 0, st>>>(
-      feat, gp, C, N, K, d_s_hat);
+  proto_grad_kernel<<<dim3((C + 31) / 32, (N + PG_CHUNK - 1) / PG_CHUNK, B), 256, 0, st>>>(feat, gp, C, N, K, d_s_hat);
   if (mode == SL_BWD_AUTO && C >= 32) {
     const int rc = sl_pop_bwd_tc_run(feat, B, C, N, s_hat, K, W1p, W2, w3, g_logits, Ktot, bg_ch, gp, dW1p, dW2, dw3, d_feat,
                                      reinterpret_cast<uint16_t*>(h1), wsplit, st);

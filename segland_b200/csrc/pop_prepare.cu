@@ -192,21 +192,29 @@ __global__ void __launch_bounds__(128) pb_dlayer3_kernel(const float* __restrict
   }
 }
 
-// out[v][i] = [mask[v][i] > 0] * sum_o W_sel[o][i] d[v][o]   (transposed mat-vec).   grid (ceil(C/128), V), 128 threads
+// out[v][i] = [mask[v][i] > 0] * sum_o W_sel[o][i] d[v][o]   (transposed mat-vec).   grid (ceil(C/32), V), 128 threads:
+// lane = column i, the four warps split the rows o (coalesced 128-byte row segments), partial sums meet in shared memory.
 __global__ void __launch_bounds__(128) pb_matvec_t_kernel(const float* __restrict__ d, int Kb, int C,
                                                           const float* __restrict__ Wf, const float* __restrict__ Wg,
                                                           const float* __restrict__ mask, float* __restrict__ out) {
-  extern __shared__ float dv[];                       // [C]
+  extern __shared__ float dv[];                       // [C] + [4][32]
+  float* part = dv + C;
   const int v = blockIdx.y, k = v >> 1;
   const float* W = k < Kb ? Wf : Wg;
   for (int o = threadIdx.x; o < C; o += 128) dv[o] = d[static_cast<size_t>(v) * C + o];
   __syncthreads();
-  const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i >= C) return;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int o = 0; o < C; ++o) acc = fmaf(__ldg(W + static_cast<size_t>(o) * C + i), dv[o], acc);
-  if (mask != nullptr && !(mask[static_cast<size_t>(v) * C + i] > 0.f)) acc = 0.f;
-  out[static_cast<size_t>(v) * C + i] = acc;
+  if (i < C)
+    for (int o = g; o < C; o += 4) acc = fmaf(__ldg(W + static_cast<size_t>(o) * C + i), dv[o], acc);
+  part[g * 32 + lane] = acc;
+  __syncthreads();
+  if (g == 0 && i < C) {
+    acc = (part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane]);
+    if (mask != nullptr && !(mask[static_cast<size_t>(v) * C + i] > 0.f)) acc = 0.f;
+    out[static_cast<size_t>(v) * C + i] = acc;
+  }
 }
 
 // dW_target[o][i] += sum_{v of that target} a[v][o] * b[v][i];  b = h1, or +-s_hat when b_is_shat.   grid C, 128 threads
@@ -254,23 +262,28 @@ __global__ void __launch_bounds__(128) pb_fold_dw_kernel(const float* __restrict
   }
 }
 
-// ds_fold[k][i] = - sum_o (U[k][o] D[o][i] + V[k][o] W1[o][i])                  grid (ceil(C/128), K), 128 threads
+// ds_fold[k][i] = - sum_o (U[k][o] D[o][i] + V[k][o] W1[o][i])                  grid (ceil(C/32), K), 128 threads
 __global__ void __launch_bounds__(128) pb_fold_ds_kernel(const float* __restrict__ U, const float* __restrict__ V,
                                                          const float* __restrict__ D, const float* __restrict__ W1, int C,
                                                          float* __restrict__ out) {
-  extern __shared__ float uv[];                       // U[k][:], V[k][:]
+  extern __shared__ float uv[];                       // U[k][:], V[k][:], then [4][32] partial sums
+  float* part = uv + 2 * C;
   const int k = blockIdx.y;
   for (int o = threadIdx.x; o < C; o += 128) {
     uv[o] = U[static_cast<size_t>(k) * C + o];
     uv[C + o] = V[static_cast<size_t>(k) * C + o];
   }
   __syncthreads();
-  const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i >= C) return;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int o = 0; o < C; ++o)
-    acc = fmaf(uv[o], __ldg(D + static_cast<size_t>(o) * C + i), fmaf(uv[C + o], __ldg(W1 + static_cast<size_t>(o) * C + i), acc));
-  out[static_cast<size_t>(k) * C + i] = -acc;
+  if (i < C)
+    for (int o = g; o < C; o += 4)
+      acc = fmaf(uv[o], __ldg(D + static_cast<size_t>(o) * C + i), fmaf(uv[C + o], __ldg(W1 + static_cast<size_t>(o) * C + i), acc));
+  part[g * 32 + lane] = acc;
+  __syncthreads();
+  if (g == 0 && i < C)
+    out[static_cast<size_t>(k) * C + i] = -((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane]));
 }
 
 // d_protos[k] = (g - s_hat_k (s_hat_k . g)) / max(||protos_k||, 1e-12),  g = d_s_in + dx[+] - dx[-] + ds_fold
@@ -383,17 +396,17 @@ extern "C" int sl_pop_prepare_bwd(const float* protos, int K, int Kb, int C, con
   sl::mlp1_kernel<<<(C + 7) / 8, 256, xs_bytes, st>>>(s_hat, K, Kb, C, W1_fg, W1_bg, h1);
   sl::mlp2_kernel<<<(C + 7) / 8, 256, xs_bytes, st>>>(h1, K, Kb, C, W2_fg, W2_bg, h2);
   // alpha / beta -> MLP weights and s_hat
-  const dim3 gv((C + 127) / 128, 2 * K);
+  const dim3 gv((C + 31) / 32, 2 * K);
   sl::pb_dlayer3_kernel<<<2 * K, 128, 0, st>>>(h2, d_alpha, d_beta, Kb, C, w3_fg, w3_bg, da2, t3, dw3_bg);
   sl::pb_outer_kernel<<<C, 128, 0, st>>>(da2, h1, 0, K, Kb, C, t2, dW2_bg);
-  sl::pb_matvec_t_kernel<<<gv, 128, C * sizeof(float), st>>>(da2, Kb, C, W2_fg, W2_bg, h1, da1);
+  sl::pb_matvec_t_kernel<<<gv, 128, (C + 128) * sizeof(float), st>>>(da2, Kb, C, W2_fg, W2_bg, h1, da1);
   sl::pb_outer_kernel<<<C, 128, 0, st>>>(da1, s_hat, 1, K, Kb, C, t1, dW1_bg);
-  sl::pb_matvec_t_kernel<<<gv, 128, C * sizeof(float), st>>>(da1, Kb, C, W1_fg, W1_bg, nullptr, dx);
+  sl::pb_matvec_t_kernel<<<gv, 128, (C + 128) * sizeof(float), st>>>(da1, Kb, C, W1_fg, W1_bg, nullptr, dx);
   // the fold W1' = W1_bg (I - S^T S)
   sl::pb_rowdot_kernel<<<C, 128, 0, st>>>(W1_bg, s_hat, K, C, U);
   sl::pb_rowdot_kernel<<<C, 128, 0, st>>>(dW1p, s_hat, K, C, V);
   sl::pb_fold_dw_kernel<<<C, 128, 0, st>>>(dW1p, V, s_hat, K, C, dW1_bg);
-  sl::pb_fold_ds_kernel<<<dim3((C + 127) / 128, K), 128, 2 * C * sizeof(float), st>>>(U, V, dW1p, W1_bg, C, dsf);
+  sl::pb_fold_ds_kernel<<<dim3((C + 31) / 32, K), 128, (2 * C + 128) * sizeof(float), st>>>(U, V, dW1p, W1_bg, C, dsf);
   // through the normalisation
   sl::pb_finalize_kernel<<<K, 128, 0, st>>>(protos, s_hat, d_s_hat, dx, dsf, C, d_protos);
   return SL_LAUNCH_RESULT();
