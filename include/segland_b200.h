@@ -111,7 +111,8 @@ SL_API int sl_pop_bg_simt(const uint16_t *feat, int B, int C, int N,
                    float *logits, int Ktot, int ch, void *stream);
 
 /* Background logit on tcgen05 tensor cores, fp32 accumulation in TMEM.
- * C % 32 == 0, 32 <= C <= 512, N % 128 == 0; SL_EINVAL outside that range (callers use _simt).
+ * C % 32 == 0, 32 <= C <= 512, N % 8 == 0 (a partial last 128-pixel tile is zero-filled by TMA); SL_EINVAL
+ * outside that range (callers use _simt).
  *   precision  SL_TC_PRECISE  split-bf16 operands, 2 + 3 MMA passes: ~5e-6 of the fp32 reference.
  *              SL_TC_BALANCED layer 1 split-bf16 (2 passes), layer 2 single-pass fp16 (3 passes):
  *                             ~3e-4 relative to the tensor maximum.  Needs W2_f16.

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, 1) bg_small_kernel(const __grid_const
       const int mt = tile_of(s);
       const int img = mt / p.tiles_per_image;
       const int n = (mt - img * p.tiles_per_image) * BLOCK_M + row;
-      p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
+      if (n < p.N) p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
     }
   }
   tc_fence_before();
@@ -290,8 +290,8 @@ int sl_pop_bg_small_launch(const uint16_t* feat, int B, int C, int N, const uint
   SmallParams p;
   p.C = C;
   p.kblocks = (C + BLOCK_K - 1) / BLOCK_K;
-  p.m_tiles = static_cast<int>(static_cast<long long>(B) * N / BLOCK_M);
-  p.tiles_per_image = N / BLOCK_M;
+  p.tiles_per_image = (N + BLOCK_M - 1) / BLOCK_M;
+  p.m_tiles = B * p.tiles_per_image;
   p.N = N; p.Ktot = Ktot; p.ch = ch; p.w3 = w3_bg; p.logits = logits;
   {
     const char* de = getenv("SL_SMALL_DBG");                   // device pointer (decimal) of a 64 x 16 int64 buffer

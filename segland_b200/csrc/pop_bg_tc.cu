@@ -60,7 +60,7 @@ struct Params {
   int NT;               // n-tile width
   int n_tiles;          // C / NT
   int m_tiles;          // B*N / 128
-  int tiles_per_image;  // N / 128
+  int tiles_per_image;  // ceil(N / 128): a partial last tile is zero-filled by TMA and its stores are guarded
   int N;                // pixels per image
   int Ktot, ch;         // logits layout
   int l1_passes;        // 2: split-bf16 W1' (hi, lo)
@@ -321,7 +321,7 @@ bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
           const int n = (mt - img * p.tiles_per_image) * BLOCK_M + pm;
 #pragma unroll
           for (int k = 0; k < KP; ++k)
-            if (k < p.K) {
+            if (k < p.K && n < p.N) {
               const float pr = acc[k];
               p.logits[(static_cast<size_t>(img) * p.Ktot + p.fg_ch[k]) * p.N + n] =
                   pr >= 0.f ? pr * __ldg(p.alpha + k) : -pr * __ldg(p.beta + k);
@@ -448,7 +448,7 @@ bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
         const int mt = tile_of(s);
         const int img = mt / p.tiles_per_image;
         const int n = (mt - img * p.tiles_per_image) * BLOCK_M + row;
-        p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
+        if (n < p.N) p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
       }
     };
     for_each_phase([&](int s) { for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(false, s, nt); },
@@ -765,7 +765,7 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
         const int mt = tile_raw(s);
         const int img = mt / p.tiles_per_image;
         const int n = (mt - img * p.tiles_per_image) * BLOCK_M + row;
-        p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
+        if (n < p.N) p.logits[(static_cast<size_t>(img) * p.Ktot + p.ch) * p.N + n] = logit;
       }
     };
     for_each_phase([&](int s) { for (int nt = 0; nt < p.n_tiles; ++nt) epi_job(false, s, nt); },
@@ -808,9 +808,9 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
   if (precision == SL_TC_PRECISE) { SL_CHECK_PTR(W2_hi); SL_CHECK_PTR(W2_lo); } else { SL_CHECK_PTR(W2_f16); }
   // pointers the chosen mode does not read alias a valid buffer so every tensor map stays well formed
   if (precision != SL_TC_PRECISE) { W2_hi = W2_f16; W2_lo = W2_f16; }
-  SL_CHECK_ARG(B >= 1 && C >= 32 && C <= 512 && C % 32 == 0 && N >= 128 && N % 128 == 0);
+  SL_CHECK_ARG(B >= 1 && C >= 32 && C <= 512 && C % 32 == 0 && N >= 8 && N % 8 == 0);
   SL_CHECK_ARG(Ktot >= 1 && Ktot <= SL_MAX_CLASSES && ch >= 0 && ch < Ktot);
-  SL_CHECK_ARG(static_cast<long long>(B) * N / BLOCK_M < (1ll << 30));
+  SL_CHECK_ARG(static_cast<long long>(B) * ((N + BLOCK_M - 1) / BLOCK_M) < (1ll << 30));
   SL_CHECK_ALIGN(feat, 16); SL_CHECK_ALIGN(h1_ws, 128);
   SL_CHECK_ALIGN(W1p_hi, 16); SL_CHECK_ALIGN(W1p_lo, 16); SL_CHECK_ALIGN(W2_hi, 16); SL_CHECK_ALIGN(W2_lo, 16);
   const int KQ = K > 0 ? (K + 3) / 4 : 0;
@@ -835,8 +835,8 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
   for (int nt = 32; nt <= MAX_NT && nt <= C; nt += 32)
     if (C % nt == 0) p.NT = nt;
   p.n_tiles = C / p.NT;
-  p.m_tiles = static_cast<int>(static_cast<long long>(B) * N / BLOCK_M);
-  p.tiles_per_image = N / BLOCK_M;
+  p.m_tiles = static_cast<int>(static_cast<long long>(B) * ((N + BLOCK_M - 1) / BLOCK_M));
+  p.tiles_per_image = (N + BLOCK_M - 1) / BLOCK_M;
   p.N = N; p.Ktot = Ktot; p.ch = ch;
   p.w3 = w3_bg;
   p.logits = logits;

@@ -63,7 +63,7 @@ class PopHead:
     [bg, base_1..Kb, novel_1..Kn] (pspnet_pop.py:159).  In ft mode the background and novel
     channels use classifier_n, base channels use classifier (pspnet_pop.py:150-157).
 
-    bg_mode: 'tc'   tcgen05 tensor-core MLP (C % 32 == 0, C <= 512, N % 128 == 0)
+    bg_mode: 'tc'   tcgen05 tensor-core MLP (C % 32 == 0, C <= 512; any N % 8 == 0)
              'simt' exact fp32 CUDA-core MLP (any C % 8 == 0, C <= 768)
              'auto' tc when the shape allows, else simt
     tc_precision: 'precise' (split-bf16, 5 MMA passes, ~5e-6 of fp32; the default and the mode the
@@ -165,9 +165,9 @@ class PopHead:
     def _use_tc(self, N):
         if self.bg_mode == 'simt':
             return False
-        ok = self._plan.split is not None and N % 128 == 0
+        ok = self._plan.split is not None and N % 8 == 0
         if self.bg_mode == 'tc' and not ok:
-            raise ValueError(f'bg_mode="tc" needs C % 32 == 0, C <= 512, N % 128 == 0 (C={self.C}, N={N})')
+            raise ValueError(f'bg_mode="tc" needs C % 32 == 0, 32 <= C <= 512, N % 8 == 0 (C={self.C}, N={N})')
         return ok
 
     def bg_tc(self, feats, out):
@@ -254,9 +254,9 @@ class _PopHeadTrainFn(torch.autograd.Function):
         fg = (f32(W1).view(C, C), f32(W2).view(C, C), f32(w3).view(C))
         bg = fg if W1n is None else (f32(W1n).view(C, C), f32(W2n).view(C, C), f32(w3n).view(C))
         new = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
-        use_tc = bg_mode != 'simt' and C % 32 == 0 and 32 <= C <= 512 and N % 128 == 0
+        use_tc = bg_mode != 'simt' and C % 32 == 0 and 32 <= C <= 512 and N % 8 == 0
         if bg_mode == 'tc' and not use_tc:
-            raise ValueError(f'bg_mode="tc" needs C % 32 == 0, C <= 512, N % 128 == 0 (C={C}, N={N})')
+            raise ValueError(f'bg_mode="tc" needs C % 32 == 0, 32 <= C <= 512, N % 8 == 0 (C={C}, N={N})')
         s_hat, alpha, beta, W1p_t, W2_t = new(K, C), new(K), new(K), new(C, C), new(C, C)
         split = tuple(new(C, C, dtype=torch.int16) for _ in range(4)) if use_tc else (None,) * 4
         ws = new(_cabi.lib().sl_pop_prepare_ws_bytes(K, C) // 4)
