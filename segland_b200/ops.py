@@ -214,9 +214,17 @@ class PopHead:
         feats = _cuda(features, torch.bfloat16)
         B, C, h, w = feats.shape
         N = h * w
-        if N % 8:
-            raise ValueError('h*w must be a multiple of 8')
         Ktot = 1 + self.K
+        if N % 8:
+            # TMA wants 16-byte row strides: pad the pixel axis to a multiple of 8 (one extra copy of the features;
+            # feature maps of the reference's models at its tile sizes never take this path) and drop the padding
+            pad = -N % 8
+            padded = torch.nn.functional.pad(feats.reshape(B, C, N), (0, pad)).view(B, C, 1, N + pad)
+            res = self.__call__(padded, fg_only=fg_only)[..., :N].reshape(B, Ktot, h, w)
+            if out is None:
+                return res
+            out.copy_(res)
+            return out
         if out is None:
             out = torch.empty(B, Ktot, h, w, dtype=torch.float32, device=feats.device)
         p = self._plan

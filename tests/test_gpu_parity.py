@@ -148,9 +148,12 @@ def test_head_argument_errors(ops):
     head = make_head(ops, st, 'simt')
     with pytest.raises(ValueError):
         head(torch.zeros(1, 32, 8, 8, dtype=torch.bfloat16, device='cuda'))
-    with pytest.raises(ValueError):
-        head(torch.zeros(1, 64, 3, 3, dtype=torch.bfloat16, device='cuda'))     # N % 8 != 0
+    assert head(torch.zeros(1, 64, 3, 3, dtype=torch.bfloat16, device='cuda')).shape == (1, 8, 3, 3)   # padded internally
     from segland_b200 import _cabi
+    with pytest.raises(_cabi.SeglandError):                                       # the C ABI itself keeps N % 8 == 0
+        _cabi.call('sl_pop_fg_lowres', _cabi.ptr(torch.zeros(64 * 9, dtype=torch.bfloat16, device='cuda')), 1, 64, 9,
+                   _cabi.ptr(head._plan.s_hat), _cabi.ptr(head._plan.alpha), _cabi.ptr(head._plan.beta), 7,
+                   _cabi.ptr(torch.zeros(8 * 9, device='cuda')), 8, _cabi.int_array([1 + k for k in range(7)]), None)
     with pytest.raises(_cabi.SeglandError):                                       # NULL pointer -> SL_ENULL
         _cabi.call('sl_pop_fg_lowres', None, 1, 64, 64, None, None, None, 7, None, 8, _cabi.int_array([1] * 7), None)
 
@@ -913,3 +916,13 @@ def test_head_tc_ragged_pixel_counts(ops, C, Kn, hw, B):
     if Kn == 0 and C == 512:                                   # fused head on a ragged tile as well
         fused = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n, bg_mode='tc', fuse=True)(feats)
         assert_close_rel(fused.cpu(), simt.cpu(), 1e-4, 'ragged fused head')
+
+
+def test_head_pixel_count_not_multiple_of_eight(ops):
+    """125x125 feature maps (1000^2 tiles at stride 8): padded internally, same logits as the oracle."""
+    st = synth.make_head_state(64, 7, 4, seed=21)
+    feats = synth.make_random_features(2, 64, 5, 5, seed=21).cuda()
+    out = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n)(feats)
+    ref = ref_ops.ref_head(feats.cpu().float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
+    assert out.shape == ref.shape
+    assert_close_rel(out.cpu(), ref, RTOL, 'padded head')
