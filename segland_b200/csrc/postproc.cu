@@ -465,30 +465,59 @@ __global__ void __launch_bounds__(256) confusion_kernel(const uint8_t* __restric
 }
 
 // ------------------------------------------------------------------ intersection / union
-// ws: [3][K] int64 = {intersection, area_output, area_target}
+// ws: [3][K] int64 = {intersection, area_output, area_target}.  One joint (output, target) histogram of (K+1)^2 bins
+// per CTA (bin K = "outside [0,K)", which torch.histc ignores), filled by per-thread run-length accumulation like
+// the confusion kernel (prediction / label maps are piecewise constant along a row), then folded into the three
+// marginals: intersection = diagonal, area_output = row sums, area_target = column sums.
 __global__ void __launch_bounds__(256) inter_union_kernel(long long* __restrict__ output,
                                                           const long long* __restrict__ target, long long n, int K,
                                                           long long ignore, unsigned long long* __restrict__ ws) {
-  __shared__ unsigned int hist[3 * SL_MAX_CLASSES];
-  for (int i = threadIdx.x; i < 3 * K; i += 256) hist[i] = 0u;
+  __shared__ unsigned int hist[(SL_MAX_CLASSES + 1) * (SL_MAX_CLASSES + 1)];
+  const int K1 = K + 1;
+  for (int i = threadIdx.x; i < K1 * K1; i += 256) hist[i] = 0u;
   __syncthreads();
+  int run_bin = 0;
+  unsigned int run_cnt = 0;
+  auto add = [&](long long i, long long o, long long t) {
+    if (t == ignore && o != ignore) { o = ignore; output[i] = ignore; }          // utils/pyt_utils.py:299
+    const int oi = (o >= 0 && o < K) ? static_cast<int>(o) : K;
+    const int ti = (t >= 0 && t < K) ? static_cast<int>(t) : K;
+    const int bin = oi * K1 + ti;
+    if (bin == run_bin) { ++run_cnt; return; }
+    if (run_cnt) atomicAdd(&hist[run_bin], run_cnt);
+    run_bin = bin;
+    run_cnt = 1u;
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(output) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
+  const long long nvec = vec ? n / 2 : 0;
   const long long stride = static_cast<long long>(gridDim.x) * 256;
   const long long start = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  const long long iters = (n + stride - 1) / stride;
-  for (long long it = 0; it < iters; ++it) {
-    const long long i = start + it * stride;
-    const bool active = i < n;
-    long long o = active ? output[i] : -1, t = active ? target[i] : -1;
-    if (active && t == ignore) { o = ignore; output[i] = ignore; }   // utils/pyt_utils.py:299
-    const bool o_in = active && o >= 0 && o < K;
-    const bool t_in = active && t >= 0 && t < K;
-    hist_add_warp(hist, o_in ? static_cast<int>(o) : 0, o_in && o == t);          // intersection
-    hist_add_warp(hist, o_in ? K + static_cast<int>(o) : 0, o_in);                // area_output
-    hist_add_warp(hist, t_in ? 2 * K + static_cast<int>(t) : 0, t_in);            // area_target
+  // a thread owns runs of 4 consecutive 16-byte pairs (8 pixels) so that its run-length counter sees neighbours
+  for (long long v = start * 4; v < nvec; v += stride * 4) {
+    longlong2 o2[4], t2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u < nvec) {
+        o2[u] = *reinterpret_cast<const longlong2*>(output + 2 * (v + u));
+        t2[u] = __ldg(reinterpret_cast<const longlong2*>(target + 2 * (v + u)));
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u < nvec) {
+        add(2 * (v + u), o2[u].x, t2[u].x);
+        add(2 * (v + u) + 1, o2[u].y, t2[u].y);
+      }
   }
+  for (long long i = nvec * 2 + start; i < n; i += stride) add(i, output[i], target[i]);
+  if (run_cnt) atomicAdd(&hist[run_bin], run_cnt);
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * K; i += 256)
-    if (hist[i]) atomicAdd(&ws[i], static_cast<unsigned long long>(hist[i]));
+  for (int k = threadIdx.x; k < K; k += 256) {
+    unsigned long long row = 0, col = 0;
+    for (int j = 0; j < K1; ++j) { row += hist[k * K1 + j]; col += hist[j * K1 + k]; }
+    if (hist[k * K1 + k]) atomicAdd(&ws[k], static_cast<unsigned long long>(hist[k * K1 + k]));
+    if (row) atomicAdd(&ws[K + k], row);
+    if (col) atomicAdd(&ws[2 * K + k], col);
+  }
 }
 
 __global__ void inter_union_finish_kernel(const unsigned long long* __restrict__ ws, int K, float* __restrict__ inter,

@@ -926,3 +926,20 @@ def test_head_pixel_count_not_multiple_of_eight(ops):
     ref = ref_ops.ref_head(feats.cpu().float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
     assert out.shape == ref.shape
     assert_close_rel(out.cpu(), ref, RTOL, 'padded head')
+
+
+@pytest.mark.parametrize('n,offset', [(1, 0), (7, 1), (4096 + 3, 1), (1 << 20, 0), ((1 << 20) + 1, 1)])
+def test_inter_union_odd_sizes_alignment_and_out_of_range(ops, n, offset):
+    """Odd lengths, 8-byte-misaligned views and labels outside [0,K) (histc ignores them) against the oracle."""
+    K = 12
+    gen = torch.Generator().manual_seed(n)
+    base_o = torch.randint(-2, K + 3, (n + offset,), generator=gen)
+    base_t = torch.randint(0, K, (n + offset,), generator=gen)
+    base_t[torch.rand(n + offset, generator=gen) < 0.1] = 255
+    base_t[torch.rand(n + offset, generator=gen) < 0.02] = 40            # a label beyond K that is not the ignore value
+    o_ref, t_ref = base_o[offset:].clone(), base_t[offset:].clone()
+    ri, ru, rt = ref_ops.ref_inter_union(o_ref, t_ref, K)
+    o_dev, t_dev = base_o.cuda()[offset:], base_t.cuda()[offset:]
+    gi, gu, gt = ops.intersectionAndUnionGPU(o_dev, t_dev, K)
+    assert torch.equal(gi.cpu(), ri) and torch.equal(gu.cpu(), ru) and torch.equal(gt.cpu(), rt)
+    assert torch.equal(o_dev.cpu(), o_ref)                                # same in-place side effect
