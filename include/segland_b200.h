@@ -235,8 +235,9 @@ SL_API int sl_inter_union(long long *output, const long long *target, long long 
 /* ---------------------------------------------------------------------------
  * (a9) masked_average_pooling(feature, mask), networks/pspnet.py:7-15
  *   feat [B,C,h,w] bf16; mask [B,1,H,W] fp32.
- *   mask_lr_ws [B*h*w + B*ceil(h*w/1024)] fp32 scratch: the align_corners bilinear down-sample
- *           of mask followed by per-1024-pixel chunk sums;
+ *   mask_lr_ws [B*h*w + B*ceil(h*w/1024) + 8*B*C] fp32 scratch: the align_corners bilinear down-sample
+ *           of mask, per-1024-pixel chunk sums, and up to 8 partial channel sums per image (added in
+ *           index order, so the result is bit-reproducible);
  *   per_image [B,C] fp32 = sum_hw(f*m)/(sum_hw m + 1e-5); proto [C] fp32 = mean_B.
  *   h*w % 8 == 0.
  */

@@ -43,10 +43,12 @@ __global__ void __launch_bounds__(256) map_mask_kernel(const float* __restrict__
 // ---- MAP step 2: per (image, channel) masked sum.  A warp owns MAP_CH channels at a time so each
 // mask value loaded from L1 is reused MAP_CH times; features stream once with 128-bit loads.
 constexpr int MAP_CH = 4;
-__global__ void __launch_bounds__(256) map_reduce_kernel(const uint16_t* __restrict__ feat, int C, int N,
-                                                         const float* __restrict__ mask_lr,
-                                                         const float* __restrict__ partial, int n_chunks,
-                                                         float* __restrict__ per_image) {
+// grid (ceil(C / 32), B, splits): the pixel range is cut into `splits` pieces of split_len pixels so that enough
+// warps are in flight to cover the HBM latency (B * C / 4 warps alone left the SMs a quarter full); every piece
+// writes its unnormalised sums to part[b][split][c] and map_finish_kernel adds them in index order.
+constexpr int MAP_MAX_SPLITS = 8;
+__global__ void __launch_bounds__(256) map_reduce_kernel(const uint16_t* __restrict__ feat, int C, int N, int split_len,
+                                                         const float* __restrict__ mask_lr, float* __restrict__ part) {
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = (blockIdx.x * 8 + warp) * MAP_CH;
@@ -68,8 +70,9 @@ __global__ void __launch_bounds__(256) map_reduce_kernel(const uint16_t* __restr
       acc[j] = a;
     }
   };
-  int n = lane * 8;
-  for (; n + 256 < N; n += 512) {
+  const int n_end = min(N, (static_cast<int>(blockIdx.z) + 1) * split_len);
+  int n = blockIdx.z * split_len + lane * 8;
+  for (; n + 256 < n_end; n += 512) {
     uint4 v0[MAP_CH], v1[MAP_CH];
 #pragma unroll
     for (int j = 0; j < MAP_CH; ++j) {
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(256) map_reduce_kernel(const uint16_t* __restr
     accumulate(v0, ma0, mb0);
     accumulate(v1, ma1, mb1);
   }
-  for (; n < N; n += 256) {
+  for (; n < n_end; n += 256) {
     uint4 v[MAP_CH];
 #pragma unroll
     for (int j = 0; j < MAP_CH; ++j)
@@ -90,21 +93,28 @@ __global__ void __launch_bounds__(256) map_reduce_kernel(const uint16_t* __restr
     const float4 ma = __ldg(reinterpret_cast<const float4*>(m + n)), mb = __ldg(reinterpret_cast<const float4*>(m + n + 4));
     accumulate(v, ma, mb);
   }
-  float msum = 0.f;
-  for (int i = 0; i < n_chunks; ++i) msum += partial[static_cast<size_t>(b) * n_chunks + i];
-  const float denom = msum + 1e-5f;
 #pragma unroll
   for (int j = 0; j < MAP_CH; ++j) {
     const float t = warp_sum(acc[j]);
-    if (lane == 0 && c0 + j < C) per_image[static_cast<size_t>(b) * C + c0 + j] = t / denom;
+    if (lane == 0 && c0 + j < C) part[(static_cast<size_t>(b) * gridDim.z + blockIdx.z) * C + c0 + j] = t;
   }
 }
 
-__global__ void map_mean_kernel(const float* __restrict__ per_image, int B, int C, float* __restrict__ proto) {
+// per_image[b][c] = sum_split part / (sum of the image's mask + 1e-5);  proto[c] = mean over images (fixed order)
+__global__ void map_finish_kernel(const float* __restrict__ part, int splits, const float* __restrict__ partial,
+                                  int n_chunks, int B, int C, float* __restrict__ per_image, float* __restrict__ proto) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float t = 0.f;
-  for (int b = 0; b < B; ++b) t += per_image[static_cast<size_t>(b) * C + c];
+  for (int b = 0; b < B; ++b) {
+    float msum = 0.f;
+    for (int i = 0; i < n_chunks; ++i) msum += partial[static_cast<size_t>(b) * n_chunks + i];
+    float sv = 0.f;
+    for (int z = 0; z < splits; ++z) sv += part[(static_cast<size_t>(b) * splits + z) * C + c];
+    const float v = sv / (msum + 1e-5f);
+    per_image[static_cast<size_t>(b) * C + c] = v;
+    t += v;
+  }
   proto[c] = t / static_cast<float>(B);
 }
 
@@ -184,9 +194,19 @@ extern "C" int sl_map_proto(const uint16_t* feat, const float* mask, int B, int 
   float* partial = mask_lr_ws + static_cast<size_t>(B) * N;   // [B][n_chunks] chunk sums follow the [B,N] map
   sl::map_mask_kernel<<<dim3(n_chunks, B), 256, 0, st>>>(mask, h, w, H, W, sl::ac_scale(H, h), sl::ac_scale(W, w),
                                                         mask_lr_ws, partial, n_chunks);
-  dim3 grid((C + 8 * sl::MAP_CH - 1) / (8 * sl::MAP_CH), B);
-  sl::map_reduce_kernel<<<grid, 256, 0, st>>>(feat, C, static_cast<int>(N), mask_lr_ws, partial, n_chunks, per_image);
-  sl::map_mean_kernel<<<(C + 127) / 128, 128, 0, st>>>(per_image, B, C, proto);
+  // enough pixel splits to put ~48 warps on every SM, each at least 2048 pixels long
+  const long long warps = static_cast<long long>(B) * ((C + sl::MAP_CH - 1) / sl::MAP_CH);
+  long long splits = (static_cast<long long>(sl::kNumSMs) * 48 + warps - 1) / warps;
+  if (splits > sl::MAP_MAX_SPLITS) splits = sl::MAP_MAX_SPLITS;
+  if (splits > (N + 2047) / 2048) splits = (N + 2047) / 2048;
+  if (splits < 1) splits = 1;
+  const int split_len = static_cast<int>(((N + splits - 1) / splits + 511) / 512 * 512);
+  splits = (N + split_len - 1) / split_len;
+  float* part = partial + static_cast<size_t>(B) * n_chunks;     // [B][splits][C]
+  dim3 grid((C + 8 * sl::MAP_CH - 1) / (8 * sl::MAP_CH), B, static_cast<unsigned>(splits));
+  sl::map_reduce_kernel<<<grid, 256, 0, st>>>(feat, C, static_cast<int>(N), split_len, mask_lr_ws, part);
+  sl::map_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, static_cast<int>(splits), partial, n_chunks, B, C, per_image,
+                                                        proto);
   return SL_LAUNCH_RESULT();
 }
 

@@ -506,7 +506,7 @@ def masked_average_pooling(feature, mask, return_per_image=False):
     if mask.shape[0] != B or mask.numel() != B * H * W:
         raise ValueError('mask must be [B,1,H,W]')
     dev = feature.device
-    ws = torch.empty(B * h * w + B * ((h * w + 1023) // 1024), dtype=torch.float32, device=dev)
+    ws = torch.empty(B * h * w + B * ((h * w + 1023) // 1024) + 8 * B * C, dtype=torch.float32, device=dev)
     per_image = torch.empty(B, C, dtype=torch.float32, device=dev)
     proto = torch.empty(C, dtype=torch.float32, device=dev)
     call('sl_map_proto', ptr(feature), ptr(mask), B, C, h, w, H, W, ptr(ws), ptr(per_image), ptr(proto), _stream())
