@@ -261,18 +261,19 @@ SL_API int sl_orth_loss(const float *rows, int Kr, const float *others, int Ko, 
  *     scale_pred = F.interpolate(pred, target.shape[1:], mode='bilinear', align_corners=True)
  *     loss = nn.CrossEntropyLoss(ignore_index, reduction='mean')(scale_pred, target)
  *   without materialising scale_pred.  logits_lr [B,K,h,w] fp32; target [B,H,W] int64.
- *   ws: sl_upsample_ce_ws_bytes(B,H,W) bytes, 16-byte aligned; the forward leaves the per-pixel
- *       log-sum-exp there and the backward reads it (same buffer, same shapes).
+ *   ws: sl_upsample_ce_ws_bytes(B,K,w,H,W) bytes, 16-byte aligned; the forward leaves the per-pixel
+ *       log-sum-exp there; the backward reads it and uses the rest for its row-reduced gradients
+ *       (same buffer, same shapes).
  *   fwd: loss [1] fp32 (NaN when every pixel is ignored, like torch), n_valid [1] int64.
  *   bwd: grad_out [1] fp32 = d(objective)/d(loss); grad_logits_lr [B,K,h,w] fp32 is OVERWRITTEN.
  *   Both directions are deterministic (no floating-point atomics).
  */
-SL_API size_t sl_upsample_ce_ws_bytes(int B, int H, int W);
+SL_API size_t sl_upsample_ce_ws_bytes(int B, int K, int w, int H, int W);
 SL_API int sl_upsample_ce_fwd(const float *logits_lr, int B, int K, int h, int w, int H, int W,
                        const long long *target, int ignore_label, void *ws,
                        float *loss, long long *n_valid, void *stream);
 SL_API int sl_upsample_ce_bwd(const float *logits_lr, int B, int K, int h, int w, int H, int W,
-                       const long long *target, int ignore_label, const void *ws,
+                       const long long *target, int ignore_label, void *ws,
                        const long long *n_valid, const float *grad_out,
                        float *grad_logits_lr, void *stream);
 

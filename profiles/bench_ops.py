@@ -93,6 +93,17 @@ def main():
             t = timeit(lambda: step(**kw), iters=10)
             print(f'{"train head fwd+bwd " + name + " (" + label_ + ")":58s} {t * 1e3:9.3f} ms/step '
                   f'{flops / t / 1e12:7.1f} TFLOP/s fp32-equivalent (10 C^2 N)')
+    # ---- f-1: cross-entropy of the up-sampled logits without materialising them (loss/criterion.py:51-52)
+    for name, hw in (('128^2 -> 1024^2', 128), ('256^2 -> 1024^2', 256)):
+        lgt = torch.randn(8, 12, hw, hw, device=dev, generator=g).requires_grad_(True)
+        tgt = torch.randint(0, 12, (8, 1024, 1024), device=dev, generator=g)
+
+        def ce_step():
+            lgt.grad = None
+            ops.seg_cross_entropy(lgt, tgt).backward()
+        t = timeit(ce_step, iters=10)
+        # algorithmic bytes: int64 target once per direction + low-res logits / gradients
+        report(f'seg_cross_entropy fwd+bwd K=12 {name} (int64 labels)', t, 8 * (2 * 8 * 1024 * 1024 + 3 * 12 * hw * hw * 4), 8)
     # ---- metric kernels on 1024^2 label maps (32 tiles)
     gt = torch.randint(0, 12, (32, 1024, 1024), device=dev, dtype=torch.uint8, generator=g)
     pr = torch.randint(0, 12, (32, 1024, 1024), device=dev, dtype=torch.uint8, generator=g)

@@ -69,7 +69,7 @@ def lib():
         handle.sl_pop_prepare_bwd_ws_bytes.restype = c_size_t
         handle.sl_pop_prepare_ws_bytes.argtypes = [c_int, c_int]
         handle.sl_pop_prepare_ws_bytes.restype = c_size_t
-        handle.sl_upsample_ce_ws_bytes.argtypes = [c_int, c_int, c_int]
+        handle.sl_upsample_ce_ws_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
         handle.sl_upsample_ce_ws_bytes.restype = c_size_t
         if handle.sl_abi_version() != 1:
             raise ImportError(f'{LIB_PATH}: ABI version {handle.sl_abi_version()} != 1; rebuild')

@@ -555,7 +555,7 @@ class _SegCEFn(torch.autograd.Function):
         tgt = target.detach().to(torch.int64).contiguous()
         H, W = tgt.shape[-2:]
         dev = logits.device
-        ws = torch.empty(_cabi.lib().sl_upsample_ce_ws_bytes(B, H, W), dtype=torch.uint8, device=dev)
+        ws = torch.empty(_cabi.lib().sl_upsample_ce_ws_bytes(B, K, w, H, W), dtype=torch.uint8, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         n_valid = torch.empty(1, dtype=torch.int64, device=dev)
         call('sl_upsample_ce_fwd', ptr(logits), B, K, h, w, H, W, ptr(tgt), int(ignore_index), ptr(ws), ptr(loss),
