@@ -308,30 +308,52 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
         for (int k = 0; k < KP; ++k) {
           if (k < K) {
             const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-            const float v[4] = {l0 * a.x + l1 * c.x, l0 * a.y + l1 * c.y, l0 * a.z + l1 * c.z, l0 * a.w + l1 * c.w};
+            // l0*a + l1*c on packed fp32 pairs (FMUL2 + FFMA2): same products and sums as the scalar form
+            float2 t01 = mul2(make_float2(l0, l0), make_float2(a.x, a.y)), t23 = mul2(make_float2(l0, l0), make_float2(a.z, a.w));
+            t01 = fma2(make_float2(l1, l1), make_float2(c.x, c.y), t01);
+            t23 = fma2(make_float2(l1, l1), make_float2(c.z, c.w), t23);
+            const float v[4] = {t01.x, t01.y, t23.x, t23.y};
+            if (!bad) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { argmax_step(v[j], k, best[j], idx[j]); vals[j][k] = v[j]; }
+              for (int j = 0; j < 4; ++j) { if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; } vals[j][k] = v[j]; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { argmax_step(v[j], k, best[j], idx[j]); vals[j][k] = v[j]; }
+            }
             if (logits_hr)
               __stcs(reinterpret_cast<float4*>(logits_hr + (static_cast<size_t>(b) * K + k) * HW + plane_off),
                      make_float4(v[0], v[1], v[2], v[3]));
           }
         }
         if (conf || probs) {
+          // softmax with exp2: e = 2^(v*log2e - best*log2e) (one FFMA + MUFU.EX2 per value), 1/sum by MUFU.RCP
+          constexpr float kLog2e = 1.4426950408889634f;
           float s[4] = {0.f, 0.f, 0.f, 0.f};
+          const float nb[4] = {-best[0] * kLog2e, -best[1] * kLog2e, -best[2] * kLog2e, -best[3] * kLog2e};
 #pragma unroll
           for (int k = 0; k < KP; ++k)
             if (k < K) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { vals[j][k] = __expf(vals[j][k] - best[j]); s[j] += vals[j][k]; }
+              for (int j = 0; j < 4; ++j) {
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(vals[j][k], kLog2e, nb[j])));
+                vals[j][k] = e;
+                s[j] += e;
+              }
             }
-          const float inv[4] = {1.f / s[0], 1.f / s[1], 1.f / s[2], 1.f / s[3]};
+          float inv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv[j]) : "f"(s[j]));
           if (conf) *reinterpret_cast<float4*>(conf + pix) = make_float4(inv[0], inv[1], inv[2], inv[3]);
           if (probs) {
 #pragma unroll
             for (int k = 0; k < KP; ++k)
-              if (k < K)
+              if (k < K) {
+                const float2 p01 = mul2(make_float2(vals[0][k], vals[1][k]), make_float2(inv[0], inv[1]));
+                const float2 p23 = mul2(make_float2(vals[2][k], vals[3][k]), make_float2(inv[2], inv[3]));
                 __stcs(reinterpret_cast<float4*>(probs + (static_cast<size_t>(b) * K + k) * HW + plane_off),   // streaming:
-                       make_float4(vals[0][k] * inv[0], vals[1][k] * inv[1], vals[2][k] * inv[2], vals[3][k] * inv[3]));  // written once
+                       make_float4(p01.x, p01.y, p23.x, p23.y));                                               // written once
+              }
           }
         }
       }
