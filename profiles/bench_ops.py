@@ -93,6 +93,16 @@ def main():
             t = timeit(lambda: step(**kw), iters=10)
             print(f'{"train head fwd+bwd " + name + " (" + label_ + ")":58s} {t * 1e3:9.3f} ms/step '
                   f'{flops / t / 1e12:7.1f} TFLOP/s fp32-equivalent (10 C^2 N)')
+    # ---- C4: flip test-time augmentation at feature resolution (orig + h-flip views -> mean logits)
+    views = torch.randn(2, 32, 12, 256, 256, device=dev, generator=g)
+    t = timeit(lambda: ops.aggregate_views(views, [0, 1]))
+    report('C4 aggregate_views V=2 (orig + h-flip) K=12 256^2', t, 3 * 32 * 12 * 256 * 256 * 4, 32)
+    del views
+    # ---- C3: pseudo-labelling of base images (pspnet_pop.py:221-231), 5 classifier_n channels -> int64 masks
+    p2 = torch.randn(8, 5, 128, 128, device=dev, generator=g)
+    mk = torch.zeros(8, 1024, 1024, dtype=torch.int64, device=dev)
+    t = timeit(lambda: ops.pseudo_label(p2, mk.zero_(), 7))
+    report('C3 pseudo_label 1+Kn=5, 128^2 -> 1024^2 int64 masks (+memset)', t, 8 * (3 * 8 * 1024 * 1024), 8)
     # ---- f-1: cross-entropy of the up-sampled logits without materialising them (loss/criterion.py:51-52)
     for name, hw in (('128^2 -> 1024^2', 128), ('256^2 -> 1024^2', 256)):
         lgt = torch.randn(8, 12, hw, hw, device=dev, generator=g).requires_grad_(True)

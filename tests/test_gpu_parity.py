@@ -222,6 +222,12 @@ def test_views_reduce(ops):
     views = torch.stack([base, base.flip(-1), base.flip(-2), base.flip(-1, -2)])
     out = ops.aggregate_views(views, [0, 1, 2, 3])
     assert torch.allclose(out, base, atol=1e-6)
+    # widths that are not a multiple of 4 take the scalar kernel; both against a plain torch mean of un-flipped views
+    for w in (8, 12, 6, 7):
+        b2 = torch.randn(3, 5, 9, w, generator=g).cuda()
+        v2 = torch.stack([b2 * 2, (b2 * 3).flip(-1), (b2 * 5).flip(-2)])
+        got = ops.aggregate_views(v2, [0, 1, 2])
+        assert torch.allclose(got, b2 * (10.0 / 3.0), rtol=1e-6, atol=1e-6), w
     # flip commutes with align-corners upsampling: pred(view) flipped back == pred(orig)
     p0 = ops.upsample_argmax(base, (64, 64))['pred']
     p1 = ops.upsample_argmax(base.flip(-1).contiguous(), (64, 64))['pred'].flip(-1)
