@@ -432,6 +432,56 @@ __global__ void __launch_bounds__(256) pseudo_label_kernel(const float* __restri
   }
 }
 
+// Same result, bit for bit, with the gathers hoisted: a thread owns one source cell of one output row (the four
+// corner values of every channel in registers) and visits the cell's output pixels; only pixels whose mask is 0
+// are evaluated, with ATen's association l0y*(l0x*a + l1x*b) + l1y*(l0x*c + l1x*d) as in bilerp().
+// grid (ceil(w/32), ceil(H/8), B), block 256 = 32 cells x 8 rows.  K2 <= KP.
+template <int KP>
+__global__ void __launch_bounds__(256) pseudo_label_cells_kernel(const float* __restrict__ preds2, int K2, int h, int w,
+                                                                 int H, int W, float sy, float sx, int n_base,
+                                                                 long long* __restrict__ mask) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), b = blockIdx.z;
+  if (j >= w || y >= H) return;
+  // output columns whose left source column is j (src_coord(sx, x, w).i0 == j): a contiguous range
+  auto first_x = [&](int col) {
+    if (col <= 0) return 0;
+    if (col >= w) return W;
+    int x = sx > 0.f ? static_cast<int>(ceilf(static_cast<float>(col) / sx)) : W;
+    x = max(0, min(W, x));
+    while (x > 0 && src_coord(sx, x - 1, w).i0 >= col) --x;
+    while (x < W && src_coord(sx, x, w).i0 < col) ++x;
+    return x;
+  };
+  const int x_lo = first_x(j), x_hi = first_x(j + 1) - 1;
+  if (x_hi < x_lo) return;
+  long long* mrow = mask + (static_cast<size_t>(b) * H + y) * W;
+  bool any = false;
+  for (int x = x_lo; x <= x_hi; ++x) any |= mrow[x] == 0;
+  if (!any) return;
+  const SrcCoord cy = src_coord(sy, y, h);
+  const int hw = h * w, j1 = min(j + 1, w - 1);
+  const float* r0 = preds2 + static_cast<size_t>(b) * K2 * hw + cy.i0 * w;
+  const float* r1 = r0 + cy.step * w;
+  float a[KP], bb[KP], c[KP], d[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k)
+    if (k < K2) {
+      a[k] = __ldg(r0 + j); bb[k] = __ldg(r0 + j1); c[k] = __ldg(r1 + j); d[k] = __ldg(r1 + j1);
+      r0 += hw; r1 += hw;
+    }
+  for (int x = x_lo; x <= x_hi; ++x) {
+    if (mrow[x] != 0) continue;
+    const SrcCoord cx = src_coord(sx, x, w);
+    // cx.step == 0 only in the last column, where j1 == j already
+    float best = -INFINITY;
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      if (k < K2) argmax_step(cy.l0 * (cx.l0 * a[k] + cx.l1 * bb[k]) + cy.l1 * (cx.l0 * c[k] + cx.l1 * d[k]), k, best, idx);
+    mrow[x] = idx > 0 ? idx + n_base : 0;
+  }
+}
+
 // ------------------------------------------------------------------ confusion on label maps
 __global__ void __launch_bounds__(256) confusion_kernel(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pr,
                                                         long long n, int K, int ignore_label,
@@ -658,9 +708,16 @@ extern "C" int sl_pseudo_label(const float* preds2, int B, int K2, int h, int w,
                                long long* mask, void* stream) {
   SL_CHECK_PTR(preds2); SL_CHECK_PTR(mask);
   SL_CHECK_ARG(B >= 1 && K2 >= 1 && K2 <= SL_MAX_CLASSES && h >= 1 && w >= 1 && H >= 1 && W >= 1 && n_base >= 0);
+  const float sy = sl::ac_scale(h, H), sx = sl::ac_scale(w, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (K2 <= 8 && B <= 65535 && (H + 7) / 8 <= 65535) {            // 1 + Kn channels: OEM has 5
+    const dim3 grid((w + 31) / 32, (H + 7) / 8, B);
+    if (K2 <= 5) sl::pseudo_label_cells_kernel<5><<<grid, 256, 0, st>>>(preds2, K2, h, w, H, W, sy, sx, n_base, mask);
+    else sl::pseudo_label_cells_kernel<8><<<grid, 256, 0, st>>>(preds2, K2, h, w, H, W, sy, sx, n_base, mask);
+    return SL_LAUNCH_RESULT();
+  }
   const long long items = static_cast<long long>(B) * H * W;
-  sl::pseudo_label_kernel<<<sl::grid_for(items, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      preds2, B, K2, h, w, H, W, sl::ac_scale(h, H), sl::ac_scale(w, W), n_base, mask);
+  sl::pseudo_label_kernel<<<sl::grid_for(items, 16), 256, 0, st>>>(preds2, B, K2, h, w, H, W, sy, sx, n_base, mask);
   return SL_LAUNCH_RESULT();
 }
 

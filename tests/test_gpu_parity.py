@@ -949,3 +949,17 @@ def test_inter_union_odd_sizes_alignment_and_out_of_range(ops, n, offset):
     gi, gu, gt = ops.intersectionAndUnionGPU(o_dev, t_dev, K)
     assert torch.equal(gi.cpu(), ri) and torch.equal(gu.cpu(), ru) and torch.equal(gt.cpu(), rt)
     assert torch.equal(o_dev.cpu(), o_ref)                                # same in-place side effect
+
+
+@pytest.mark.parametrize('K2,hw,HW', [(5, (16, 16), (128, 128)), (3, (9, 13), (70, 101)), (8, (8, 8), (8, 8)), (12, (8, 8), (64, 64)),
+                                      (5, (32, 32), (16, 16))])
+def test_pseudo_label_shapes_match_oracle(ops, K2, hw, HW):
+    """Cell-based kernel (K2 <= 8) and per-pixel fallback (K2 > 8), non-integer scales, identity and down-sampling,
+    against the oracle's F.interpolate + argmax; partially labelled masks keep their labels."""
+    gen = torch.Generator().manual_seed(K2 * 100 + hw[0])
+    preds2 = torch.randn(3, K2, *hw, generator=gen)
+    mask = torch.randint(0, 3, (3, *HW), generator=gen) * torch.randint(0, 2, (3, *HW), generator=gen)
+    want = ref_ops.ref_pseudo_label(preds2, mask.clone(), 7)
+    got = ops.pseudo_label(preds2.cuda(), mask.clone().cuda(), 7).cpu()
+    assert (got == want).float().mean().item() >= 0.9995
+    assert torch.equal(got[mask != 0], mask[mask != 0])
