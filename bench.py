@@ -354,9 +354,16 @@ def run_e2e(ev, head, feats_h, labels_h, Te, steps, dev, world, dist):
     from segland_b200 import ops
     n_gen = feats_h.shape[0]
     reps = (Te + n_gen - 1) // n_gen
+    # first-touch the pinned staging buffers on the GPU's NUMA node (8 ranks otherwise pull from one socket), then
+    # give the process its CPUs back for the CPU-baseline leg
+    from segland_b200 import sweep
+    cpus_before = os.sched_getaffinity(0)
+    numa_node = sweep.bind_to_gpu_numa_node(dev.index)
     f_pin = feats_h.repeat(reps, 1, 1, 1)[:Te].contiguous().pin_memory()
     l_pin = labels_h.repeat(reps, 1, 1)[:Te].contiguous().pin_memory()
     pred_pin = torch.empty(Te, TILE, TILE, dtype=torch.uint8).pin_memory()
+    pred_pin.zero_()
+    os.sched_setaffinity(0, cpus_before)
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream()
     bufs = [(torch.empty_like(f_pin, device=dev), torch.empty_like(l_pin, device=dev)) for _ in range(2)]
@@ -409,7 +416,8 @@ def run_e2e(ev, head, feats_h, labels_h, Te, steps, dev, world, dist):
     return {'value': world * Te * steps / (ms * 1e-3), 'unit': '1024x1024 tiles/s',
             'h2d_bytes_per_step': int(f_pin.numel() * 2 + l_pin.numel()),
             'd2h_bytes_per_step': int(pred_pin.numel()), 'tiles_per_step_per_gpu': Te,
-            'api': 'segland_b200.sweep.TileEvaluator.step(features_host->device, labels) + pred D2H'}
+            'api': 'segland_b200.sweep.TileEvaluator.step(features_host->device, labels) + pred D2H',
+            'host_numa_node': numa_node}
 
 
 def main():

@@ -22,6 +22,31 @@ def shard_range(n_items, rank, world_size):
     return range(start, start + base + (1 if rank < rem else 0))
 
 
+def bind_to_gpu_numa_node(device_index=None):
+    """Pin the calling process (and so its first-touch pinned host buffers) to the CPUs of the NUMA node the GPU hangs
+    off, so that eight ranks streaming features host->device do not all pull from one socket's memory.  Best effort:
+    returns the node index, or None when sysfs does not tell (containers, single-node hosts)."""
+    import os
+    try:
+        idx = torch.cuda.current_device() if device_index is None else int(device_index)
+        props = torch.cuda.get_device_properties(idx)
+        bus = f'{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0'
+        node = int(open(f'/sys/bus/pci/devices/{bus}/numa_node').read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:                                                  # noqa: BLE001  (no sysfs / no permission)
+        return None
+
+
 def all_reduce_sum_(t, group=None):
     """In-place SUM all-reduce when a process group is up; identity otherwise.  Integer tensors
     stay integer, so confusion matrices reduce bit-exactly in any rank order."""
