@@ -335,8 +335,9 @@ def run_ours(args, rank, world, local_rank):
         'roofline': roofline,
         'stage_s': stage_s,
         'e2e': e2e,
-        # per step: 5 (prepare) + head (2 launches fused incl. the prototype transpose, else fg + bg) + upsample/argmax/confusion
-        'gpu_launches': args.steps * 8,
+        # per step: 5 (prepare) + head (2 launches fused incl. the prototype transpose, else fg + bg) + upsample/argmax
+        # + confusion over (label, pred)
+        'gpu_launches': args.steps * 9,
         'clocks': clocks,
         'miou_total': float(mious[2]),
     }
