@@ -34,6 +34,14 @@ extern "C" {
 
 #define SL_ABI_VERSION 1
 
+/* Environment switches read by the library (debugging and A/B measurements only; defaults are the fast paths):
+ *   SL_TC_PAIR=0        background MLP on the single-CTA tcgen05 kernel instead of the cta_group::2 pair kernel
+ *   SL_TC_SMALL=0       C <= 128: streaming kernel instead of the weights-resident narrow-head kernel
+ *   SL_POST_FUSED_CM=1  sl_upsample_argmax counts the confusion matrix inside the interpolation kernel
+ *   SL_TC_DEBUG=<bits>  knock-outs inside the single-CTA kernel (timing experiments, results INVALID)
+ *   SL_SMALL_DBG=<ptr>  device pointer (decimal) of a 64x16 int64 buffer receiving per-tile cycle stamps of CTA 0
+ */
+
 #if defined(__GNUC__)
 #define SL_API __attribute__((visibility("default")))
 #else
