@@ -29,6 +29,23 @@ constexpr int THREADS = 64 + 32 * (EPI_WARPS + EPI2_WARPS);
 constexpr int MAX_XS = 4;
 constexpr int BAR_BYTES = 128;
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows x 16 bf16 = 8 packed 32-bit columns) comes from tensor memory
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// 32 lanes x 16 columns: thread = lane = row, 16 consecutive 32-bit columns
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
 struct SmallParams {
   int C, kblocks, xs;            // channels, k-blocks (1 or 2), feature ring slots
   int m_tiles, tiles_per_image, N, Ktot, ch;
@@ -49,10 +66,13 @@ __global__ void __launch_bounds__(THREADS, 1) bg_small_kernel(const __grid_const
   if ((base & 1023u) != 0) asm volatile("trap;");
   constexpr int kblocks = KB;
   constexpr uint32_t w_plane = static_cast<uint32_t>(kblocks) * C * 128u;          // one weight plane: kblocks x [C rows x 128 B]
-  // layout: weights [4 planes] | H1 [hi, lo][kblocks][16 KB] | X ring [xs][kblocks][16 KB] | barriers
+  // layout: weights [4 planes] | X ring [xs][kblocks][16 KB] | barriers.  The hidden tile lives in TENSOR MEMORY
+  // (columns 384.. : bf16 pairs packed per 32-bit column, hi plane then lo plane), written by the layer-1 epilogue
+  // with tcgen05.st and read by layer 2 as a TMEM A operand -- no shared-memory round trip, no proxy fence, and the
+  // layer-2 MMAs do not compete with their own A reads for shared-memory bandwidth.
   const uint32_t w_base = base;
-  const uint32_t h_base = (w_base + 4 * w_plane + 1023u) & ~1023u;
-  const uint32_t x_base = h_base + 2u * kblocks * KB_TILE;
+  const uint32_t x_base = (w_base + 4 * w_plane + 1023u) & ~1023u;
+  constexpr uint32_t H_HI_COL = 384, H_LO_COL = 384 + 64;
   const uint32_t bar0 = x_base + static_cast<uint32_t>(p.xs) * kblocks * KB_TILE;
   uint8_t* gen = smem + (bar0 - base);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 8 * (2 * MAX_XS + 8));
@@ -85,10 +105,6 @@ __global__ void __launch_bounds__(THREADS, 1) bg_small_kernel(const __grid_const
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // the hidden tile's padding columns (C..64*kblocks) are read by layer 2's MMAs against zero weights: keep them finite
-  for (uint32_t o = threadIdx.x * 16u; o < 2u * kblocks * KB_TILE; o += THREADS * 16u)
-    st_shared_v4(h_base + o, 0u, 0u, 0u, 0u);
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -125,7 +141,6 @@ __global__ void __launch_bounds__(THREADS, 1) bg_small_kernel(const __grid_const
       mbar_wait(w_bar, 0);
       // descriptor bases: the start-address field is the low 14 bits (>> 4), so stepping is an integer add
       const uint64_t db_w1 = make_desc(w_base, 16, 1024);
-      const uint64_t da_h = make_desc(h_base, 16, 1024);
       int slot = 0; uint32_t phase = 0;
       // Issue order G1(0) | G1(1) G2(0) | G1(2) G2(1) | ...: layer 1 of the next tile runs on the tensor core while the
       // layer-1 epilogue of the current one converts its accumulators; layer 2 follows as soon as the hidden tile is in
@@ -167,9 +182,9 @@ __global__ void __launch_bounds__(THREADS, 1) bg_small_kernel(const __grid_const
           for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
             for (int k = 0; k < (kb == KB - 1 ? KSL : 4); ++k)
-              tc_mma(tmem_base + 256u, da_h + ((((pass == 1 ? 1 : 0) * KB + kb) * KB_TILE + k * (UMMA_K * 2)) >> 4),
-                     db_w1 + ((((pass == 2 ? 3 : 2) * w_plane) + kb * C * 128 + k * (UMMA_K * 2)) >> 4), idesc_g2,
-                     (pass | kb | k) ? 1u : 0u);
+              tc_mma_ts(tmem_base + 256u, tmem_base + (pass == 1 ? H_LO_COL : H_HI_COL) + (kb * BLOCK_K + k * UMMA_K) / 2,
+                        db_w1 + ((((pass == 2 ? 3 : 2) * w_plane) + kb * C * 128 + k * (UMMA_K * 2)) >> 4), idesc_g2,
+                        (pass | kb | k) ? 1u : 0u);
         tc_commit(tfull2_bar);
         stamp(s, 5);
       }
@@ -184,7 +199,6 @@ __global__ void __launch_bounds__(THREADS, 1) bg_small_kernel(const __grid_const
     const int half = (warp - 2) >> 2;
     constexpr int n_chunks = C / 32;                         // <= 4: at most 2 chunks per warp
     constexpr int c_split = (n_chunks + 1) / 2;
-    const uint32_t sw = static_cast<uint32_t>(row & 7);
     const int c_begin = half == 0 ? 0 : c_split, c_end = half == 0 ? c_split : n_chunks;
     for (int s = 0; s < n_my; ++s) {
       const int b = s & 1;
@@ -219,21 +233,15 @@ __global__ void __launch_bounds__(THREADS, 1) bg_small_kernel(const __grid_const
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         if (c_begin + i < c_end) {
-          const int c0 = (c_begin + i) * 32;
-          const uint32_t kb = static_cast<uint32_t>(c0 >> 6), chunk0 = static_cast<uint32_t>((c0 & 63) >> 3);
-          const uint32_t rb_hi = h_base + kb * KB_TILE + static_cast<uint32_t>(row) * 128u;
-          const uint32_t rb_lo = rb_hi + static_cast<uint32_t>(kblocks) * KB_TILE;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t off = ((chunk0 + q) ^ sw) << 4;
-            st_shared_v4(rb_hi + off, hi[i][4 * q], hi[i][4 * q + 1], hi[i][4 * q + 2], hi[i][4 * q + 3]);
-            st_shared_v4(rb_lo + off, lo[i][4 * q], lo[i][4 * q + 1], lo[i][4 * q + 2], lo[i][4 * q + 3]);
-          }
+          const uint32_t col = static_cast<uint32_t>((c_begin + i) * 16);       // 32 channels = 16 packed columns
+          const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
+          tc_st16(lane_addr + H_HI_COL + col, hi[i]);
+          tc_st16(lane_addr + H_LO_COL + col, lo[i]);
         }
       }
-      fence_async_smem();                                    // generic-proxy writes -> visible to the tensor core (async proxy)
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
       __syncwarp();
-      if (warp == 2 && lane == 0) stamp(s, 9);
       if (lane == 0) mbar_arrive(h1_bar);
     }
   } else {
@@ -298,7 +306,7 @@ int sl_pop_bg_small_launch(const uint16_t* feat, int B, int C, int N, const uint
     p.dbg = de ? reinterpret_cast<long long*>(strtoull(de, nullptr, 10)) : nullptr;
   }
   const size_t w_bytes = (static_cast<size_t>(4) * p.kblocks * C * 128 + 1023) / 1024 * 1024;
-  const size_t h_bytes = static_cast<size_t>(2) * p.kblocks * KB_TILE;
+  const size_t h_bytes = 0;                                             // the hidden tile lives in tensor memory
   const size_t x_slot = static_cast<size_t>(p.kblocks) * KB_TILE;
   const size_t budget = 232448 - 1024 - BAR_BYTES;                      // minus alignment slack and barriers
   int xs = static_cast<int>((budget - w_bytes - h_bytes) / x_slot);
