@@ -7,13 +7,16 @@
 //   * all four weight planes (W1' hi/lo, W2 hi/lo; <= 128 KB in UMMA layout) are loaded ONCE per CTA and stay
 //     in shared memory,
 //   * a feature tile is loaded once (one ring slot holds all its k-blocks) and serves both layer-1 passes,
-//   * the hidden tile never leaves the SM: the layer-1 epilogue writes relu(.) as bf16 hi/lo straight into
-//     shared memory in the K-major SWIZZLE_128B layout layer 2's A operand wants.
-// Shared->tensor traffic aside, the only memory traffic left is the features (HBM) and 4 bytes per pixel out.
+//   * the hidden tile never leaves the SM: the layer-1 epilogue packs relu(.) as bf16 hi/lo pairs and writes them
+//     with tcgen05.st into TENSOR MEMORY, and layer 2 takes its A operand from there (tcgen05.mma with a TMEM A
+//     address), so its MMAs read only B from shared memory.
+// The only memory traffic left is the features (HBM) and 4 bytes per pixel out.
 // Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = layer-1 epilogue, warps 10-13 =
 // layer-2 epilogue (separate warps, so the logit reduction of tile t overlaps the layer-1 epilogue of tile t+1:
 // layer 1 of tile t+1 is issued before layer 2 of tile t and has its own pair of TMEM accumulators, so with one
 // hidden-tile slot per SM the per-tile cycle is: hidden-tile stores -> layer-2 MMAs -> next tile's stores).
+// SM resources at C = 128: 128 KB weights + 3 x 32 KB feature slots of shared memory; TMEM columns 0 / 128 (layer-1
+// accumulators), 256 (layer 2), 384.. (hidden tile, C/2 packed columns per plane).
 #include <cstdlib>
 #include "tma.cuh"
 
