@@ -315,7 +315,9 @@ int sl_pop_bg_small_launch(const uint16_t* feat, int B, int C, int N, const uint
   int xs = static_cast<int>((budget - w_bytes - h_bytes) / x_slot);
   if (xs < 1) return static_cast<int>(cudaErrorInvalidConfiguration);
   p.xs = xs > MAX_XS ? MAX_XS : xs;
-  const size_t smem = w_bytes + h_bytes + p.xs * x_slot + BAR_BYTES + 1024;
+  // at least 117 KB so that two CTAs can never share an SM: each allocates all 512 TMEM columns
+  size_t smem = w_bytes + h_bytes + p.xs * x_slot + BAR_BYTES + 1024;
+  if (smem < 117 * 1024) smem = 117 * 1024;
   SmallMaps m;
   int rc;
   {
