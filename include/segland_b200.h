@@ -296,6 +296,39 @@ SL_API int sl_fuse_argmax(const float *const *mats_host, int M, int K, long long
                    uint8_t *pred, float *fused,
                    const uint8_t *label, int ignore_label, long long *cm, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * (f-4) decoder tails: the last operators of the reference's decoders, emitting the head's bf16 NCHW features
+ *   directly, so the fp32 feature tensor makes no round trip through HBM between decoder and head (the
+ *   reference hands fp32 features to orthogonal_decompose, pspnet_pop.py:142-148; the bf16 conversion is this
+ *   repo's input format).  x / maps are fp32 [B,C,N] (NCHW, N = h*w, N % 8 == 0, 16-byte aligned);
+ *   feat_out is [B,C,N] bf16 = round-to-nearest-even of the fp32 result.
+ *
+ * sl_tail_layernorm: FPN_Seg_OCR_Decoder.norm, networks/convnext_pop.py:13,27 --
+ *   nn.LayerNorm(C) applied over the channel axis of every pixel (biased variance, eps inside the sqrt),
+ *   y = (x - mean) / sqrt(var + eps) * gamma[c] + beta[c].  C <= 1536.
+ *
+ * sl_tail_bn_relu_conv: PSPModule.bottleneck[1:4], networks/pspnet_pop.py:19-22 (and PSP_Plus_Decoder.fc[1:4],
+ *   networks/pspplus_pop.py:44-47): inference-mode BatchNorm2d -> ReLU -> 1x1 convolution with bias,
+ *   y[co] = bias[co] + sum_ci W[co][ci] * relu(bn(x)[ci]).  The convolution runs on tcgen05 as a split-bf16
+ *   product (3 passes, fp32 accumulation, ~1e-5 of fp32).  bn_weight == NULL skips the normalisation
+ *   (then bn_bias/mean/var are ignored); relu == 0 skips the ReLU; bias may be NULL.
+ *   W_hi/W_lo [Cout][Cin] bf16 come from sl_tail_conv_prepare(W [Cout][Cin] fp32), once per weight update.
+ *   Cin % 8 == 0; ws: sl_tail_bn_relu_conv_ws_bytes(B, Cin, N) bytes, 128-byte aligned.
+ *
+ * sl_tail_sum: torch.stack(fpn_outs, dim=-1).sum(-1), networks/swin_pop.py:169-172, lsk_pop.py:163-165:
+ *   maps_host is a HOST array of M <= 8 device pointers, each n fp32 elements (n % 8 == 0); sequential fp32 adds
+ *   in map order.
+ */
+SL_API int sl_tail_layernorm(const float *x, int B, int C, int N, const float *gamma, const float *beta, float eps,
+                      uint16_t *feat_out, void *stream);
+SL_API int sl_tail_conv_prepare(const float *W, int Cout, int Cin, uint16_t *W_hi, uint16_t *W_lo, void *stream);
+SL_API size_t sl_tail_bn_relu_conv_ws_bytes(int B, int Cin, int N);
+SL_API int sl_tail_bn_relu_conv(const float *x, int B, int Cin, int N,
+                         const float *bn_weight, const float *bn_bias, const float *bn_mean, const float *bn_var,
+                         float bn_eps, int relu, const uint16_t *W_hi, const uint16_t *W_lo, const float *bias,
+                         int Cout, void *ws, uint16_t *feat_out, void *stream);
+SL_API int sl_tail_sum(const float *const *maps_host, int M, long long n, uint16_t *feat_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

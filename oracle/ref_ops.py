@@ -243,3 +243,37 @@ def ref_eval_tile(features, label, base_emb, novel_emb, cls, cls_n, out_size, n_
     pred = ref_upsample_argmax(logits, out_size)
     cm = ref_confusion(label, pred, n_classes)
     return pred, cm, logits
+
+
+# --------------------------------------------------------------------------- decoder tails
+def ref_tail_layernorm(x, gamma, beta, eps=1e-5):
+    """FPN_Seg_OCR_Decoder.norm applied channels-last, networks/convnext_pop.py:13,27:
+    self.norm(feats.permute(0, 2, 3, 1)).permute(0, 3, 1, 2).  x [B,C,h,w] fp32 -> fp32."""
+    C = x.shape[1]
+    return F.layer_norm(x.permute(0, 2, 3, 1), (C,), gamma, beta, eps).permute(0, 3, 1, 2)
+
+
+def ref_tail_bn_relu_conv(x, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, W, bias, relu=True):
+    """PSPModule.bottleneck[1:4] in eval mode, networks/pspnet_pop.py:19-22: BatchNorm2d (running statistics)
+    -> ReLU -> Conv2d(C, C, kernel_size=1) with bias.  x [B,Cin,h,w]; W [Cout,Cin]; -> fp32 [B,Cout,h,w]."""
+    y = x
+    if bn_weight is not None:
+        y = F.batch_norm(y, bn_mean, bn_var, bn_weight, bn_bias, False, 0.0, bn_eps)
+    if relu:
+        y = F.relu(y)
+    return F.conv2d(y, W.reshape(W.shape[0], W.shape[1], 1, 1), bias)
+
+
+def ref_tail_sum(maps):
+    """torch.stack(fpn_outs, dim=-1).sum(-1), networks/swin_pop.py:169-172 / lsk_pop.py:163-165."""
+    return torch.stack(list(maps), dim=-1).sum(-1)
+
+
+def bf16_ulp_report(got_bf16, ref_fp32):
+    """How a bf16 feature tensor compares with round-to-nearest(ref_fp32): fraction of identical bit patterns and
+    the largest |got - ref_fp32| in units of the reference element's bf16 spacing (0.5 = ideal rounding)."""
+    got = got_bf16.float().double()
+    ref = ref_fp32.double()
+    exact = (got_bf16 == ref_fp32.to(torch.bfloat16)).float().mean().item()
+    spacing = torch.pow(2.0, torch.floor(torch.log2(ref.abs().clamp_min(1e-30))) - 7)
+    return exact, ((got - ref).abs() / spacing)

@@ -34,6 +34,10 @@ _SIGNATURES = {
     'sl_orth_loss': [_P, c_int, _P, c_int, c_int, _P, _P, _P, _P],
     'sl_fuse_argmax': [POINTER(_P), c_int, c_int, c_longlong, c_int, _P, _P, _P, c_int, _P, _P],
     'sl_upsample_ce_fwd': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P],
+    'sl_tail_layernorm': [_P, c_int, c_int, c_int, _P, _P, c_float, _P, _P],
+    'sl_tail_conv_prepare': [_P, c_int, c_int, _P, _P, _P],
+    'sl_tail_bn_relu_conv': [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, c_int, _P, _P, _P],
+    'sl_tail_sum': [POINTER(_P), c_int, c_longlong, _P, _P],
     'sl_upsample_ce_bwd': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P],
 }
 
@@ -71,6 +75,8 @@ def lib():
         handle.sl_pop_prepare_ws_bytes.restype = c_size_t
         handle.sl_upsample_ce_ws_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
         handle.sl_upsample_ce_ws_bytes.restype = c_size_t
+        handle.sl_tail_bn_relu_conv_ws_bytes.argtypes = [c_int, c_int, c_int]
+        handle.sl_tail_bn_relu_conv_ws_bytes.restype = c_size_t
         if handle.sl_abi_version() != 1:
             raise ImportError(f'{LIB_PATH}: ABI version {handle.sl_abi_version()} != 1; rebuild')
         _lib = handle
@@ -79,7 +85,7 @@ def lib():
 
 def exported_names():
     return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes', 'sl_pop_prepare_ws_bytes', 'sl_upsample_ce_ws_bytes',
-                                     'sl_pop_head_bwd_ws_bytes', 'sl_pop_prepare_bwd_ws_bytes']
+                                     'sl_pop_head_bwd_ws_bytes', 'sl_pop_prepare_bwd_ws_bytes', 'sl_tail_bn_relu_conv_ws_bytes']
 
 
 def call(name, *args):

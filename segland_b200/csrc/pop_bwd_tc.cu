@@ -31,7 +31,7 @@ static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory li
 constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
 
 enum LoadKind { LD_K2D = 0, LD_MN2D = 1, LD_MN3D = 2, LD_K3D = 3 };
-enum EpiKind { EPI_RELU_SPLIT = 0, EPI_LAYER2 = 1, EPI_MASK_SPLIT = 2, EPI_RED = 3, EPI_DFEAT = 4 };
+enum EpiKind { EPI_RELU_SPLIT = 0, EPI_LAYER2 = 1, EPI_MASK_SPLIT = 2, EPI_RED = 3, EPI_DFEAT = 4, EPI_TAIL = 5 };
 
 struct GemmMaps { CUtensorMap a[3], b[3]; };
 
@@ -50,6 +50,7 @@ struct GemmParams {
   float* dw3;
   float* red_out;
   float* d_feat; const float* gp; const float* s_hat; int K;
+  uint16_t* tail_out; const float* tail_bias; int C_out;    // EPI_TAIL: bf16 NCHW features = acc + bias (decoder tail, f-4)
 };
 
 __device__ __forceinline__ void split_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -319,6 +320,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                           make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
                                       __uint_as_float(r[4 * q + 3])));
           }
+        } else if (EPI == EPI_TAIL) {  // features[img][col][n] = bf16(acc + bias[col]): the head's input layout
+          if (row_ok) {
+            uint16_t* o = p.tail_out + (static_cast<long long>(img) * p.C_out + col0) * p.N_img + n_in_img;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) {
+                const float bj = p.tail_bias != nullptr ? __ldg(p.tail_bias + col0 + j) : 0.f;
+                o[static_cast<long long>(j) * p.N_img] = f32_to_bf16_rn(__uint_as_float(r[j]) + bj);
+              }
+          }
         } else {  // EPI_DFEAT: d_q[img][col][n] = acc (the projection term is added by dfeat_proj_kernel)
           if (row_ok) {
             float* o = p.d_feat + (static_cast<long long>(img) * p.C + col0) * p.N_img + n_in_img;
@@ -417,6 +428,34 @@ static int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t st) {
 
 }  // namespace tcg
 }  // namespace sl
+
+// Decoder tail: the final 1x1 convolution of PSPModule.bottleneck (networks/pspnet_pop.py:22)
+// as a split-bf16 GEMM whose epilogue adds the bias and stores the head's bf16 NCHW features directly.
+//   act_hi/lo [B,Cin,N] bf16 planes of relu(bn(x)) (tails.cu), W_hi/lo [Cout][Cin]; 3 passes, ~1e-5 of fp32.
+int sl_tail_gemm_run(const uint16_t* act_hi, const uint16_t* act_lo, int B, int Cin, int N, const uint16_t* W_hi,
+                     const uint16_t* W_lo, const float* bias, int Cout, uint16_t* feat_out, cudaStream_t st) {
+  using namespace sl::tcg;
+  GemmParams p{};
+  p.C = Cin; p.N_img = N; p.B = B; p.C_out = Cout;
+  p.NT = (Cout + 63) / 64 * 64 < MAX_NT ? (Cout + 63) / 64 * 64 : MAX_NT;
+  p.n_tiles = (Cout + p.NT - 1) / p.NT;
+  p.n_valid = Cout; p.m_valid = Cout;
+  p.m_tiles_per_img = (N + BLOCK_M - 1) / BLOCK_M;
+  p.m_is_px = 1; p.k_is_px = 0; p.k_flat = 0;
+  p.m_tiles = B * p.m_tiles_per_img; p.k_chunks = 1; p.chunks_per_img = 1; p.chunk_kb = 0;
+  p.a_policy = L2_EVICT_FIRST; p.b_policy = L2_EVICT_LAST;
+  p.passes = 3; p.a_kind = LD_MN3D; p.b_kind = LD_K2D;
+  p.tail_out = feat_out; p.tail_bias = bias;
+  GemmMaps m{};
+  int rc;
+  const uint16_t* as[3] = {act_hi, act_lo, act_hi};
+  const uint16_t* bs[3] = {W_hi, W_hi, W_lo};
+  for (int i = 0; i < 3; ++i) {
+    if ((rc = map3d(&m.a[i], as[i], N, Cin, B, 64, BLOCK_K)) != 0) return rc;
+    if ((rc = map2d(&m.b[i], bs[i], Cin, Cout, BLOCK_K, p.NT)) != 0) return rc;
+  }
+  return launch<EPI_TAIL>(m, p, st);
+}
 
 // capacity of the sign-fix-up queue: ~0.1 % of the elements are expected, 1.6 % fit (the rest stay as computed)
 int sl_pop_bwd_flag_cap(long long px, int C) {

@@ -624,3 +624,100 @@ def fuse_logits(mats, n_lists=None, label=None, cm=None, ignore_label=IGNORE_LAB
     call('sl_fuse_argmax', ptr_array(mats), len(mats), K, HW, int(len(mats) if n_lists is None else n_lists),
          ptr(pred), ptr(fused), ptr(label) if cm is not None else None, int(ignore_label), ptr(cm), _stream())
     return (pred, fused) if want_fused else pred
+
+
+# ============================================================== decoder tails
+def _tail_out(x, C_out, out):
+    B, _, h, w = x.shape
+    if out is None:
+        out = torch.empty(B, C_out, h, w, dtype=torch.bfloat16, device=x.device)
+    elif out.dtype != torch.bfloat16 or tuple(out.shape) != (B, C_out, h, w) or not out.is_contiguous():
+        raise ValueError(f'out must be a contiguous bf16 [{B},{C_out},{h},{w}] tensor')
+    return out
+
+
+def _tail_in(x):
+    x = _cuda(x, torch.float32)
+    if x.dim() != 4:
+        raise ValueError(f'expected [B,C,h,w], got {tuple(x.shape)}')
+    if (x.shape[2] * x.shape[3]) % 8:
+        raise ValueError('h*w must be a multiple of 8 (the head pads other sizes itself: hand it fp32 features)')
+    return x
+
+
+def layernorm_tail(x, weight, bias, eps=1e-5, out=None):
+    """The last line of FPN_Seg_OCR_Decoder.forward (networks/convnext_pop.py:27):
+    `self.norm(feats.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)` with nn.LayerNorm(C), returned as the contiguous bf16
+    [B,C,h,w] feature tensor PopHead consumes (the reference keeps fp32; bf16 features are north_star's format).
+    x is the 1x1 convolution's fp32 output [B,C,h,w]."""
+    x = _tail_in(x)
+    B, C, h, w = x.shape
+    out = _tail_out(x, C, out)
+    call('sl_tail_layernorm', ptr(x), B, C, h * w, ptr(_cuda(weight.detach(), torch.float32)),
+         ptr(_cuda(bias.detach(), torch.float32)), float(eps), ptr(out), _stream())
+    return out
+
+
+class ConvTail:
+    """BN (inference) -> ReLU -> 1x1 convolution + bias -> bf16 features: PSPModule.bottleneck[1:4]
+    (networks/pspnet_pop.py:19-22) and PSP_Plus_Decoder.fc[1:4] (networks/pspplus_pop.py:44-47).
+    `from_sequential(seq)` takes the reference's nn.Sequential [conv3x3, norm, ReLU, conv1x1]; `__call__(x)` takes
+    the 3x3 convolution's fp32 output.  The split weights are rebuilt by `refresh()` after a weight update."""
+
+    def __init__(self, W, bias=None, bn=None, relu=True, device=None):
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        self._W = W
+        self._bias = bias
+        self._bn = bn                 # (weight, bias, running_mean, running_var, eps) or None
+        self.relu = bool(relu)
+        self._ws = None
+        self.refresh()
+
+    @classmethod
+    def from_sequential(cls, seq, **kw):
+        norm, conv = seq[1], seq[3]
+        if conv.kernel_size != (1, 1) or not isinstance(seq[2], torch.nn.ReLU):
+            raise ValueError('expected [conv, norm, ReLU, 1x1 conv]')
+        if norm.training:
+            raise ValueError('ConvTail folds running statistics: put the decoder in eval() mode')
+        bn = (norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.eps)
+        return cls(conv.weight, conv.bias, bn=bn, relu=True, device=conv.weight.device, **kw)
+
+    def refresh(self):
+        f32 = lambda t: None if t is None else t.detach().to(self.device, torch.float32).contiguous()
+        W = f32(self._W)
+        W = W.reshape(W.shape[0], -1)
+        self.C_out, self.C_in = W.shape
+        self.bias = f32(self._bias)
+        self.bn = None if self._bn is None else tuple(f32(t) for t in self._bn[:4]) + (float(self._bn[4]),)
+        self.W_hi = torch.empty(self.C_out, self.C_in, dtype=torch.int16, device=self.device)
+        self.W_lo = torch.empty_like(self.W_hi)
+        with torch.cuda.device(self.device):
+            call('sl_tail_conv_prepare', ptr(W), self.C_out, self.C_in, ptr(self.W_hi), ptr(self.W_lo), _stream())
+
+    def __call__(self, x, out=None):
+        x = _tail_in(x)
+        B, C, h, w = x.shape
+        if C != self.C_in:
+            raise ValueError(f'expected {self.C_in} input channels, got {C}')
+        out = _tail_out(x, self.C_out, out)
+        need = _cabi.lib().sl_tail_bn_relu_conv_ws_bytes(B, C, h * w)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        bn = self.bn or (None, None, None, None, 0.0)
+        call('sl_tail_bn_relu_conv', ptr(x), B, C, h * w, ptr(bn[0]), ptr(bn[1]), ptr(bn[2]), ptr(bn[3]), float(bn[4]),
+             int(self.relu), ptr(self.W_hi), ptr(self.W_lo), ptr(self.bias), self.C_out, ptr(self._ws), ptr(out), _stream())
+        return out
+
+
+def sum_tail(maps, out=None):
+    """`torch.stack(fpn_outs, dim=-1).sum(-1)` (networks/swin_pop.py:169-172, lsk_pop.py:163-165) as bf16 features:
+    maps is the list of same-shape fp32 [B,C,h,w] FPN outputs (already interpolated), added in list order."""
+    maps = [_tail_in(m) for m in maps]
+    for m in maps:
+        if m.shape != maps[0].shape:
+            raise ValueError('all maps must share one shape')
+    out = _tail_out(maps[0], maps[0].shape[1], out)
+    call('sl_tail_sum', ptr_array(maps), len(maps), maps[0].numel(), ptr(out), _stream())
+    return out

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import ref_ops
-from helpers import bf16_from_bits, state_from_npz
+from helpers import bf16_from_bits, rel_err, state_from_npz
 
 HEAD_CASES = ['head_base_c64', 'head_ft_c64', 'head_base_c512', 'head_ft_c192_s4', 'head_ft_c96_rand']
 
@@ -147,3 +147,25 @@ def test_forward_base_gradients(golden):
     for g, key in zip(got, ['g_base_emb', 'g_W1', 'g_W2', 'g_w3', 'g_img']):
         ref = torch.from_numpy(z[f'base_c64_{key}']).reshape(g.shape)
         assert (g - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-9, key
+
+
+# ------------------------------------------------------------------ decoder tails
+def test_tails_match_reference_decoders(golden):
+    """oracle tail functions vs what the reference's PSPModule / FPN_Seg_OCR_Decoder / UperNet_Decoder_Plus computed
+    from the hooked tail inputs (oracle/gen_golden_tails.py)."""
+    z = golden('tails')
+    t = lambda k: torch.from_numpy(z[k].copy())
+    for name in ('psp_c64', 'psp_c512', 'psp_c96'):
+        out = ref_ops.ref_tail_bn_relu_conv(t(name + '_x'), t(name + '_bn_w'), t(name + '_bn_b'), t(name + '_bn_m'),
+                                            t(name + '_bn_v'), float(z[name + '_bn_eps']), t(name + '_W'), t(name + '_bias'))
+        # same ATen kernels; the convolution's blocking may differ with the thread count, hence 1e-6 not bit-exact
+        assert rel_err(out, z[name + '_out']) <= 1e-6, name
+    for name in ('ln_c192', 'ln_c96', 'ln_c480', 'ln_c40'):
+        out = ref_ops.ref_tail_layernorm(t(name + '_x'), t(name + '_gamma'), t(name + '_beta'), float(z[name + '_eps']))
+        assert np.array_equal(out.numpy(), z[name + '_out']), name
+    maps = [t(f'sum_swin_map{i}') for i in range(4)]
+    assert np.array_equal(ref_ops.ref_tail_sum(maps).numpy(), z['sum_swin_out'])
+    # the report helper: ideal rounding is <= 0.5 spacings everywhere and 100 % identical patterns
+    ref = t('ln_c96_out')
+    exact, d = ref_ops.bf16_ulp_report(ref.to(torch.bfloat16), ref)
+    assert exact == 1.0 and d.max().item() <= 0.5
