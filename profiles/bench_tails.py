@@ -20,7 +20,8 @@ from bench_ops import report, timeit  # noqa: E402
 def main():
     dev = 'cuda'
     g = torch.Generator(dev).manual_seed(0)
-    for name, C, hw, T in (('ConvNeXt-T C=192 256^2', 192, 256, 16), ('Swin-T/S C=96 256^2', 96, 256, 32),
+    conv_only = '--conv-only' in sys.argv
+    for name, C, hw, T in () if conv_only else (('ConvNeXt-T C=192 256^2', 192, 256, 16), ('Swin-T/S C=96 256^2', 96, 256, 32),
                            ('HRNet-w32 C=480 256^2', 480, 256, 8)):
         x = torch.randn(T, C, hw, hw, device=dev, generator=g)
         gamma, beta = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev)
@@ -31,7 +32,7 @@ def main():
                    .to(torch.bfloat16).contiguous(), iters=5)
         report(f'  eager: layer_norm(permute) -> permute -> bf16 contiguous', t, x.numel() * 6, T)
         del x, out
-    for name, C, hw, T, M in (('Swin-T/S C=96 256^2 M=4', 96, 256, 16, 4), ('LSK-T C=192 256^2 M=4', 192, 256, 8, 4)):
+    for name, C, hw, T, M in () if conv_only else (('Swin-T/S C=96 256^2 M=4', 96, 256, 16, 4), ('LSK-T C=192 256^2 M=4', 192, 256, 8, 4)):
         maps = [torch.randn(T, C, hw, hw, device=dev, generator=g) for _ in range(M)]
         out = torch.empty(T, C, hw, hw, dtype=torch.bfloat16, device=dev)
         t = timeit(lambda: ops.sum_tail(maps, out=out))
@@ -50,6 +51,8 @@ def main():
         flops = 2 * C * C * hw * hw * T
         print(f'{"conv_tail BN+ReLU+1x1 conv+bias -> bf16 " + name:58s} {t * 1e6 / T:9.2f} us/tile {T / t:10.0f} tiles/s '
               f'{flops / t / 1e12:7.1f} TFLOP/s algorithmic ({3 * flops / t / 1e12:.0f} executed), {x.numel() * 6 / t / 1e9:.0f} GB/s in+out')
+        if conv_only:
+            continue
         with torch.no_grad():
             for tf32 in (True, False):
                 torch.backends.cudnn.allow_tf32 = tf32

@@ -653,8 +653,10 @@ def layernorm_tail(x, weight, bias, eps=1e-5, out=None):
     x = _tail_in(x)
     B, C, h, w = x.shape
     out = _tail_out(x, C, out)
-    call('sl_tail_layernorm', ptr(x), B, C, h * w, ptr(_cuda(weight.detach(), torch.float32)),
-         ptr(_cuda(bias.detach(), torch.float32)), float(eps), ptr(out), _stream())
+    gamma, beta = _cuda(weight.detach(), torch.float32), _cuda(bias.detach(), torch.float32)   # keep both alive
+    if gamma.numel() != C or beta.numel() != C:
+        raise ValueError(f'LayerNorm weight/bias must have {C} elements')
+    call('sl_tail_layernorm', ptr(x), B, C, h * w, ptr(gamma), ptr(beta), float(eps), ptr(out), _stream())
     return out
 
 
@@ -682,7 +684,7 @@ class ConvTail:
         if norm.training:
             raise ValueError('ConvTail folds running statistics: put the decoder in eval() mode')
         bn = (norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.eps)
-        return cls(conv.weight, conv.bias, bn=bn, relu=True, device=conv.weight.device, **kw)
+        return cls(conv.weight, conv.bias, bn=bn, relu=True, device=conv.weight.device if conv.weight.is_cuda else None, **kw)
 
     def refresh(self):
         f32 = lambda t: None if t is None else t.detach().to(self.device, torch.float32).contiguous()

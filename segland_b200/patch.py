@@ -8,7 +8,9 @@ replaces, in place,
     (`eval_base.py:167`, `eval_ft.py:167`, `ft_pop.py:327`, `train_base.py:331`) the head after the
     decoder -- `orthogonal_decompose` + `classifier` / `classifier_n` + channel assembly
     (`pspnet_pop.py:143-159`, `:171-182`) -- runs in libsegland_b200.so; backbones and decoders stay
-    stock PyTorch.  Training-mode calls on CUDA tensors -- `forward_novel` (`ft_pop.py:252`,
+    stock PyTorch, except that in inference the decoder's last operators (PSPModule.bottleneck[1:4],
+    `pspnet_pop.py:19-22`; FPN_Seg_OCR_Decoder.norm, `convnext_pop.py:27`) run fused and emit the head's bf16
+    features directly (`patch(tails=False)` disables it).  Training-mode calls on CUDA tensors -- `forward_novel` (`ft_pop.py:252`,
     `pspnet_pop.py:191-245`) and `forward_base` with a criterion (`train_base.py:259`, `:161-189`) -- run
     the same head with autograd (`ops.forward_novel_train` / `ops.forward_base_train`: forward kernels +
     `sl_pop_head_bwd`), so gradients reach `novel_emb`, `classifier_n`, `classifier`, `base_emb` and the
@@ -33,13 +35,92 @@ _BASE_FORWARD = ('pspnet_pop', 'pspplus_pop', 'deeplab_pop')     # ResNet backbo
 _originals = []
 
 
-def _features(model, img):
-    """The part of forward_all/forward_base before the head (`pspnet_pop.py:141-142` and siblings)."""
+def _features(model, img, fused_tail=False):
+    """The part of forward_all/forward_base before the head (`pspnet_pop.py:141-142` and siblings).
+    fused_tail (inference only): the decoder's last operators run in libsegland_b200.so and hand the head bf16
+    features directly."""
     if hasattr(model, 'net') and not hasattr(model, 'decoder'):           # vggunet_pop.py
         return model.net(img)
     name = type(model).__module__.rsplit('.', 1)[-1]
     feats = model.backbone.base_forward(img) if name in _BASE_FORWARD else model.backbone(img)
+    if fused_tail and _tails_enabled[0]:
+        return _decode_fused(model.decoder, feats)
     return model.decoder(feats)
+
+
+class _ConvTailSeq(torch.nn.Module):
+    """Stands in for `[conv3x3, norm, ReLU, conv1x1]` (PSPModule.bottleneck, `pspnet_pop.py:18-23`;
+    PSP_Plus_Decoder.fc, `pspplus_pop.py:44-47`) during one inference call: the reference's own 3x3 convolution, then
+    BN -> ReLU -> 1x1 conv + bias -> bf16 in one C-ABI call."""
+
+    def __init__(self, seq):
+        super().__init__()
+        self.seq = seq
+        self.sig = None
+        self.tail = None
+
+    def forward(self, x):
+        x = self.seq[0](x)
+        if (x.shape[2] * x.shape[3]) % 8 or not x.is_cuda:
+            return self.seq[3](self.seq[2](self.seq[1](x)))
+        params = [self.seq[1].weight, self.seq[1].bias, self.seq[1].running_mean, self.seq[1].running_var,
+                  self.seq[3].weight, self.seq[3].bias]
+        sig = tuple((p.data_ptr(), p._version) for p in params)
+        if self.sig != sig:
+            self.tail, self.sig = ops.ConvTail.from_sequential(self.seq), sig
+        return self.tail(x)
+
+
+class _LayerNormTail(torch.nn.Module):
+    """Stands in for FPN_Seg_OCR_Decoder.norm (`convnext_pop.py:13`), which the decoder applies to the channels-last
+    VIEW of the convolution output and permutes back (`:27`): undo the view, run the fused LayerNorm on the NCHW
+    tensor, return the matching view so the decoder's own permute yields contiguous bf16 NCHW features."""
+
+    def __init__(self, norm):
+        super().__init__()
+        self.norm = norm
+
+    def forward(self, x_nhwc):
+        x = x_nhwc.permute(0, 3, 1, 2)
+        if not x.is_cuda or not x.is_contiguous() or (x.shape[2] * x.shape[3]) % 8:
+            return self.norm(x_nhwc)
+        return ops.layernorm_tail(x, self.norm.weight, self.norm.bias, self.norm.eps).permute(0, 2, 3, 1)
+
+
+def _swap_spec(dec):
+    """(attribute name, stand-in module) for decoders whose tail the library fuses, else None."""
+    kind = type(dec).__name__
+    attr = {'PSPModule': 'bottleneck', 'PSP_Plus_Decoder': 'fc'}.get(kind)
+    if attr is not None:
+        seq = getattr(dec, attr, None)
+        if (isinstance(seq, torch.nn.Sequential) and len(seq) == 4 and isinstance(seq[1], torch.nn.BatchNorm2d)
+                and isinstance(seq[2], torch.nn.ReLU) and isinstance(seq[3], torch.nn.Conv2d)
+                and seq[3].kernel_size == (1, 1) and seq[3].in_channels % 8 == 0):
+            return attr, _ConvTailSeq(seq)
+    if kind == 'FPN_Seg_OCR_Decoder' and isinstance(getattr(dec, 'norm', None), torch.nn.LayerNorm):
+        return 'norm', _LayerNormTail(dec.norm)
+    return None
+
+
+def _decode_fused(dec, feats):
+    """`self.decoder(features)` with the decoder's tail swapped for its fused stand-in for the duration of the call
+    (the module tree, state_dict and parameters are untouched afterwards).  Decoders in train mode, and decoders
+    without a fused tail, run as they are."""
+    if dec.training:
+        return dec(feats)
+    cached = dec.__dict__.get('_sl_tail')
+    if cached is None:
+        cached = _swap_spec(dec) or ()
+        dec.__dict__['_sl_tail'] = cached
+    if not cached:
+        return dec(feats)
+    attr, stand_in = cached
+    original = dec._modules[attr]
+    dec._modules[attr] = stand_in
+    try:
+        return dec(feats)
+    finally:
+        dec._modules[attr] = original
 
 
 def _head_params(model):
@@ -84,20 +165,23 @@ def _make_forward(orig_forward):
             return ops.forward_base_train(_features(self, img), mask, self.base_emb, _mlp_weights(self.classifier),
                                           criterion=self.criterion)
         with torch.no_grad():                                         # forward_all / forward_base, inference
-            feats = _features(self, img)
+            feats = _features(self, img, fused_tail=True)
             return head_for(self)(feats)
     forward._sl_patched = True
     return forward
 
 
 _train_enabled = [True]
+_tails_enabled = [True]
 
 
-def patch(verbose=False, train=True):
+def patch(verbose=False, train=True, tails=True):
     """Install the B200 path into every importable reference module.  Returns the list of patched names.
-    train=False leaves training-mode forwards (forward_novel, forward_base with a criterion) on the reference."""
+    train=False leaves training-mode forwards (forward_novel, forward_base with a criterion) on the reference.
+    tails=False keeps the decoders entirely stock (fp32 features, cast by the head)."""
     ops.check_device()
     _train_enabled[0] = bool(train)
+    _tails_enabled[0] = bool(tails)
     done = []
     for name in MODEL_MODULES:
         try:

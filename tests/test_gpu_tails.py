@@ -199,3 +199,140 @@ def test_tails_full_size_properties(ops):
     err = (y[0].double() - ref).abs()
     spacing = torch.pow(2.0, torch.floor(torch.log2(ref.abs().clamp_min(1e-30))) - 7)
     assert (err - 0.5 * spacing - 2e-5 * ref.pow(2).mean().sqrt()).max().item() <= 0
+
+
+def test_patch_runs_decoder_tails_fused(ops):
+    """segland_b200.patch with reference-shaped decoders (the real tree is not on the GPU box; the class names,
+    attribute names and forward bodies follow networks/pspnet_pop.py:8-35 and networks/convnext_pop.py:8-28): in
+    eval mode the patched forward swaps the tail in for the call, the head receives bf16 features, and the logits
+    match the un-fused path; the module tree is untouched afterwards."""
+    import sys
+    import types
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from segland_b200 import patch as slp
+
+    class PSPModule(nn.Module):
+        def __init__(self, features, out_features, sizes=(1, 2)):
+            super().__init__()
+            self.stages = nn.ModuleList([nn.Sequential(nn.AdaptiveAvgPool2d(s), nn.Conv2d(features, out_features, 1, bias=False),
+                                                       nn.BatchNorm2d(out_features), nn.ReLU(inplace=True)) for s in sizes])
+            self.bottleneck = nn.Sequential(nn.Conv2d(features + len(sizes) * out_features, out_features, 3, padding=1, bias=False),
+                                            nn.BatchNorm2d(out_features), nn.ReLU(inplace=True),
+                                            nn.Conv2d(out_features, out_features, 1))
+
+        def forward(self, feats):
+            h, w = feats.shape[2:]
+            priors = [F.interpolate(st(feats), size=(h, w), mode='bilinear', align_corners=False) for st in self.stages] + [feats]
+            return self.bottleneck(torch.cat(priors, 1))
+
+    class FPN_Seg_OCR_Decoder(nn.Module):
+        def __init__(self, in_ch, out_ch):
+            super().__init__()
+            self.conv = nn.Conv2d(in_ch, out_ch, 1)
+            self.norm = nn.LayerNorm(out_ch)
+
+        def forward(self, x):
+            feats = self.conv(x)
+            return self.norm(feats.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+    class Backbone(nn.Module):
+        def base_forward(self, x):
+            return x
+
+        forward = base_forward
+
+    def make_model(modname, decoder, C):
+        st = synth.make_head_state(C, 7, 4, seed=C)
+
+        def mlp(ws):
+            seq = nn.Sequential(nn.Conv2d(C, C, 1, bias=False), nn.ReLU(inplace=True), nn.Conv2d(C, C, 1, bias=False),
+                                nn.ReLU(inplace=True), nn.Conv2d(C, 1, 1, bias=False))
+            with torch.no_grad():
+                seq[0].weight.copy_(ws[0].view(C, C, 1, 1)); seq[2].weight.copy_(ws[1].view(C, C, 1, 1))
+                seq[4].weight.copy_(ws[2].view(1, C, 1, 1))
+            return seq
+
+        class GFSS_Model(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.backbone, self.decoder = Backbone(), decoder
+                self.classifier, self.classifier_n = mlp(st.cls), mlp(st.cls_n)
+                self.base_emb = nn.Parameter(st.base_emb.clone(), requires_grad=False)
+                self.novel_emb = nn.Parameter(st.novel_emb.clone())
+                self.is_ft, self.criterion = True, None
+
+            def forward(self, img, mask=None, img_b=None, mask_b=None):
+                return 'reference path'
+
+        GFSS_Model.__module__ = 'networks.' + modname
+        return GFSS_Model
+
+    torch.manual_seed(11)
+    psp = PSPModule(32, 64)
+    for m in psp.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5)
+    fpn = FPN_Seg_OCR_Decoder(48, 192)
+    classes = {'pspnet_pop': make_model('pspnet_pop', psp, 64), 'convnext_pop': make_model('convnext_pop', fpn, 192)}
+    names = ['networks'] + ['networks.' + n for n in classes]
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules['networks'] = types.ModuleType('networks')
+    for n, cls in classes.items():
+        mod = types.ModuleType('networks.' + n)
+        mod.GFSS_Model = cls
+        sys.modules['networks.' + n] = mod
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the stock 3x3 / 1x1 convolutions in fp32, as on the CPU
+    try:
+        for n, cls in classes.items():
+            model = cls().cuda().eval()
+            img = torch.randn(2, 32 if n == 'pspnet_pop' else 48, 16, 24, device='cuda')
+            keys = list(model.state_dict())
+            slp.patch(tails=False)
+            plain = model(img)
+            slp.unpatch()
+            slp.patch()
+            seen = []
+            head = slp.head_for(model)
+            orig_call = type(head).__call__
+            type(head).__call__ = lambda self, f, *a, **k: (seen.append(f.dtype), orig_call(self, f, *a, **k))[1]
+            try:
+                fused = model(img)
+            finally:
+                type(head).__call__ = orig_call
+            slp.unpatch()
+            assert seen == [torch.bfloat16], (n, seen)                   # the tail handed bf16 features to the head
+            assert_close_rel(fused.cpu(), plain.cpu(), RTOL, f'{n}: fused-tail logits vs stock decoder + head')
+            assert list(model.state_dict()) == keys
+            assert isinstance(model.decoder.bottleneck if n == 'pspnet_pop' else model.decoder.norm,
+                              nn.Sequential if n == 'pspnet_pop' else nn.LayerNorm)
+            # the reference computation end to end on the CPU: decoder in fp32 -> bf16 features -> oracle head
+            with torch.no_grad():
+                f32 = model.decoder.cpu()(img.cpu())
+            model.cuda()
+            ref = ref_ops.ref_head(f32.to(torch.bfloat16).float(), model.base_emb.detach().cpu(), model.novel_emb.detach().cpu(),
+                                   tuple(w.detach().cpu().reshape(w.shape[0], -1).squeeze(0) for w in
+                                         (model.classifier[0].weight, model.classifier[2].weight, model.classifier[4].weight)),
+                                   tuple(w.detach().cpu().reshape(w.shape[0], -1).squeeze(0) for w in
+                                         (model.classifier_n[0].weight, model.classifier_n[2].weight, model.classifier_n[4].weight)))
+            assert_close_rel(fused.cpu(), ref, 2e-3, f'{n}: patched model vs CPU decoder + oracle head')
+            # a decoder left in train mode is not touched
+            model.decoder.train()
+            slp.patch()
+            seen.clear()
+            type(head).__call__ = lambda self, f, *a, **k: (seen.append(f.dtype), orig_call(self, f, *a, **k))[1]
+            try:
+                model(img)
+            finally:
+                type(head).__call__ = orig_call
+                slp.unpatch()
+            assert seen == [torch.float32]
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+        slp.unpatch()
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

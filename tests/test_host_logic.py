@@ -184,6 +184,23 @@ def test_patch_installs_into_the_real_reference_when_present(monkeypatch):
         assert torch.equal(out.detach(), want)
         assert {'base_emb', 'novel_emb'} <= set(dict(model.named_parameters()))
         assert [type(m).__name__ for m in model.classifier_n] == ['Conv2d', 'ReLU', 'Conv2d', 'ReLU', 'Conv2d']
+        # fused decoder tails: the real decoders have the structure the swap expects, the swap leaves
+        # CPU calls on the reference's own arithmetic and restores the module tree
+        import networks.convnext_pop as cp
+        import networks.pspplus_pop as ppp
+        import networks.swin_pop as sp
+        torch.manual_seed(0)
+        psp = pp.PSPModule(16, 64).eval()
+        x = torch.randn(1, 16, 8, 8)
+        assert slp._swap_spec(psp)[0] == 'bottleneck'
+        assert torch.equal(slp._decode_fused(psp, x), psp(x)) and isinstance(psp.bottleneck, torch.nn.Sequential)
+        fpn = cp.FPN_Seg_OCR_Decoder(8 + 16 + 32 + 64, 192).eval()
+        xs = [torch.randn(1, c, 16 >> i, 16 >> i) for i, c in enumerate((8, 16, 32, 64))]
+        assert slp._swap_spec(fpn)[0] == 'norm'
+        assert torch.equal(slp._decode_fused(fpn, xs), fpn(xs)) and isinstance(fpn.norm, torch.nn.LayerNorm)
+        assert slp._swap_spec(ppp.PSP_Plus_Decoder(32, out_features=64))[0] == 'fc'
+        assert slp._swap_spec(sp.UperNet_Decoder_Plus([16, 32, 64, 128], 16)) is None
+        assert 'bottleneck.0.weight' in psp.state_dict() and not any('_sl' in k for k in psp.state_dict())
     finally:
         slp.unpatch()
         sys.path[:] = [p for p in sys.path if p != ref]
