@@ -328,6 +328,17 @@ SL_API int sl_tail_bn_relu_conv(const float *x, int B, int Cin, int N,
                          float bn_eps, int relu, const uint16_t *W_hi, const uint16_t *W_lo, const float *bias,
                          int Cout, void *ws, uint16_t *feat_out, void *stream);
 SL_API int sl_tail_sum(const float *const *maps_host, int M, long long n, uint16_t *feat_out, void *stream);
+/* sl_tail_bn_relu: inference BatchNorm2d -> ReLU -> bf16, the `bn` + `relu` of _ConvBnReLU after _ASPP.fc's
+ *   convolution (networks/deeplab_pop.py:12-29,61,66) and DoubleConv's last BN + ReLU in VGGUNet.up4
+ *   (networks/vggunet_pop.py:19-20,79).  Arguments as in sl_tail_bn_relu_conv; x [B,C,N] fp32.
+ * sl_tail_concat: torch.cat([x0, x1, x2, x3], 1) of HRFPN_Seg_Decoder (networks/seghr_pop.py:23-24) as bf16:
+ *   maps_host[m] is fp32 [B,channels_host[m],N]; feat_out [B,sum(channels),N] bf16; M <= 16.
+ */
+SL_API int sl_tail_bn_relu(const float *x, int B, int C, int N,
+                    const float *bn_weight, const float *bn_bias, const float *bn_mean, const float *bn_var,
+                    float bn_eps, int relu, uint16_t *feat_out, void *stream);
+SL_API int sl_tail_concat(const float *const *maps_host, const int *channels_host, int M, int B, int N,
+                   uint16_t *feat_out, void *stream);
 
 #ifdef __cplusplus
 }

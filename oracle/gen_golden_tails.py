@@ -10,6 +10,8 @@ the tail this repo replaces:
   networks/convnext_pop.py  FPN_Seg_OCR_Decoder.forward; hook on .conv: LayerNorm over channels of it (:26-27)
   networks/swin_pop.py      UperNet_Decoder_Plus.forward; hooks on fpn_convs[i]: the output is
                             stack(interpolate(fpn_outs)).sum(-1) (:163-172)
+  networks/deeplab_pop.py   _ASPP.forward; hook on fc.conv: the output is relu(bn(.)) of it (:12-29,61,66)
+  networks/seghr_pop.py     HRFPN_Seg_Decoder.forward: cat of x[0] and the interpolated x[1:] (:8-24)
 BatchNorm running statistics and affine parameters are randomised so the normalisation is not an identity.
 """
 from __future__ import annotations
@@ -117,6 +119,34 @@ def main():
         print(name, len(maps), 'maps', tuple(out.shape))
 
     sum_case('sum_swin', (16, 32, 64, 128), 16, 1, 48, 48, seed=321)
+
+    # _ASPP (deeplab_pop.py:46-66): hook on fc.conv; the module output is relu(bn(.)) of it
+    import networks.deeplab_pop as deeplab_pop
+    import networks.seghr_pop as seghr_pop
+    gen = torch.Generator().manual_seed(331)
+    torch.manual_seed(331)
+    aspp = deeplab_pop._ASPP(24, 64, rates=[1, 2, 3]).eval()
+    randomise_norms(aspp, gen)
+    box, hk = capture(aspp.fc.conv)
+    with torch.no_grad():
+        out = aspp(torch.randn(2, 24, 12, 10, generator=gen))
+    hk.remove()
+    bn = aspp.fc.bn
+    arrays.update({'aspp_x': box[0].numpy(), 'aspp_out': out.numpy(), 'aspp_bn_w': bn.weight.detach().numpy(),
+                   'aspp_bn_b': bn.bias.detach().numpy(), 'aspp_bn_m': bn.running_mean.numpy(),
+                   'aspp_bn_v': bn.running_var.numpy(), 'aspp_bn_eps': np.float64(bn.eps)})
+    print('aspp', tuple(box[0].shape), '->', tuple(out.shape))
+    # HRFPN_Seg_Decoder (seghr_pop.py:8-24): inputs at four scales; the maps entering the concatenation are x[0] and
+    # the stock align_corners interpolations of x[1:], recomputed here with the same call
+    dec = seghr_pop.HRFPN_Seg_Decoder().eval()
+    xs = [torch.randn(2, c, 16 >> i, 24 >> i, generator=gen) for i, c in enumerate((8, 16, 32, 64))]
+    with torch.no_grad():
+        out = dec(xs)
+    maps = [xs[0]] + [F.interpolate(x, size=xs[0].shape[-2:], mode='bilinear', align_corners=True) for x in xs[1:]]
+    for i, m in enumerate(maps):
+        arrays[f'cat_hr_map{i}'] = m.numpy()
+    arrays['cat_hr_out'] = out.numpy()
+    print('cat_hr', [tuple(m.shape) for m in maps], '->', tuple(out.shape))
     path = os.path.join(REPO, 'tests', 'golden', 'tails.npz')
     np.savez_compressed(path, **arrays)
     print(path, '%.2f MB' % (os.path.getsize(path) / 1e6))

@@ -269,6 +269,18 @@ def ref_tail_sum(maps):
     return torch.stack(list(maps), dim=-1).sum(-1)
 
 
+def ref_tail_bn_relu(x, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, relu=True):
+    """The `bn` + `relu` of _ConvBnReLU after _ASPP.fc's convolution, networks/deeplab_pop.py:12-29,61,66 (eval mode),
+    and the last BatchNorm2d + ReLU of DoubleConv in VGGUNet.up4, networks/vggunet_pop.py:19-20."""
+    y = F.batch_norm(x, bn_mean, bn_var, bn_weight, bn_bias, False, 0.0, bn_eps)
+    return F.relu(y) if relu else y
+
+
+def ref_tail_concat(maps):
+    """torch.cat([x[0], x1, x2, x3], 1), HRFPN_Seg_Decoder.forward, networks/seghr_pop.py:23-24."""
+    return torch.cat(list(maps), 1)
+
+
 def bf16_ulp_report(got_bf16, ref_fp32):
     """How a bf16 feature tensor compares with round-to-nearest(ref_fp32): fraction of identical bit patterns and
     the largest |got - ref_fp32| in units of the reference element's bf16 spacing (0.5 = ideal rounding)."""

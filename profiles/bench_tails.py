@@ -22,7 +22,7 @@ def main():
     g = torch.Generator(dev).manual_seed(0)
     conv_only = '--conv-only' in sys.argv
     for name, C, hw, T in () if conv_only else (('ConvNeXt-T C=192 256^2', 192, 256, 16), ('Swin-T/S C=96 256^2', 96, 256, 32),
-                           ('HRNet-w32 C=480 256^2', 480, 256, 8)):
+                           ('wide head C=480 256^2 (no reference model: 32-pixel tiles)', 480, 256, 8)):
         x = torch.randn(T, C, hw, hw, device=dev, generator=g)
         gamma, beta = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev)
         out = torch.empty(T, C, hw, hw, dtype=torch.bfloat16, device=dev)
@@ -39,6 +39,24 @@ def main():
         report(f'sum_tail {name}', t, maps[0].numel() * (4 * M + 2), T)
         t = timeit(lambda: torch.stack(maps, dim=-1).sum(-1).to(torch.bfloat16), iters=5)
         report(f'  eager: stack(..., -1).sum(-1) -> bf16', t, maps[0].numel() * (4 * M + 2), T)
+        del maps, out
+    if not conv_only:
+        x = torch.randn(32, 256, 128, 128, device=dev, generator=g)
+        bn = torch.nn.BatchNorm2d(256).to(dev).eval()
+        bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5)
+        out = torch.empty(32, 256, 128, 128, dtype=torch.bfloat16, device=dev)
+        t = timeit(lambda: ops.bn_relu_tail(x, bn, out=out))
+        report('bn_relu_tail DeepLab C=256 128^2', t, x.numel() * 6, 32)
+        with torch.no_grad():
+            t = timeit(lambda: F.relu(bn(x)).to(torch.bfloat16), iters=5)
+        report('  eager: bn -> relu -> bf16', t, x.numel() * 6, 32)
+        del x, out
+        maps = [torch.randn(8, c, 256, 256, device=dev, generator=g) for c in (32, 64, 128, 256)]
+        out = torch.empty(8, 480, 256, 256, dtype=torch.bfloat16, device=dev)
+        t = timeit(lambda: ops.concat_tail(maps, out=out))
+        report('concat_tail HRNet-w32 C=480 256^2', t, out.numel() * 6, 8)
+        t = timeit(lambda: torch.cat(maps, 1).to(torch.bfloat16), iters=5)
+        report('  eager: cat -> bf16', t, out.numel() * 6, 8)
         del maps, out
     for name, C, hw, T in (('PSPNet C=512 128^2', 512, 128, 32), ('PSPNet C=512 64^2 (512^2 tiles)', 512, 64, 64)):
         x = torch.randn(T, C, hw, hw, device=dev, generator=g)

@@ -38,6 +38,8 @@ _SIGNATURES = {
     'sl_tail_conv_prepare': [_P, c_int, c_int, _P, _P, _P],
     'sl_tail_bn_relu_conv': [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, c_int, _P, _P, _P],
     'sl_tail_sum': [POINTER(_P), c_int, c_longlong, _P, _P],
+    'sl_tail_bn_relu': [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_float, c_int, _P, _P],
+    'sl_tail_concat': [POINTER(_P), POINTER(c_int), c_int, c_int, c_int, _P, _P],
     'sl_upsample_ce_bwd': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P],
 }
 

@@ -5,6 +5,9 @@
 //   sl_tail_bn_relu_conv   PSPModule.bottleneck[1:4] (BN -> ReLU -> 1x1 conv + bias), networks/pspnet_pop.py:19-22
 //                          (same tail in PSP_Plus_Decoder.fc, networks/pspplus_pop.py:44-47)
 //   sl_tail_sum            torch.stack(fpn_outs, -1).sum(-1), networks/swin_pop.py:169-172, lsk_pop.py:163-165
+//   sl_tail_bn_relu        _ConvBnReLU's bn + relu after _ASPP.fc's convolution, networks/deeplab_pop.py:12-29,61,66;
+//                          DoubleConv's last BN + ReLU in VGGUNet.up4, networks/vggunet_pop.py:19-20,79
+//   sl_tail_concat         torch.cat([x0, x1, x2, x3], 1) of HRFPN_Seg_Decoder, networks/seghr_pop.py:23-24
 // The LayerNorm and sum kernels are HBM-bound (4 B read + 2 B written per element); the 1x1 convolution runs on
 // tcgen05 through the generic split-bf16 GEMM of pop_bwd_tc.cu (EPI_TAIL).
 #include "common.cuh"
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(256) sum_tail_kernel(SumPtrs maps, int M, long
 // r = relu(bn_eval(x)) as bf16 hi/lo planes (hi = bf16(r), lo = bf16(r - hi): 16 mantissa bits), the A operand
 // of the tail GEMM.  Batch-norm in inference form, as ATen evaluates it: alpha = w / sqrt(var + eps),
 // y = x * alpha + (b - mean * alpha).  bn_weight == NULL: no normalisation (plain ReLU when relu != 0).
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) bn_relu_split_kernel(const float* __restrict__ x, int C, int n8_per_row,
                                                             long long total8, const float* __restrict__ bw,
                                                             const float* __restrict__ bb, const float* __restrict__ bm,
@@ -170,8 +174,20 @@ __global__ void __launch_bounds__(256) bn_relu_split_kernel(const float* __restr
       h[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
       l[j] = pack_bf16(v[2 * j] - bf16lo(h[j]), v[2 * j + 1] - bf16hi(h[j]));
     }
-    reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[0], h[1], h[2], h[3]);    // re-read by the GEMM: keep in L2
-    reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[0], l[1], l[2], l[3]);
+    reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[0], h[1], h[2], h[3]);    // re-read by the GEMM / the head: keep in L2
+    if (SPLIT) reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// fp32 [B,Cs,N] -> bf16 channel slice [c_off, c_off + Cs) of [B,Ctot,N] (torch.cat along channels + conversion)
+__global__ void __launch_bounds__(256) concat_cast_kernel(const float* __restrict__ src, long long img8, long long total8,
+                                                          long long out_img8, long long out_off8,
+                                                          uint16_t* __restrict__ out) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total8; i += gridDim.x * 256ll) {
+    const long long b = i / img8, r = i - b * img8;
+    const float4 a = ld_stream_f4(src + i * 8), c = ld_stream_f4(src + i * 8 + 4);
+    reinterpret_cast<uint4*>(out)[b * out_img8 + out_off8 + r] =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
   }
 }
 
@@ -263,9 +279,49 @@ extern "C" int sl_tail_bn_relu_conv(const float* x, int B, int Cin, int N, const
   const long long total8 = plane / 8;
   const long long want = (total8 + 255) / 256;
   const int grid = static_cast<int>(want < 16ll * sl::kNumSMs ? want : 16ll * sl::kNumSMs);
-  sl::tails::bn_relu_split_kernel<<<grid, 256, 0, st>>>(x, Cin, N / 8, total8, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
+  sl::tails::bn_relu_split_kernel<true><<<grid, 256, 0, st>>>(x, Cin, N / 8, total8, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
                                                         relu, hi, lo);
   const int rc = SL_LAUNCH_RESULT();
   if (rc != 0) return rc;
   return sl_tail_gemm_run(hi, lo, B, Cin, N, W_hi, W_lo, bias, Cout, feat_out, st);
+}
+
+extern "C" int sl_tail_bn_relu(const float* x, int B, int C, int N, const float* bn_weight, const float* bn_bias,
+                               const float* bn_mean, const float* bn_var, float bn_eps, int relu, uint16_t* feat_out,
+                               void* stream) {
+  SL_CHECK_PTR(x); SL_CHECK_PTR(feat_out);
+  if (bn_weight != nullptr) { SL_CHECK_PTR(bn_bias); SL_CHECK_PTR(bn_mean); SL_CHECK_PTR(bn_var); }
+  SL_CHECK_ARG(B >= 1 && C >= 1 && N >= 8 && N % 8 == 0);
+  SL_CHECK_ALIGN(x, 16); SL_CHECK_ALIGN(feat_out, 16);
+  const long long total8 = static_cast<long long>(B) * C * N / 8;
+  const long long want = (total8 + 255) / 256;
+  const int grid = static_cast<int>(want < 16ll * sl::kNumSMs ? want : 16ll * sl::kNumSMs);
+  sl::tails::bn_relu_split_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, C, N / 8, total8, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, relu, feat_out, nullptr);
+  return SL_LAUNCH_RESULT();
+}
+
+extern "C" int sl_tail_concat(const float* const* maps_host, const int* channels_host, int M, int B, int N,
+                              uint16_t* feat_out, void* stream) {
+  SL_CHECK_PTR(maps_host); SL_CHECK_PTR(channels_host); SL_CHECK_PTR(feat_out);
+  SL_CHECK_ARG(M >= 1 && M <= 16 && B >= 1 && N >= 8 && N % 8 == 0);
+  SL_CHECK_ALIGN(feat_out, 16);
+  long long c_total = 0;
+  for (int m = 0; m < M; ++m) {
+    SL_CHECK_PTR(maps_host[m]); SL_CHECK_ALIGN(maps_host[m], 16);
+    SL_CHECK_ARG(channels_host[m] >= 1);
+    c_total += channels_host[m];
+  }
+  long long c_off = 0;
+  for (int m = 0; m < M; ++m) {
+    const long long img8 = static_cast<long long>(channels_host[m]) * N / 8, total8 = img8 * B;
+    const long long want = (total8 + 255) / 256;
+    const int grid = static_cast<int>(want < 16ll * sl::kNumSMs ? want : 16ll * sl::kNumSMs);
+    sl::tails::concat_cast_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(maps_host[m], img8, total8,
+                                                                                       c_total * N / 8, c_off * N / 8, feat_out);
+    const int rc = SL_LAUNCH_RESULT();
+    if (rc != 0) return rc;
+    c_off += channels_host[m];
+  }
+  return 0;
 }

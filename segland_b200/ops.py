@@ -723,3 +723,39 @@ def sum_tail(maps, out=None):
     out = _tail_out(maps[0], maps[0].shape[1], out)
     call('sl_tail_sum', ptr_array(maps), len(maps), maps[0].numel(), ptr(out), _stream())
     return out
+
+
+def bn_relu_tail(x, bn, relu=True, out=None):
+    """Inference BatchNorm2d -> ReLU as bf16 features: the tail of _ASPP.fc (`_ConvBnReLU`, networks/deeplab_pop.py:12-29,
+    61,66) and of VGGUNet.up4's DoubleConv (networks/vggunet_pop.py:19-20).  x is the convolution's fp32 output;
+    bn = the nn.BatchNorm2d module (eval mode) or a (weight, bias, running_mean, running_var, eps) tuple."""
+    x = _tail_in(x)
+    B, C, h, w = x.shape
+    if isinstance(bn, torch.nn.Module):
+        if bn.training:
+            raise ValueError('bn_relu_tail uses running statistics: put the module in eval() mode')
+        bn = (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+    params = [_cuda(t.detach(), torch.float32) for t in bn[:4]]          # kept alive until the launch is queued
+    if any(t.numel() != C for t in params):
+        raise ValueError(f'BatchNorm parameters must have {C} elements')
+    out = _tail_out(x, C, out)
+    call('sl_tail_bn_relu', ptr(x), B, C, h * w, ptr(params[0]), ptr(params[1]), ptr(params[2]), ptr(params[3]),
+         float(bn[4]), int(bool(relu)), ptr(out), _stream())
+    return out
+
+
+def concat_tail(maps, out=None):
+    """`torch.cat([x[0], x1, x2, x3], 1)` of HRFPN_Seg_Decoder (networks/seghr_pop.py:23-24) as bf16 features:
+    maps are fp32 [B,C_m,h,w] tensors of one spatial size (already interpolated)."""
+    maps = [_tail_in(m) for m in maps]
+    B, _, h, w = maps[0].shape
+    for m in maps:
+        if m.shape[0] != B or tuple(m.shape[2:]) != (h, w):
+            raise ValueError('all maps must share batch and spatial size')
+    chans = [int(m.shape[1]) for m in maps]
+    if out is None:
+        out = torch.empty(B, sum(chans), h, w, dtype=torch.bfloat16, device=maps[0].device)
+    elif out.dtype != torch.bfloat16 or tuple(out.shape) != (B, sum(chans), h, w) or not out.is_contiguous():
+        raise ValueError('out must be a contiguous bf16 [B,sum(C_m),h,w] tensor')
+    call('sl_tail_concat', ptr_array(maps), int_array(chans), len(maps), B, h * w, ptr(out), _stream())
+    return out

@@ -9,7 +9,8 @@ replaces, in place,
     decoder -- `orthogonal_decompose` + `classifier` / `classifier_n` + channel assembly
     (`pspnet_pop.py:143-159`, `:171-182`) -- runs in libsegland_b200.so; backbones and decoders stay
     stock PyTorch, except that in inference the decoder's last operators (PSPModule.bottleneck[1:4],
-    `pspnet_pop.py:19-22`; FPN_Seg_OCR_Decoder.norm, `convnext_pop.py:27`) run fused and emit the head's bf16
+    `pspnet_pop.py:19-22`; FPN_Seg_OCR_Decoder.norm, `convnext_pop.py:27`; _ASPP.fc's BN + ReLU,
+    `deeplab_pop.py:61`; VGGUNet.up4's last BN + ReLU, `vggunet_pop.py:79`) run fused and emit the head's bf16
     features directly (`patch(tails=False)` disables it).  Training-mode calls on CUDA tensors -- `forward_novel` (`ft_pop.py:252`,
     `pspnet_pop.py:191-245`) and `forward_base` with a criterion (`train_base.py:259`, `:161-189`) -- run
     the same head with autograd (`ops.forward_novel_train` / `ops.forward_base_train`: forward kernels +
@@ -40,7 +41,7 @@ def _features(model, img, fused_tail=False):
     fused_tail (inference only): the decoder's last operators run in libsegland_b200.so and hand the head bf16
     features directly."""
     if hasattr(model, 'net') and not hasattr(model, 'decoder'):           # vggunet_pop.py
-        return model.net(img)
+        return _decode_fused(model.net, img) if fused_tail and _tails_enabled[0] else model.net(img)
     name = type(model).__module__.rsplit('.', 1)[-1]
     feats = model.backbone.base_forward(img) if name in _BASE_FORWARD else model.backbone(img)
     if fused_tail and _tails_enabled[0]:
@@ -87,9 +88,47 @@ class _LayerNormTail(torch.nn.Module):
         return ops.layernorm_tail(x, self.norm.weight, self.norm.bias, self.norm.eps).permute(0, 2, 3, 1)
 
 
+class _BnReluTailSeq(torch.nn.Module):
+    """Stands in for a Sequential that ends `..., conv, BatchNorm2d, ReLU` (_ASPP.fc = `_ConvBnReLU`,
+    `deeplab_pop.py:12-29,61`; VGGUNet.up4.conv.double_conv, `vggunet_pop.py:13-20`): everything up to and including
+    the last convolution runs as it is, then BN -> ReLU -> bf16 in one C-ABI call."""
+
+    def __init__(self, seq):
+        super().__init__()
+        self.seq = seq
+
+    def forward(self, x):
+        mods = list(self.seq)
+        for m in mods[:-2]:
+            x = m(x)
+        if (x.shape[2] * x.shape[3]) % 8 or not x.is_cuda:
+            return mods[-1](mods[-2](x))
+        return ops.bn_relu_tail(x, mods[-2], relu=True)
+
+
+def _ends_conv_bn_relu(seq):
+    mods = list(seq) if isinstance(seq, torch.nn.Sequential) else []
+    return (len(mods) >= 3 and isinstance(mods[-3], torch.nn.Conv2d) and isinstance(mods[-2], torch.nn.BatchNorm2d)
+            and isinstance(mods[-1], torch.nn.ReLU))
+
+
 def _swap_spec(dec):
-    """(attribute name, stand-in module) for decoders whose tail the library fuses, else None."""
+    """(owner module, attribute name, stand-in module) for decoders whose tail the library fuses, else None."""
+    spec = _swap_spec_local(dec)
+    if spec is not None:
+        return (dec,) + spec
     kind = type(dec).__name__
+    if kind == 'VGGUNet':                                               # vggunet_pop.py:79 -> Up.conv -> DoubleConv
+        dc = getattr(getattr(getattr(dec, 'up4', None), 'conv', None), 'double_conv', None)
+        if _ends_conv_bn_relu(dc):
+            return dec.up4.conv, 'double_conv', _BnReluTailSeq(dc)
+    return None
+
+
+def _swap_spec_local(dec):
+    kind = type(dec).__name__
+    if kind == '_ASPP' and _ends_conv_bn_relu(getattr(dec, 'fc', None)):
+        return 'fc', _BnReluTailSeq(dec.fc)
     attr = {'PSPModule': 'bottleneck', 'PSP_Plus_Decoder': 'fc'}.get(kind)
     if attr is not None:
         seq = getattr(dec, attr, None)
@@ -114,13 +153,13 @@ def _decode_fused(dec, feats):
         dec.__dict__['_sl_tail'] = cached
     if not cached:
         return dec(feats)
-    attr, stand_in = cached
-    original = dec._modules[attr]
-    dec._modules[attr] = stand_in
+    owner, attr, stand_in = cached
+    original = owner._modules[attr]
+    owner._modules[attr] = stand_in
     try:
         return dec(feats)
     finally:
-        dec._modules[attr] = original
+        owner._modules[attr] = original
 
 
 def _head_params(model):

@@ -150,6 +150,41 @@ def test_sum_tail_vs_golden_and_oracle(ops, golden):
         ops.sum_tail([torch.zeros(1, 8, 8, 8).cuda()] * 9)
 
 
+def test_bn_relu_tail_vs_golden_and_oracle(ops, golden):
+    z = golden('tails')
+    t = lambda k: torch.from_numpy(z['aspp' + k])
+    bn = (t('_bn_w'), t('_bn_b'), t('_bn_m'), t('_bn_v'), float(z['aspp_bn_eps']))
+    got = ops.bn_relu_tail(t('_x').cuda(), bn)
+    torch.cuda.synchronize()
+    check_features(got, t('_out'), 1e-6, 0.999, 'aspp')
+    g = torch.Generator().manual_seed(41)
+    for C, B, h, w in ((256, 2, 64, 64), (64, 1, 40, 56), (8, 3, 2, 4)):
+        x = torch.randn(B, C, h, w, generator=g) * 2
+        bn = (1 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g),
+              0.5 + torch.rand(C, generator=g), 1e-5)
+        for relu in (True, False):
+            ref = ref_ops.ref_tail_bn_relu(x, bn[0], bn[1], bn[2], bn[3], bn[4], relu=relu)
+            check_features(ops.bn_relu_tail(x.cuda(), bn, relu=relu), ref, 1e-6, 0.999, f'bn_relu C={C}')
+    mod = torch.nn.BatchNorm2d(8)
+    with pytest.raises(ValueError):
+        ops.bn_relu_tail(torch.zeros(1, 8, 2, 4).cuda(), mod)          # train mode: no running-statistics fold
+
+
+def test_concat_tail_vs_golden_and_oracle(ops, golden):
+    z = golden('tails')
+    maps = [torch.from_numpy(z[f'cat_hr_map{i}']) for i in range(4)]
+    got = ops.concat_tail([m.cuda() for m in maps]).cpu()
+    assert torch.equal(got, torch.from_numpy(z['cat_hr_out']).to(torch.bfloat16))       # a pure conversion: bit-exact
+    g = torch.Generator().manual_seed(43)
+    maps = [torch.randn(3, c, 24, 40, generator=g) for c in (32, 64, 128, 256)]        # HRNet-w32's 480 channels
+    out = torch.zeros(3, 480, 24, 40, dtype=torch.bfloat16, device='cuda')
+    got = ops.concat_tail([m.cuda() for m in maps], out=out)
+    assert torch.equal(got.cpu(), ref_ops.ref_tail_concat(maps).to(torch.bfloat16))
+    assert torch.equal(ops.concat_tail([maps[1].cuda()]).cpu(), maps[1].to(torch.bfloat16))
+    with pytest.raises(ValueError):
+        ops.concat_tail([maps[0].cuda(), maps[1][:2].cuda()])
+
+
 @pytest.mark.parametrize('kind', ['psp', 'ln'])
 def test_head_on_tail_features_matches_head_on_reference_features(ops, kind):
     """End of the chain: logits of the POP head fed by the fused tail vs fed by bf16(oracle tail output)."""

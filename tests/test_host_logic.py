@@ -192,14 +192,19 @@ def test_patch_installs_into_the_real_reference_when_present(monkeypatch):
         torch.manual_seed(0)
         psp = pp.PSPModule(16, 64).eval()
         x = torch.randn(1, 16, 8, 8)
-        assert slp._swap_spec(psp)[0] == 'bottleneck'
+        assert slp._swap_spec(psp)[1] == 'bottleneck'
         assert torch.equal(slp._decode_fused(psp, x), psp(x)) and isinstance(psp.bottleneck, torch.nn.Sequential)
         fpn = cp.FPN_Seg_OCR_Decoder(8 + 16 + 32 + 64, 192).eval()
         xs = [torch.randn(1, c, 16 >> i, 16 >> i) for i, c in enumerate((8, 16, 32, 64))]
-        assert slp._swap_spec(fpn)[0] == 'norm'
+        assert slp._swap_spec(fpn)[1] == 'norm'
         assert torch.equal(slp._decode_fused(fpn, xs), fpn(xs)) and isinstance(fpn.norm, torch.nn.LayerNorm)
-        assert slp._swap_spec(ppp.PSP_Plus_Decoder(32, out_features=64))[0] == 'fc'
+        assert slp._swap_spec(ppp.PSP_Plus_Decoder(32, out_features=64))[1] == 'fc'
         assert slp._swap_spec(sp.UperNet_Decoder_Plus([16, 32, 64, 128], 16)) is None
+        import networks.deeplab_pop as dp
+        aspp = dp._ASPP(16, 32, rates=[1, 2]).eval()
+        xa = torch.randn(2, 16, 8, 8)
+        assert slp._swap_spec(aspp)[1] == 'fc'
+        assert torch.equal(slp._decode_fused(aspp, xa), aspp(xa)) and type(aspp.fc).__name__ == '_ConvBnReLU'
         assert 'bottleneck.0.weight' in psp.state_dict() and not any('_sl' in k for k in psp.state_dict())
     finally:
         slp.unpatch()

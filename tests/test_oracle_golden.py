@@ -165,6 +165,10 @@ def test_tails_match_reference_decoders(golden):
         assert np.array_equal(out.numpy(), z[name + '_out']), name
     maps = [t(f'sum_swin_map{i}') for i in range(4)]
     assert np.array_equal(ref_ops.ref_tail_sum(maps).numpy(), z['sum_swin_out'])
+    out = ref_ops.ref_tail_bn_relu(t('aspp_x'), t('aspp_bn_w'), t('aspp_bn_b'), t('aspp_bn_m'), t('aspp_bn_v'),
+                                   float(z['aspp_bn_eps']))
+    assert np.array_equal(out.numpy(), z['aspp_out'])
+    assert np.array_equal(ref_ops.ref_tail_concat([t(f'cat_hr_map{i}') for i in range(4)]).numpy(), z['cat_hr_out'])
     # the report helper: ideal rounding is <= 0.5 spacings everywhere and 100 % identical patterns
     ref = t('ln_c96_out')
     exact, d = ref_ops.bf16_ulp_report(ref.to(torch.bfloat16), ref)
