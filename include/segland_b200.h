@@ -39,6 +39,7 @@ extern "C" {
  *   SL_TC_SMALL=0       C <= 128: streaming kernel instead of the weights-resident narrow-head kernel
  *   SL_POST_FUSED_CM=1  sl_upsample_argmax counts the confusion matrix inside the interpolation kernel
  *   SL_TC_DEBUG=<bits>  knock-outs inside the single-CTA kernel (timing experiments, results INVALID)
+ *   SL_TAIL_FUSED=0     sl_tail_bn_relu_conv as two kernels (bf16 hi/lo planes in the workspace + generic GEMM)
  *   SL_SMALL_DBG=<ptr>  device pointer (decimal) of a 64x16 int64 buffer receiving per-tile cycle stamps of CTA 0
  */
 

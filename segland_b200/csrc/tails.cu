@@ -10,8 +10,12 @@
 //   sl_tail_concat         torch.cat([x0, x1, x2, x3], 1) of HRFPN_Seg_Decoder, networks/seghr_pop.py:23-24
 // The LayerNorm and sum kernels are HBM-bound (4 B read + 2 B written per element); the 1x1 convolution runs on
 // tcgen05 through the generic split-bf16 GEMM of pop_bwd_tc.cu (EPI_TAIL).
+#include <stdlib.h>
 #include "common.cuh"
 
+int sl_tail_conv_fused_run(const float* x, int B, int Cin, int N, const float* bn_w, const float* bn_b, const float* bn_m,
+                           const float* bn_v, float eps, int relu, const uint16_t* W_hi, const uint16_t* W_lo,
+                           const float* bias, int Cout, uint16_t* out, cudaStream_t st);
 int sl_tail_gemm_run(const uint16_t* act_hi, const uint16_t* act_lo, int B, int Cin, int N, const uint16_t* W_hi,
                      const uint16_t* W_lo, const float* bias, int Cout, uint16_t* feat_out, cudaStream_t st);
 
@@ -269,6 +273,18 @@ extern "C" int sl_tail_bn_relu_conv(const float* x, int B, int Cin, int N, const
   SL_CHECK_ARG(static_cast<long long>(B) * N < (1ll << 31));
   SL_CHECK_ALIGN(x, 16); SL_CHECK_ALIGN(ws, 128); SL_CHECK_ALIGN(W_hi, 16); SL_CHECK_ALIGN(W_lo, 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // Default: the fused kernel of tail_conv.cu (BN/ReLU/split applied to the A operand on the SM, no intermediate
+  // planes).  SL_TAIL_FUSED=0, or a shape outside its range (Cin > 1024), takes the two-kernel path below.
+  static int fused = -1;
+  if (fused < 0) {
+    const char* fe = getenv("SL_TAIL_FUSED");
+    fused = (fe != nullptr && fe[0] == '0') ? 0 : 1;
+  }
+  if (fused) {
+    const int frc = sl_tail_conv_fused_run(x, B, Cin, N, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, relu, W_hi, W_lo, bias,
+                                           Cout, feat_out, st);
+    if (frc != SL_EINVAL) return frc;
+  }
   // One split launch and one GEMM launch for the whole batch.  (Working through the batch in L2-sized groups of
   // images, so the hi/lo planes never leave the chip, was measured slower: 1 / 2 / 4 images per group 49.0 / 42.4 /
   // 36.1 us per PSPNet tile against 34.9 for the whole batch -- the persistent GEMM's partial last wave costs more
