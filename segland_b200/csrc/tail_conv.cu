@@ -13,7 +13,8 @@
 // TMA; warp 1's elected thread issues the twelve MMAs of the stage (3 passes x 4 k-slices) from ONE copy of each
 // operand, so a 96 KB stage feeds 1536 tensor cycles (the two-kernel path loaded 144 KB for the same work); four
 // epilogue warps read the double-buffered 128 x 256 accumulators, add the bias and store bf16.
-// Work item = (128-pixel tile, 256-channel n-tile), n-tile fastest so the second n-tile's x comes from L2.
+// Work item = (128-pixel tile, 256-channel n-tile); a CTA walks every n-tile of its pixel tiles, so the second
+// n-tile's x comes from L2.
 #include "tma.cuh"
 
 namespace sl {
@@ -69,7 +70,10 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
   auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * STAGES + 2 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int items = p.m_tiles * p.n_tiles;
+  // A CTA owns whole pixel tiles (every n-tile of tile blockIdx.x + i * gridDim.x, n-tile inner): the second n-tile's
+  // rows of x are L2 hits issued by the same SM a moment after the first pass fetched them from HBM.
+  const int my_mtiles = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int my_items = my_mtiles * p.n_tiles;
   const int kbs = (p.Cin + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
@@ -103,8 +107,8 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
     // ===================================================================== TMA producer: weight planes
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < items; w += gridDim.x) {
-        const int n0 = (w % p.n_tiles) * NT;
+      for (int i = 0; i < my_items; ++i) {
+        const int n0 = (i % p.n_tiles) * NT;
         for (int kb = 0; kb < kbs; ++kb) {
           mbar_wait(s_empty(stage), phase ^ 1u);
           mbar_expect_tx(b_full(stage), 2 * B_PLANE);
@@ -121,7 +125,7 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
       const uint32_t idesc = make_idesc(BLOCK_M, NT, true, 1u, 1u, false);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      for (int i = 0; i < my_items; ++i) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * NT);
@@ -163,15 +167,13 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
     // unpredicated loads from clamped addresses (rows past Cin read row Cin-1 and are zeroed by alpha = shift = 0 in
     // the table, pixels past N read the tile's last valid pixels and land in accumulator rows that are never stored).
     float4 preA[ROWS_PER_WARP], preB[ROWS_PER_WARP];
-    const int my_items = (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const int total = my_items * kbs;
     const size_t row_stride = static_cast<size_t>(p.N);
     // load cursor
     int ld_item = 0, ld_kb = 0;
     const float* ld_base = nullptr;                              // x[img][0][clamped pixel of this lane]
     auto ld_item_setup = [&]() {
-      const int w = blockIdx.x + ld_item * gridDim.x;
-      const int mt = w / p.n_tiles;
+      const int mt = blockIdx.x + (ld_item / p.n_tiles) * gridDim.x;
       const int img = mt / p.m_tiles_per_img;
       const int px = min((mt - img * p.m_tiles_per_img) * BLOCK_M + 4 * lane, p.N - 4);
       ld_base = p.x + static_cast<size_t>(img) * p.Cin * row_stride + px;
@@ -244,8 +246,8 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
     const int sub = warp & 3;
     const int row = sub * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < items; w += gridDim.x) {
-      const int nt = w % p.n_tiles, mt = w / p.n_tiles;
+    for (int i = 0; i < my_items; ++i) {
+      const int nt = i % p.n_tiles, mt = blockIdx.x + (i / p.n_tiles) * gridDim.x;
       const int img = mt / p.m_tiles_per_img;
       const int n_in_img = (mt - img * p.m_tiles_per_img) * BLOCK_M + row;
       const bool row_ok = n_in_img < p.N;
@@ -324,9 +326,8 @@ int sl_tail_conv_fused_run(const float* x, int B, int Cin, int N, const float* b
   if ((rc = make_map(&ml, W_lo, 2, dims, box)) != 0) return rc;
   cudaError_t e = cudaFuncSetAttribute(tail_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
-  const long long items = static_cast<long long>(p.m_tiles) * p.n_tiles;
-  if (items >= (1ll << 31)) return SL_EINVAL;
-  const int grid = static_cast<int>(items < sl::kNumSMs ? items : sl::kNumSMs);
+  if (static_cast<long long>(p.m_tiles) * p.n_tiles >= (1ll << 31)) return SL_EINVAL;
+  const int grid = p.m_tiles < sl::kNumSMs ? p.m_tiles : sl::kNumSMs;
   tail_conv_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mh, ml, p);
   return SL_LAUNCH_RESULT();
 }
