@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
     const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred, float* __restrict__ conf,
     float* __restrict__ probs, float* __restrict__ logits_hr, unsigned long long* __restrict__ cm, int coop) {
   constexpr bool EXTRA = KP > 0;
+  if constexpr (KP < 0) K = -KP;                               // exact-K instantiation of the plain path: loops fully unrolled
   extern __shared__ __align__(16) float hrow[];                 // [2][K][THREADS] float4, then raw [K][ncols] (coop)
   __shared__ unsigned int hist[SL_MAX_CLASSES * SL_MAX_CLASSES];
   const bool do_cm = cm != nullptr;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
       const bool bad = ((cy.i0 & 1) ? bad_odd : bad_even) | ((r1 & 1) ? bad_odd : bad_even);
       if constexpr (!EXTRA) {
         if (!bad) {
-#pragma unroll 4
+#pragma unroll (KP < 0 ? -KP : 4)
           for (int k = 0; k < K; ++k) {
             const float4 a = h0[k * THREADS], c = h1[k * THREADS];
             // l0*a + l1*c on packed fp32 pairs (FMUL2 + FFMA2): same products and sums as the scalar form
@@ -450,7 +451,8 @@ static int launch_rows(const float* logits_lr, int B, int K, int h, int w, int H
   const int coop = (sx > 0.f && sx <= 0.5f && (extra || sx > 0.2f) &&
                     base_smem + raw_smem <= (THREADS == 256 ? 110 * 1024 : 48 * 1024)) ? 1 : 0;
   const size_t smem = base_smem + (coop ? raw_smem : 0);
-  auto kern = !extra ? upsample_rows_kernel<THREADS, 0>
+  auto kern = !extra ? (K == 8 ? upsample_rows_kernel<THREADS, -8> : K == 12 ? upsample_rows_kernel<THREADS, -12>
+                                                                             : upsample_rows_kernel<THREADS, 0>)
               : K <= 8 ? upsample_rows_kernel<THREADS, 8>
               : K <= 12 ? upsample_rows_kernel<THREADS, 12>
               : K <= 16 ? upsample_rows_kernel<THREADS, 16> : upsample_rows_kernel<THREADS, 32>;
