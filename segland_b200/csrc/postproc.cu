@@ -293,13 +293,13 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
 
   size_t pix = (static_cast<size_t>(b) * H + y_begin) * W + x0;
   // labels are fetched four rows ahead so the load latency hides behind several rows of arithmetic
-  uchar4 lq0 = make_uchar4(0, 0, 0, 0), lq1 = lq0, lq2 = lq0, lq3 = lq0;
+  uint32_t lq0 = 0u, lq1 = 0u, lq2 = 0u, lq3 = 0u;              // four packed labels per row, kept as words (no byte shuffles)
   if (do_cm && col_ok) {
     const uint8_t* lp = label + pix;
-    if (y_begin + 0 < y_end) lq0 = *reinterpret_cast<const uchar4*>(lp);
-    if (y_begin + 1 < y_end) lq1 = *reinterpret_cast<const uchar4*>(lp + W);
-    if (y_begin + 2 < y_end) lq2 = *reinterpret_cast<const uchar4*>(lp + 2 * static_cast<size_t>(W));
-    if (y_begin + 3 < y_end) lq3 = *reinterpret_cast<const uchar4*>(lp + 3 * static_cast<size_t>(W));
+    if (y_begin + 0 < y_end) lq0 = *reinterpret_cast<const uint32_t*>(lp);
+    if (y_begin + 1 < y_end) lq1 = *reinterpret_cast<const uint32_t*>(lp + W);
+    if (y_begin + 2 < y_end) lq2 = *reinterpret_cast<const uint32_t*>(lp + 2 * static_cast<size_t>(W));
+    if (y_begin + 3 < y_end) lq3 = *reinterpret_cast<const uint32_t*>(lp + 3 * static_cast<size_t>(W));
   }
   // confusion counts: vertical run-length accumulation per thread (label and prediction maps are piecewise
   // constant, so a thread's four pixels usually stay in one bin for many rows): no warp collectives, one
@@ -308,14 +308,16 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
   unsigned int run_cnt = 0;
   for (int y = y_begin; y < y_end; ++y, pix += W) {
     int idx[4] = {0, 0, 0, 0};
-    const uchar4 l4 = lq0;
+    const uint32_t l4 = lq0;
     const SrcCoord cy = src_coord(sy, y, h);
     const int r1 = cy.i0 + cy.step;
     fill(cy.i0);                                                // uniform across the CTA (barriers inside when coop)
     fill(r1);
     if (col_ok) {
-      lq0 = lq1; lq1 = lq2; lq2 = lq3;
-      if (do_cm && y + 4 < y_end) lq3 = *reinterpret_cast<const uchar4*>(label + pix + 4 * static_cast<size_t>(W));
+      if (do_cm) {
+        lq0 = lq1; lq1 = lq2; lq2 = lq3;
+        if (y + 4 < y_end) lq3 = *reinterpret_cast<const uint32_t*>(label + pix + 4 * static_cast<size_t>(W));
+      }
       const float4* h0 = my + ((cy.i0 & 1) * K) * THREADS;
       const float4* h1 = my + ((r1 & 1) * K) * THREADS;
       const float l0 = cy.l0, l1 = cy.l1;
@@ -331,9 +333,14 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
             t01 = fma2(make_float2(l1, l1), make_float2(c.x, c.y), t01);
             t23 = fma2(make_float2(l1, l1), make_float2(c.z, c.w), t23);
             const float v[4] = {t01.x, t01.y, t23.x, t23.y};
+            if (KP < 0 && k == 0) {                              // finite values: v > -inf or v == -inf, either way (v, 0)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; }
+              for (int j = 0; j < 4; ++j) best[j] = v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; }
+            }
           }
         } else {
           for (int k = 0; k < K; ++k) {
@@ -402,7 +409,8 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
       if (pred) *reinterpret_cast<uchar4*>(pred + pix) = make_uchar4(idx[0], idx[1], idx[2], idx[3]);
     }
     if (do_cm && col_ok) {
-      const int lab[4] = {l4.x, l4.y, l4.z, l4.w};
+      const int lab[4] = {static_cast<int>(l4 & 0xffu), static_cast<int>((l4 >> 8) & 0xffu), static_cast<int>((l4 >> 16) & 0xffu),
+                          static_cast<int>(l4 >> 24)};
       int bin[4];
       bool valid[4];
 #pragma unroll
