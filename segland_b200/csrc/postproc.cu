@@ -199,13 +199,14 @@ __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const flo
 // KP == 0: predictions / confusion only (the eval hot path).  KP > 0: also soft outputs (conf, probs,
 // up-sampled logits) for K <= KP classes, whose interpolated values stay in registers so the softmax
 // costs one interpolation and one exp per value.
-template <int THREADS, int KP>
+template <int THREADS, int KP, bool EXACT = false>
 __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (THREADS == 256 ? 3 : 8)) upsample_rows_kernel(
     const float* __restrict__ logits_lr, int K, int h, int w, int H, int W, int rows_per_band, float sy, float sx,
     const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred, float* __restrict__ conf,
     float* __restrict__ probs, float* __restrict__ logits_hr, unsigned long long* __restrict__ cm, int coop) {
   constexpr bool EXTRA = KP > 0;
   if constexpr (KP < 0) K = -KP;                               // exact-K instantiation of the plain path: loops fully unrolled
+  if constexpr (KP > 0 && EXACT) K = KP;                       // exact-K soft-output path: the k < K predicates fold away
   extern __shared__ __align__(16) float hrow[];                 // [2][K][THREADS] float4, then raw [K][ncols] (coop)
   __shared__ unsigned int hist[SL_MAX_CLASSES * SL_MAX_CLASSES];
   const bool do_cm = cm != nullptr;
@@ -353,25 +354,36 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
       } else {
         float vals[4][KP > 0 ? KP : 1];
         const size_t plane_off = pix - static_cast<size_t>(b) * HW;
+        // output pointers advance by one class plane per k (two adds) instead of a 64-bit multiply-add per store
+        float* lg_out = logits_hr ? logits_hr + static_cast<size_t>(b) * K * HW + plane_off : nullptr;
+        if (!bad) {
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          if (k < K) {
-            const float4 a = h0[k * THREADS], c = h1[k * THREADS];
-            // l0*a + l1*c on packed fp32 pairs (FMUL2 + FFMA2): same products and sums as the scalar form
-            float2 t01 = mul2(make_float2(l0, l0), make_float2(a.x, a.y)), t23 = mul2(make_float2(l0, l0), make_float2(a.z, a.w));
-            t01 = fma2(make_float2(l1, l1), make_float2(c.x, c.y), t01);
-            t23 = fma2(make_float2(l1, l1), make_float2(c.z, c.w), t23);
-            const float v[4] = {t01.x, t01.y, t23.x, t23.y};
-            if (!bad) {
+          for (int k = 0; k < KP; ++k) {
+            if (k < K) {
+              const float4 a = h0[k * THREADS], c = h1[k * THREADS];
+              // l0*a + l1*c on packed fp32 pairs (FMUL2 + FFMA2): same products and sums as the scalar form
+              float2 t01 = mul2(make_float2(l0, l0), make_float2(a.x, a.y)), t23 = mul2(make_float2(l0, l0), make_float2(a.z, a.w));
+              t01 = fma2(make_float2(l1, l1), make_float2(c.x, c.y), t01);
+              t23 = fma2(make_float2(l1, l1), make_float2(c.z, c.w), t23);
+              const float v[4] = {t01.x, t01.y, t23.x, t23.y};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; } vals[j][k] = v[j]; }
-            } else {
+              for (int j = 0; j < 4; ++j) {
+                if (k == 0) { best[j] = v[j]; } else if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; }
+                vals[j][k] = v[j];
+              }
+              if (lg_out) { __stcs(reinterpret_cast<float4*>(lg_out), make_float4(v[0], v[1], v[2], v[3])); lg_out += HW; }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+            if (k < K) {
+              const float4 a = h0[k * THREADS], c = h1[k * THREADS];
+              const float v[4] = {l0 * a.x + l1 * c.x, l0 * a.y + l1 * c.y, l0 * a.z + l1 * c.z, l0 * a.w + l1 * c.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) { argmax_step(v[j], k, best[j], idx[j]); vals[j][k] = v[j]; }
+              if (lg_out) { __stcs(reinterpret_cast<float4*>(lg_out), make_float4(v[0], v[1], v[2], v[3])); lg_out += HW; }
             }
-            if (logits_hr)
-              __stcs(reinterpret_cast<float4*>(logits_hr + (static_cast<size_t>(b) * K + k) * HW + plane_off),
-                     make_float4(v[0], v[1], v[2], v[3]));
           }
         }
         if (conf || probs) {
@@ -395,13 +407,14 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
           for (int j = 0; j < 4; ++j) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv[j]) : "f"(s[j]));
           if (conf) *reinterpret_cast<float4*>(conf + pix) = make_float4(inv[0], inv[1], inv[2], inv[3]);
           if (probs) {
+            float* pr_out = probs + static_cast<size_t>(b) * K * HW + plane_off;
 #pragma unroll
             for (int k = 0; k < KP; ++k)
               if (k < K) {
                 const float2 p01 = mul2(make_float2(vals[0][k], vals[1][k]), make_float2(inv[0], inv[1]));
                 const float2 p23 = mul2(make_float2(vals[2][k], vals[3][k]), make_float2(inv[2], inv[3]));
-                __stcs(reinterpret_cast<float4*>(probs + (static_cast<size_t>(b) * K + k) * HW + plane_off),   // streaming:
-                       make_float4(p01.x, p01.y, p23.x, p23.y));                                               // written once
+                __stcs(reinterpret_cast<float4*>(pr_out), make_float4(p01.x, p01.y, p23.x, p23.y));   // streaming: written once
+                pr_out += HW;
               }
           }
         }
@@ -461,8 +474,10 @@ static int launch_rows(const float* logits_lr, int B, int K, int h, int w, int H
   const size_t smem = base_smem + (coop ? raw_smem : 0);
   auto kern = !extra ? (K == 8 ? upsample_rows_kernel<THREADS, -8> : K == 12 ? upsample_rows_kernel<THREADS, -12>
                                                                              : upsample_rows_kernel<THREADS, 0>)
-              : K <= 8 ? upsample_rows_kernel<THREADS, 8>
-              : K <= 12 ? upsample_rows_kernel<THREADS, 12>
+              : K == 8 ? upsample_rows_kernel<THREADS, 8, true>
+              : K < 8 ? upsample_rows_kernel<THREADS, 8>
+              : K == 12 ? upsample_rows_kernel<THREADS, 12, true>
+              : K < 12 ? upsample_rows_kernel<THREADS, 12>
               : K <= 16 ? upsample_rows_kernel<THREADS, 16> : upsample_rows_kernel<THREADS, 32>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
