@@ -199,7 +199,7 @@ __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const flo
 // KP == 0: predictions / confusion only (the eval hot path).  KP > 0: also soft outputs (conf, probs,
 // up-sampled logits) for K <= KP classes, whose interpolated values stay in registers so the softmax
 // costs one interpolation and one exp per value.
-template <int THREADS, int KP, bool EXACT = false>
+template <int THREADS, int KP, bool EXACT = false, bool LG = true>      // LG: the up-sampled logits may be requested
 __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (THREADS == 256 ? 3 : 8)) upsample_rows_kernel(
     const float* __restrict__ logits_lr, int K, int h, int w, int H, int W, int rows_per_band, float sy, float sx,
     const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred, float* __restrict__ conf,
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
         float vals[4][KP > 0 ? KP : 1];
         const size_t plane_off = pix - static_cast<size_t>(b) * HW;
         // output pointers advance by one class plane per k (two adds) instead of a 64-bit multiply-add per store
-        float* lg_out = logits_hr ? logits_hr + static_cast<size_t>(b) * K * HW + plane_off : nullptr;
+        float* lg_out = (LG && logits_hr) ? logits_hr + static_cast<size_t>(b) * K * HW + plane_off : nullptr;
         if (!bad) {
 #pragma unroll
           for (int k = 0; k < KP; ++k) {
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
                 if (k == 0) { best[j] = v[j]; } else if (v[j] > best[j]) { best[j] = v[j]; idx[j] = k; }
                 vals[j][k] = v[j];
               }
-              if (lg_out) { __stcs(reinterpret_cast<float4*>(lg_out), make_float4(v[0], v[1], v[2], v[3])); lg_out += HW; }
+              if (LG && lg_out) { __stcs(reinterpret_cast<float4*>(lg_out), make_float4(v[0], v[1], v[2], v[3])); lg_out += HW; }
             }
           }
         } else {
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(THREADS, KP > 0 ? (THREADS == 256 ? 2 : 4) : (
               const float v[4] = {l0 * a.x + l1 * c.x, l0 * a.y + l1 * c.y, l0 * a.z + l1 * c.z, l0 * a.w + l1 * c.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) { argmax_step(v[j], k, best[j], idx[j]); vals[j][k] = v[j]; }
-              if (lg_out) { __stcs(reinterpret_cast<float4*>(lg_out), make_float4(v[0], v[1], v[2], v[3])); lg_out += HW; }
+              if (LG && lg_out) { __stcs(reinterpret_cast<float4*>(lg_out), make_float4(v[0], v[1], v[2], v[3])); lg_out += HW; }
             }
           }
         }
@@ -474,9 +474,9 @@ static int launch_rows(const float* logits_lr, int B, int K, int h, int w, int H
   const size_t smem = base_smem + (coop ? raw_smem : 0);
   auto kern = !extra ? (K == 8 ? upsample_rows_kernel<THREADS, -8> : K == 12 ? upsample_rows_kernel<THREADS, -12>
                                                                              : upsample_rows_kernel<THREADS, 0>)
-              : K == 8 ? upsample_rows_kernel<THREADS, 8, true>
+              : K == 8 ? (logits_hr ? upsample_rows_kernel<THREADS, 8, true> : upsample_rows_kernel<THREADS, 8, true, false>)
               : K < 8 ? upsample_rows_kernel<THREADS, 8>
-              : K == 12 ? upsample_rows_kernel<THREADS, 12, true>
+              : K == 12 ? (logits_hr ? upsample_rows_kernel<THREADS, 12, true> : upsample_rows_kernel<THREADS, 12, true, false>)
               : K < 12 ? upsample_rows_kernel<THREADS, 12>
               : K <= 16 ? upsample_rows_kernel<THREADS, 16> : upsample_rows_kernel<THREADS, 32>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
