@@ -36,6 +36,8 @@ extern "C" {
 
 /* Environment switches read by the library (debugging and A/B measurements only; defaults are the fast paths):
  *   SL_TC_PAIR=0        background MLP on the single-CTA tcgen05 kernel instead of the cta_group::2 pair kernel
+ *   SL_TC_PAIR=1        pair kernel with one (A, B) operand pair per MMA pass and pipeline stage (the schedule before the
+ *                       de-duplicated stages; 4-10 % slower)
  *   SL_TC_SMALL=0       C <= 128: streaming kernel instead of the weights-resident narrow-head kernel
  *   SL_POST_FUSED_CM=1  sl_upsample_argmax counts the confusion matrix inside the interpolation kernel
  *   SL_TC_DEBUG=<bits>  knock-outs inside the single-CTA kernel (timing experiments, results INVALID)

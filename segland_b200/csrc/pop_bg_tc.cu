@@ -516,21 +516,32 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// DEDUP: a pipeline stage holds ONE copy of every operand tile of a k-block -- layer 1: the feature tile and the hi / lo
+// weight half-tiles (48 KB for two passes); layer 2: the hi / lo hidden tiles and the hi / lo weight half-tiles (64 KB
+// for three passes) -- instead of one (A, B) pair per pass, so the L2 -> shared-memory traffic per tensor cycle drops
+// from 64 to 47 / 42 bytes per clock per SM (three 64 KB stages in place of six 32 KB ones).
+constexpr int D_STAGES = 3;
+constexpr int D_STAGE_BYTES = 2 * A_BYTES + B_BYTES_MAX;     // [A0 16 KB][A1 16 KB][B0 16 KB][B1 16 KB]
+static_assert(D_STAGES * D_STAGE_BYTES == P_STAGES * P_STAGE_BYTES, "both pair layouts use the same 192 KB ring");
+
+template <bool DEDUP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   if ((base & 1023u) != 0) asm volatile("trap;");
+  constexpr int NSTG = DEDUP ? D_STAGES : P_STAGES;
+  constexpr int STG_BYTES = DEDUP ? D_STAGE_BYTES : P_STAGE_BYTES;
   const uint32_t stage_out = base + P_STAGES * P_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES + STAGING_BYTES + W3_BYTES);
   // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then h1_ready[slot][n-tile]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P_STAGES + 4 + 2 * MAX_N_TILES);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (P_STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * P_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * P_STAGES + 2 + s); };
-  auto h1_bar = [&](int slot, int nt) { return bar0 + 8u * (2 * P_STAGES + 4 + slot * MAX_N_TILES + nt); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (NSTG + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * NSTG + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * NSTG + 2 + s); };
+  auto h1_bar = [&](int slot, int nt) { return bar0 + 8u * (2 * NSTG + 4 + slot * MAX_N_TILES + nt); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t rank;
@@ -564,7 +575,7 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
     tma_prefetch_desc(&maps.x); tma_prefetch_desc(&maps.w1h); tma_prefetch_desc(&maps.w1l);
     tma_prefetch_desc(&maps.w2h); tma_prefetch_desc(&maps.w2l); tma_prefetch_desc(&maps.hh_ld);
     tma_prefetch_desc(&maps.hl_ld); tma_prefetch_desc(&maps.hh_st); tma_prefetch_desc(&maps.hl_st);
-    for (int s = 0; s < P_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NSTG; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * EPI_WARPS); }
     for (int s = 0; s < 2 * MAX_N_TILES; ++s) mbar_init(h1_bar(0, s), 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -584,26 +595,41 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
     // ===================================================================== TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      auto stage_wait = [&]() {
+      auto stage_wait = [&](uint32_t bytes) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         // the leader arms its full barrier with the bytes of BOTH CTAs' loads for this stage
-        if (leader_cta) mbar_expect_tx(full_bar(stage), 2u * (A_BYTES + b_bytes));
+        if (leader_cta) mbar_expect_tx(full_bar(stage), 2u * bytes);
       };
-      auto stage_next = [&]() { if (++stage == P_STAGES) { stage = 0; phase ^= 1u; } };
+      auto stage_next = [&]() { if (++stage == NSTG) { stage = 0; phase ^= 1u; } };
       auto load_g1 = [&](int s) {
         const int mt = tile_of(s);
         const int img = mt / p.tiles_per_image, n0 = (mt - img * p.tiles_per_image) * BLOCK_M;
-        for (int nt = 0; nt < p.n_tiles; ++nt)
-          for (int pass = 0; pass < p.l1_passes; ++pass)
+        if constexpr (DEDUP) {
+          for (int nt = 0; nt < p.n_tiles; ++nt)
             for (int kb = 0; kb < kblocks; ++kb) {
-              stage_wait();
-              const uint32_t sa = base + stage * P_STAGE_BYTES, sb = sa + A_BYTES;
+              stage_wait(A_BYTES + static_cast<uint32_t>(p.l1_passes) * b_bytes);
+              const uint32_t sa = base + stage * STG_BYTES, sb = sa + 2 * A_BYTES;
+              const int brow = nt * p.NT + static_cast<int>(rank) * half_nt;
               tma_load_3d_pair(sa, &maps.x, full_bar(stage), n0, kb * BLOCK_K, img, L2_EVICT_FIRST);
               tma_load_3d_pair(sa + A_BYTES / 2, &maps.x, full_bar(stage), n0 + 64, kb * BLOCK_K, img, L2_EVICT_FIRST);
-              tma_load_2d_pair(sb, pass == 1 ? &maps.w1l : &maps.w1h, full_bar(stage), kb * BLOCK_K,
-                               nt * p.NT + static_cast<int>(rank) * half_nt, L2_EVICT_LAST);
+              tma_load_2d_pair(sb, &maps.w1h, full_bar(stage), kb * BLOCK_K, brow, L2_EVICT_LAST);
+              if (p.l1_passes > 1)
+                tma_load_2d_pair(sb + B_BYTES_MAX / 2, &maps.w1l, full_bar(stage), kb * BLOCK_K, brow, L2_EVICT_LAST);
               stage_next();
             }
+        } else {
+          for (int nt = 0; nt < p.n_tiles; ++nt)
+            for (int pass = 0; pass < p.l1_passes; ++pass)
+              for (int kb = 0; kb < kblocks; ++kb) {
+                stage_wait(A_BYTES + b_bytes);
+                const uint32_t sa = base + stage * STG_BYTES, sb = sa + A_BYTES;
+                tma_load_3d_pair(sa, &maps.x, full_bar(stage), n0, kb * BLOCK_K, img, L2_EVICT_FIRST);
+                tma_load_3d_pair(sa + A_BYTES / 2, &maps.x, full_bar(stage), n0 + 64, kb * BLOCK_K, img, L2_EVICT_FIRST);
+                tma_load_2d_pair(sb, pass == 1 ? &maps.w1l : &maps.w1h, full_bar(stage), kb * BLOCK_K,
+                                 nt * p.NT + static_cast<int>(rank) * half_nt, L2_EVICT_LAST);
+                stage_next();
+              }
+        }
       };
       auto load_g2 = [&](int s) {
         const int l2_passes = p.h_f16 ? 1 : 3;
@@ -616,14 +642,28 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
                 mbar_wait(h1_bar(slot_of(s), ready), h1_parity(s));
                 fence_proxy_async_all();
               }
-            for (int pass = 0; pass < l2_passes; ++pass) {
-              stage_wait();
-              const uint32_t sa = base + stage * P_STAGE_BYTES, sb = sa + A_BYTES;
-              tma_load_2d_pair(sa, pass == 1 ? &maps.hl_ld : &maps.hh_ld, full_bar(stage), kb * BLOCK_K, ws_row0_of(s),
-                               L2_EVICT_LAST);
-              tma_load_2d_pair(sb, pass == 2 ? &maps.w2l : &maps.w2h, full_bar(stage), kb * BLOCK_K,
-                               nt * p.NT + static_cast<int>(rank) * half_nt, L2_EVICT_LAST);
+            if constexpr (DEDUP) {
+              const bool split = l2_passes == 3;
+              stage_wait((split ? 2u : 1u) * (A_BYTES + b_bytes));
+              const uint32_t sa = base + stage * STG_BYTES, sb = sa + 2 * A_BYTES;
+              const int brow = nt * p.NT + static_cast<int>(rank) * half_nt;
+              tma_load_2d_pair(sa, &maps.hh_ld, full_bar(stage), kb * BLOCK_K, ws_row0_of(s), L2_EVICT_LAST);
+              tma_load_2d_pair(sb, &maps.w2h, full_bar(stage), kb * BLOCK_K, brow, L2_EVICT_LAST);
+              if (split) {
+                tma_load_2d_pair(sa + A_BYTES, &maps.hl_ld, full_bar(stage), kb * BLOCK_K, ws_row0_of(s), L2_EVICT_LAST);
+                tma_load_2d_pair(sb + B_BYTES_MAX / 2, &maps.w2l, full_bar(stage), kb * BLOCK_K, brow, L2_EVICT_LAST);
+              }
               stage_next();
+            } else {
+              for (int pass = 0; pass < l2_passes; ++pass) {
+                stage_wait(A_BYTES + b_bytes);
+                const uint32_t sa = base + stage * STG_BYTES, sb = sa + A_BYTES;
+                tma_load_2d_pair(sa, pass == 1 ? &maps.hl_ld : &maps.hh_ld, full_bar(stage), kb * BLOCK_K, ws_row0_of(s),
+                                 L2_EVICT_LAST);
+                tma_load_2d_pair(sb, pass == 2 ? &maps.w2l : &maps.w2h, full_bar(stage), kb * BLOCK_K,
+                                 nt * p.NT + static_cast<int>(rank) * half_nt, L2_EVICT_LAST);
+                stage_next();
+              }
             }
           }
         }
@@ -643,21 +683,39 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MAX_NT);
         const uint32_t idesc = g2 ? idesc_g2 : idesc_g1;
         uint32_t accumulate = 0;
-        const int iters = (g2 ? (p.h_f16 ? 1 : 3) : p.l1_passes) * kblocks;
+        const int passes = g2 ? (p.h_f16 ? 1 : 3) : p.l1_passes;
+        const int iters = DEDUP ? kblocks : passes * kblocks;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * P_STAGE_BYTES, sb = sa + A_BYTES;
+          if constexpr (DEDUP) {
+            const uint32_t sa0 = base + stage * STG_BYTES, sb0 = sa0 + 2 * A_BYTES;
+            for (int pass = 0; pass < passes; ++pass) {
+              // layer 1: (x, W1'hi), (x, W1'lo);  layer 2: (h_hi, W2hi), (h_lo, W2hi), (h_hi, W2lo)
+              const uint32_t sa = (g2 && pass == 1) ? sa0 + A_BYTES : sa0;
+              const uint32_t sb = (g2 ? pass == 2 : pass == 1) ? sb0 + B_BYTES_MAX / 2 : sb0;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = g2 ? make_desc(sa + k * (UMMA_K * 2), 16, 1024)
-                                   : make_desc(sa + k * (UMMA_K * 128), A_BYTES / 2, 1024);
-            const uint64_t db = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            tc_mma_pair(d_tmem, da, db, idesc, accumulate);
-            accumulate = 1;
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t da = g2 ? make_desc(sa + k * (UMMA_K * 2), 16, 1024)
+                                       : make_desc(sa + k * (UMMA_K * 128), A_BYTES / 2, 1024);
+                const uint64_t db = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+                tc_mma_pair(d_tmem, da, db, idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+          } else {
+            const uint32_t sa = base + stage * STG_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t da = g2 ? make_desc(sa + k * (UMMA_K * 2), 16, 1024)
+                                     : make_desc(sa + k * (UMMA_K * 128), A_BYTES / 2, 1024);
+              const uint64_t db = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+              tc_mma_pair(d_tmem, da, db, idesc, accumulate);
+              accumulate = 1;
+            }
           }
           tc_commit_pair(empty_bar(stage));       // frees the stage in both CTAs once these MMAs retire
-          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == NSTG) { stage = 0; phase ^= 1u; }
         }
         tc_commit_pair(tfull_bar(acc));           // accumulators complete -> both CTAs' epilogues
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -901,9 +959,11 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
       if ((rc = make_map(&m.w2l, W2_lo, 2, wdims, wbox))) return rc;
       const int pair_tiles = (p.m_tiles + 1) / 2;
       int pgrid = 2 * (pair_tiles < sl::kNumSMs / 2 ? pair_tiles : sl::kNumSMs / 2);
-      cudaError_t pe2 = cudaFuncSetAttribute(bg_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+      const bool dedup = pe == nullptr || atoi(pe) != 1;            // SL_TC_PAIR=1: the older one-(A, B)-pair-per-pass stages
+      auto kern = dedup ? bg_pair_kernel<true> : bg_pair_kernel<false>;
+      cudaError_t pe2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
       if (pe2 != cudaSuccess) return static_cast<int>(pe2);
-      bg_pair_kernel<<<pgrid, THREADS, P_SMEM_BYTES, st>>>(m, p);
+      kern<<<pgrid, THREADS, P_SMEM_BYTES, st>>>(m, p);
       return SL_LAUNCH_RESULT();
     }
   }

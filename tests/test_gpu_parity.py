@@ -125,7 +125,9 @@ def test_head_tc_matches_simt_on_device(ops):
     assert torch.equal(a[:, 1:], b2[:, 1:])                                  # same fg kernel
     assert_close_rel(b[:, 1:].cpu(), a[:, 1:].cpu(), 1e-5, 'fused fg vs fg kernel (summation order only)')
     assert_close_rel(b[:, 0].cpu(), a[:, 0].cpu(), 2e-4, 'tc vs simt bg')
-    assert torch.equal(b[:, 0], b2[:, 0])
+    # single-CTA kernel (passes outer) vs pair kernel (passes inner per k-block): same products, different summation order
+    assert_close_rel(b[:, 0].cpu(), b2[:, 0].cpu(), 1e-5, 'single-CTA vs pair bg kernel')
+    assert_close_rel(b2[:, 0].cpu(), a[:, 0].cpu(), 2e-4, 'pair tc vs simt bg')
 
 
 @pytest.mark.parametrize('C,Kn,hw', [(512, 0, 64), (512, 4, 32), (192, 4, 64), (64, 4, 16)])
@@ -669,16 +671,15 @@ def test_trained_like_sweep_matches_reference_miou(ops):
 
 def test_fused_head_matches_two_launch_path(ops):
     """sl_pop_head_tc (fg logits computed inside the tensor-core kernel) against sl_pop_fg_lowres +
-    sl_pop_bg_tc: same background channel bit for bit (C > 128), foreground within fp32 summation-order noise."""
+    sl_pop_bg_tc: background and foreground within fp32 summation-order noise."""
     for C, Kn, hw in ((512, 0, (32, 32)), (512, 4, (16, 24)), (96, 4, (16, 16)), (480, 4, (8, 16)), (192, 1, (16, 16))):
         st = synth.make_head_state(C, 7, Kn, seed=C + Kn)
         feats = synth.make_random_features(2, C, hw[0], hw[1], seed=C).cuda()
         one = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n, bg_mode='tc', fuse=True)(feats)
         two = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n, bg_mode='tc', fuse=False)(feats)
-        if C > 128:
-            assert torch.equal(one[:, 0], two[:, 0])
-        else:          # narrow heads take the weights-resident kernel (pop_bg_small.cu): same products, other summation order
-            assert_close_rel(one[:, 0].cpu(), two[:, 0].cpu(), 1e-5, f'fused bg C={C}')
+        # the single-launch kernel walks passes outer / k-blocks inner, the pair kernel the other way round, and narrow
+        # heads take the weights-resident kernel (pop_bg_small.cu): same products, other summation order
+        assert_close_rel(one[:, 0].cpu(), two[:, 0].cpu(), 1e-5, f'fused bg C={C}')
         assert_close_rel(one[:, 1:].cpu(), two[:, 1:].cpu(), 1e-5, f'fused fg C={C}')
         ref = ref_ops.ref_head(feats.cpu().float(), st.base_emb, st.novel_emb, st.cls, st.cls_n)
         assert_close_rel(one.cpu(), ref, RTOL, f'fused head C={C}')
