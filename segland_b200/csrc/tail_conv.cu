@@ -6,12 +6,12 @@
 // The convolution is the split-bf16 product r_hi W_hi + r_lo W_hi + r_hi W_lo (fp32 accumulation in TMEM, ~1e-5 of
 // fp32), r = relu(bn(x)).  tcgen05.mma takes its operands from shared memory, and TMA cannot convert, so the A
 // operand is produced on the SM: eight "transform" warps load the fp32 tile of a k-block (64 channels x 128 pixels)
-// straight from global memory into registers (one channel row per warp-wide 512-byte load, issued two k-blocks
-// ahead), apply alpha = w / sqrt(var + eps), x * alpha + (b - mean * alpha), ReLU, split into bf16 hi / lo and store
+// straight from global memory into registers (one channel row per warp-wide 512-byte load, four half k-blocks in
+// flight), apply alpha = w / sqrt(var + eps), x * alpha + (b - mean * alpha), ReLU, split into bf16 hi / lo and store
 // both planes in the MN-major SWIZZLE_128B layout a TMA box load would have produced (16-byte chunk index XOR
 // channel-row & 7), then fence.proxy.async + mbarrier arrive.  Warp 0 streams the W_hi / W_lo tiles of the k-block by
 // TMA; warp 1's elected thread issues the twelve MMAs of the stage (3 passes x 4 k-slices) from ONE copy of each
-// operand, so a 96 KB stage feeds 1536 tensor cycles (the two-kernel path loaded 144 KB for the same work); four
+// operand, so 96 KB of operands feed 1536 tensor cycles (the two-kernel path loaded 144 KB for the same work); four
 // epilogue warps read the double-buffered 128 x 256 accumulators, add the bias and store bf16.
 // Work item = (128-pixel tile, 256-channel n-tile); a CTA walks every n-tile of its pixel tiles, so the second
 // n-tile's x comes from L2.
@@ -21,20 +21,27 @@ namespace sl {
 namespace tailconv {
 using namespace sl::tc;
 
-constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16, NT = 256, STAGES = 2;
-constexpr int A_PLANE = BLOCK_M * BLOCK_K * 2;            // 16 KB: one bf16 plane of the activation tile
+constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16, NT = 256;
+constexpr int B_STAGES = 2;                               // weight ring: k-blocks of 64 channels
 constexpr int B_PLANE = NT * BLOCK_K * 2;                 // 32 KB: one bf16 plane of the weight tile
-constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;    // 96 KB
+constexpr int B_STAGE_BYTES = 2 * B_PLANE;                // W_hi + W_lo
+constexpr int HALF_K = 32;                                // activation ring: half k-blocks of 32 channels
+constexpr int A_SLOTS = 4;
+constexpr int A_BOX = HALF_K * 128;                       // 4 KB: 32 channel rows x 64 pixels (one SWIZZLE_128B box)
+constexpr int A_PLANE = 2 * A_BOX;                        // 8 KB: one bf16 plane of a 128-pixel half k-block
+constexpr int A_SLOT_BYTES = 2 * A_PLANE;                 // hi + lo
+constexpr int OPERAND_BYTES = B_STAGES * B_STAGE_BYTES + A_SLOTS * A_SLOT_BYTES;   // 128 + 64 = 192 KB
 constexpr int XF_WARPS = 8, EPI_WARPS = 4;
 constexpr int XF_THREADS = 32 * XF_WARPS;
 constexpr int THREADS = 64 + XF_THREADS + 32 * EPI_WARPS;   // 448
-constexpr int ROWS_PER_WARP = BLOCK_K / XF_WARPS;          // 8 channel rows of a k-block per transform warp
+constexpr int ROWS_PER_WARP = HALF_K / XF_WARPS;           // 4 channel rows of a half k-block per transform warp
+constexpr int N_BUF = 4;                                   // half k-blocks of fp32 rows in flight per thread
 constexpr int MAX_CIN = 1024;
 constexpr int MAX_COUT = 2048;
 constexpr int BN_BYTES = 2 * MAX_CIN * 4;
 constexpr int BIAS_BYTES = MAX_COUT * 4;
-constexpr int BAR_BYTES = 128;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN_BYTES + BIAS_BYTES + BAR_BYTES;
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = OPERAND_BYTES + BN_BYTES + BIAS_BYTES + BAR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 static_assert(EPI_WARPS == 4 && ((2 + XF_WARPS) & 3) == 2, "epilogue warps must cover the four TMEM lane quarters");
 
@@ -58,16 +65,18 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   if ((base & 1023u) != 0) asm volatile("trap;");
-  float* bn_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // alpha[MAX_CIN], shift[MAX_CIN]
-  float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BN_BYTES);   // [roundup32(Cout)], zero padded
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BN_BYTES + BIAS_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  float* bn_s = reinterpret_cast<float*>(smem + OPERAND_BYTES);                 // alpha[MAX_CIN], shift[MAX_CIN]
+  float* bias_s = reinterpret_cast<float*>(smem + OPERAND_BYTES + BN_BYTES);          // [roundup32(Cout)], zero padded
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OPERAND_BYTES + BN_BYTES + BIAS_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * B_STAGES + 2 * A_SLOTS + 4);
   const uint32_t bar0 = smem_u32(bars);
+  const uint32_t a_base = base + B_STAGES * B_STAGE_BYTES;
   auto b_full = [&](int s) { return bar0 + 8u * s; };
-  auto a_ready = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  auto s_empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (3 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * STAGES + 2 + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (B_STAGES + s); };
+  auto a_ready = [&](int q) { return bar0 + 8u * (2 * B_STAGES + q); };
+  auto a_empty = [&](int q) { return bar0 + 8u * (2 * B_STAGES + A_SLOTS + q); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * B_STAGES + 2 * A_SLOTS + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * B_STAGES + 2 * A_SLOTS + 2 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // A CTA owns whole pixel tiles (every n-tile of tile blockIdx.x + i * gridDim.x, n-tile inner): the second n-tile's
@@ -78,7 +87,8 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_whi); tma_prefetch_desc(&map_wlo);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(a_ready(s), XF_THREADS); mbar_init(s_empty(s), 1); }
+    for (int s = 0; s < B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int q = 0; q < A_SLOTS; ++q) { mbar_init(a_ready(q), XF_THREADS); mbar_init(a_empty(q), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -110,12 +120,12 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
       for (int i = 0; i < my_items; ++i) {
         const int n0 = (i % p.n_tiles) * NT;
         for (int kb = 0; kb < kbs; ++kb) {
-          mbar_wait(s_empty(stage), phase ^ 1u);
+          mbar_wait(b_empty(stage), phase ^ 1u);
           mbar_expect_tx(b_full(stage), 2 * B_PLANE);
-          const uint32_t sb = base + stage * STAGE_BYTES + 2 * A_PLANE;
+          const uint32_t sb = base + stage * B_STAGE_BYTES;
           tma_load_2d(sb, &map_whi, b_full(stage), kb * BLOCK_K, n0, L2_EVICT_LAST);
           tma_load_2d(sb + B_PLANE, &map_wlo, b_full(stage), kb * BLOCK_K, n0, L2_EVICT_LAST);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == B_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -124,6 +134,7 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BLOCK_M, NT, true, 1u, 1u, false);
       int stage = 0; uint32_t phase = 0;
+      int aq = 0; uint32_t a_phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int i = 0; i < my_items; ++i) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -132,22 +143,27 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
         uint32_t accumulate = 0;
         for (int kb = 0; kb < kbs; ++kb) {
           mbar_wait(b_full(stage), phase);
-          mbar_wait(a_ready(stage), phase);
-          tc_fence_after();
-          const uint32_t sa_hi = base + stage * STAGE_BYTES, sa_lo = sa_hi + A_PLANE;
-          const uint32_t sb_hi = sa_hi + 2 * A_PLANE, sb_lo = sb_hi + B_PLANE;
+          const uint32_t sb_hi = base + stage * B_STAGE_BYTES, sb_lo = sb_hi + B_PLANE;
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {                 // r_hi W_hi + r_lo W_hi + r_hi W_lo
-            const uint32_t sa = pass == 1 ? sa_lo : sa_hi, sb = pass == 2 ? sb_lo : sb_hi;
+          for (int h = 0; h < BLOCK_K / HALF_K; ++h) {           // the activation tile arrives in half k-blocks
+            mbar_wait(a_ready(aq), a_phase);
+            tc_fence_after();
+            const uint32_t sa_hi = a_base + aq * A_SLOT_BYTES, sa_lo = sa_hi + A_PLANE;
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              tc_mma(d_tmem, make_desc(sa + k * (UMMA_K * 128), 8192, 1024), make_desc(sb + k * (UMMA_K * 2), 16, 1024),
-                     idesc, accumulate);
-              accumulate = 1;
+            for (int pass = 0; pass < 3; ++pass) {               // r_hi W_hi + r_lo W_hi + r_hi W_lo
+              const uint32_t sa = pass == 1 ? sa_lo : sa_hi, sb = pass == 2 ? sb_lo : sb_hi;
+#pragma unroll
+              for (int k = 0; k < HALF_K / UMMA_K; ++k) {
+                tc_mma(d_tmem, make_desc(sa + k * (UMMA_K * 128), A_BOX, 1024),
+                       make_desc(sb + (h * (HALF_K / UMMA_K) + k) * (UMMA_K * 2), 16, 1024), idesc, accumulate);
+                accumulate = 1;
+              }
             }
+            tc_commit(a_empty(aq));                              // the half-slot is free once these six MMAs retire
+            if (++aq == A_SLOTS) { aq = 0; a_phase ^= 1u; }
           }
-          tc_commit(s_empty(stage));                             // both operands of the stage are free once these retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          tc_commit(b_empty(stage));
+          if (++stage == B_STAGES) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -157,20 +173,22 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
     // ===================================================================== transform warps: fp32 -> BN/ReLU -> bf16 hi/lo
     const int xw = warp - 2;
     // lane = pixels [4*lane, 4*lane+4) of the 128-pixel tile: box = lane/16 (64-pixel SWIZZLE_128B box), 16-byte chunk
-    // (lane%16)/2, 8-byte half lane%2; channel row r of the k-block lives at r*128 with its chunks XORed by r&7
-    const uint32_t lane_off = static_cast<uint32_t>((lane >> 4) * 8192 + (lane & 1) * 8);
+    // (lane%16)/2, 8-byte half lane%2; channel row r of the half k-block lives at r*128 with its chunks XORed by r&7
+    const uint32_t lane_off = static_cast<uint32_t>((lane >> 4) * A_BOX + (lane & 1) * 8);
     const uint32_t chunk = static_cast<uint32_t>((lane & 15) >> 1);
-    // Two k-blocks of fp32 rows are kept in flight per thread (2 x 8 x 16 B).  The loop is written for instruction
-    // count: the first version spent ~700 instructions per warp and k-block (integer divisions for the work-item
-    // decoding, per-row predicates) and the eight transform warps were issue-bound at ~2800 cycles per k-block against
-    // 1536 of tensor work (ncu source page).  Now: running cursors (a division only when the work item changes),
-    // unpredicated loads from clamped addresses (rows past Cin read row Cin-1 and are zeroed by alpha = shift = 0 in
-    // the table, pixels past N read the tile's last valid pixels and land in accumulator rows that are never stored).
-    float4 preA[ROWS_PER_WARP], preB[ROWS_PER_WARP];
-    const int total = my_items * kbs;
+    // The unit of work is a HALF k-block (32 channels, 4 rows per warp = 16 registers per thread), and four of them
+    // are in flight per thread: with whole k-blocks only two fit under the 128-register ceiling, i.e. one HBM round
+    // trip per ~1,500 tensor cycles, and the first use of a loaded row was the transform warps' top stall (tensor pipe
+    // 73 % active).  The loop is written for instruction count: running cursors (a division only when the work item
+    // changes), unpredicated loads from clamped addresses (rows past Cin read row Cin-1 and are zeroed by
+    // alpha = shift = 0 in the table, pixels past N read the tile's last valid pixels and land in accumulator rows
+    // that are never stored).
+    float4 pre0[ROWS_PER_WARP], pre1[ROWS_PER_WARP], pre2[ROWS_PER_WARP], pre3[ROWS_PER_WARP];
+    const int total = my_items * kbs * (BLOCK_K / HALF_K);       // half-steps of this CTA
     const size_t row_stride = static_cast<size_t>(p.N);
     // load cursor
-    int ld_item = 0, ld_kb = 0;
+    int ld_item = 0, ld_c = 0;                                   // ld_c: first channel of the next half k-block
+    const int c_end = kbs * BLOCK_K;
     const float* ld_base = nullptr;                              // x[img][0][clamped pixel of this lane]
     auto ld_item_setup = [&]() {
       const int mt = blockIdx.x + (ld_item / p.n_tiles) * gridDim.x;
@@ -179,7 +197,7 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
       ld_base = p.x + static_cast<size_t>(img) * p.Cin * row_stride + px;
     };
     auto issue_loads = [&](float4 (&pre)[ROWS_PER_WARP]) {
-      const int c0 = ld_kb * BLOCK_K + xw * ROWS_PER_WARP;
+      const int c0 = ld_c + xw * ROWS_PER_WARP;
       if (c0 + ROWS_PER_WARP <= p.Cin) {
         const float* src = ld_base + static_cast<size_t>(c0) * row_stride;
 #pragma unroll
@@ -189,22 +207,18 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
         for (int j = 0; j < ROWS_PER_WARP; ++j)
           pre[j] = __ldg(reinterpret_cast<const float4*>(ld_base + static_cast<size_t>(min(c0 + j, p.Cin - 1)) * row_stride));
       }
-      if (++ld_kb == kbs) { ld_kb = 0; ++ld_item; if (ld_item < my_items) ld_item_setup(); }
+      ld_c += HALF_K;
+      if (ld_c == c_end) { ld_c = 0; ++ld_item; if (ld_item < my_items) ld_item_setup(); }
     };
-    int stage = 0; uint32_t phase = 0;
-    int kb_proc = 0;
+    int aq = 0; uint32_t a_phase = 0;
+    int c_proc = 0;
     const bool relu = p.relu != 0;
     auto do_step = [&](float4 (&pre)[ROWS_PER_WARP], bool more) {
-      const int c0 = kb_proc * BLOCK_K + xw * ROWS_PER_WARP;
-      if (++kb_proc == kbs) kb_proc = 0;
-      float al[ROWS_PER_WARP], sh[ROWS_PER_WARP];
-      {
-        const float4 a0 = *reinterpret_cast<const float4*>(bn_s + c0), a1 = *reinterpret_cast<const float4*>(bn_s + c0 + 4);
-        const float4 s0 = *reinterpret_cast<const float4*>(bn_s + MAX_CIN + c0);
-        const float4 s1 = *reinterpret_cast<const float4*>(bn_s + MAX_CIN + c0 + 4);
-        al[0] = a0.x; al[1] = a0.y; al[2] = a0.z; al[3] = a0.w; al[4] = a1.x; al[5] = a1.y; al[6] = a1.z; al[7] = a1.w;
-        sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
-      }
+      const int c0 = c_proc + xw * ROWS_PER_WARP;
+      c_proc += HALF_K;
+      if (c_proc == c_end) c_proc = 0;
+      const float4 al4 = *reinterpret_cast<const float4*>(bn_s + c0), sh4 = *reinterpret_cast<const float4*>(bn_s + MAX_CIN + c0);
+      const float al[ROWS_PER_WARP] = {al4.x, al4.y, al4.z, al4.w}, sh[ROWS_PER_WARP] = {sh4.x, sh4.y, sh4.z, sh4.w};
       uint32_t hi[ROWS_PER_WARP][2], lo[ROWS_PER_WARP][2];
 #pragma unroll
       for (int j = 0; j < ROWS_PER_WARP; ++j) {
@@ -219,8 +233,8 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
         lo[j][0] = pack_bf16(v[0] - bf16lo(hi[j][0]), v[1] - bf16hi(hi[j][0]));
         lo[j][1] = pack_bf16(v[2] - bf16lo(hi[j][1]), v[3] - bf16hi(hi[j][1]));
       }
-      mbar_wait(s_empty(stage), phase ^ 1u);
-      const uint32_t sa = base + stage * STAGE_BYTES + lane_off;
+      mbar_wait(a_empty(aq), a_phase ^ 1u);
+      const uint32_t sa = a_base + aq * A_SLOT_BYTES + lane_off;
 #pragma unroll
       for (int j = 0; j < ROWS_PER_WARP; ++j) {
         const uint32_t r = static_cast<uint32_t>(xw * ROWS_PER_WARP + j);
@@ -229,17 +243,20 @@ tail_conv_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_const
         st_shared_v2(sa + A_PLANE + off, lo[j][0], lo[j][1]);
       }
       fence_async_smem();                                        // generic-proxy stores -> visible to tcgen05.mma
-      mbar_arrive(a_ready(stage));
-      // the proxy fence / release above wait for the thread's outstanding loads, so the refill goes after them
-      if (more) issue_loads(pre);
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      mbar_arrive(a_ready(aq));
+      if (more) issue_loads(pre);                                // refill after the fence (it waits for outstanding loads)
+      if (++aq == A_SLOTS) { aq = 0; a_phase ^= 1u; }
     };
     if (my_items > 0) ld_item_setup();
-    if (total > 0) issue_loads(preA);
-    if (total > 1) issue_loads(preB);
-    for (int step = 0; step < total; step += 2) {
-      do_step(preA, step + 2 < total);
-      if (step + 1 < total) do_step(preB, step + 3 < total);
+    if (total > 0) issue_loads(pre0);
+    if (total > 1) issue_loads(pre1);
+    if (total > 2) issue_loads(pre2);
+    if (total > 3) issue_loads(pre3);
+    for (int step = 0; step < total; step += N_BUF) {            // total is even; the tail is guarded
+      do_step(pre0, step + 4 < total);
+      if (step + 1 < total) do_step(pre1, step + 5 < total);
+      if (step + 2 < total) do_step(pre2, step + 6 < total);
+      if (step + 3 < total) do_step(pre3, step + 7 < total);
     }
   } else {
     // ===================================================================== epilogue: + bias, bf16, NCHW
