@@ -46,28 +46,36 @@ __global__ void __launch_bounds__(256) mlp1_kernel(const float* __restrict__ s_h
     const int i = lane + 32 * j;
     const bool ok = j < per_lane && i < C && o < C;
     wf[j] = ok ? __ldg(W1f + static_cast<size_t>(o) * C + i) : 0.f;
-    wg[j] = ok ? __ldg(W1g + static_cast<size_t>(o) * C + i) : 0.f;
+    wg[j] = W1g == W1f ? wf[j] : (ok ? __ldg(W1g + static_cast<size_t>(o) * C + i) : 0.f);      // base mode: one MLP
   }
   for (int k0 = 0; k0 < K; k0 += VCHUNK) {
     const int nk = min(VCHUNK, K - k0);
     __syncthreads();
     for (int idx = threadIdx.x; idx < nk * C; idx += 256) xs[idx] = s_hat[static_cast<size_t>(k0) * C + idx];
     __syncthreads();
-    for (int kk = 0; kk < nk; ++kk) {
-      const int k = k0 + kk;
-      const bool fg = k < Kb;
-      float acc = 0.f;
+    // all staged vectors at once: VCHUNK independent accumulation chains instead of one (the loop was latency-bound)
+    float acc[VCHUNK];
 #pragma unroll
-      for (int j = 0; j < MAXC_REG; ++j)
-        if (j < per_lane) {
-          const int i = lane + 32 * j;
-          acc = fmaf(fg ? wf[j] : wg[j], i < C ? xs[kk * C + i] : 0.f, acc);
+    for (int kk = 0; kk < VCHUNK; ++kk) acc[kk] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXC_REG; ++j)
+      if (j < per_lane) {
+        const int i = lane + 32 * j;
+        if (i < C) {
+#pragma unroll
+          for (int kk = 0; kk < VCHUNK; ++kk)
+            if (kk < nk) acc[kk] = fmaf((k0 + kk) < Kb ? wf[j] : wg[j], xs[kk * C + i], acc[kk]);
         }
-      acc = warp_sum(acc);
-      if (lane == 0 && o < C) {
-        h1[static_cast<size_t>(2 * k) * C + o] = fmaxf(acc, 0.f);
-        h1[static_cast<size_t>(2 * k + 1) * C + o] = fmaxf(-acc, 0.f);
       }
+#pragma unroll
+    for (int kk = 0; kk < VCHUNK; ++kk) acc[kk] = warp_sum(acc[kk]);
+    if (lane == 0 && o < C) {
+#pragma unroll
+      for (int kk = 0; kk < VCHUNK; ++kk)
+        if (kk < nk) {
+          h1[static_cast<size_t>(2 * (k0 + kk)) * C + o] = fmaxf(acc[kk], 0.f);
+          h1[static_cast<size_t>(2 * (k0 + kk) + 1) * C + o] = fmaxf(-acc[kk], 0.f);
+        }
     }
   }
 }
@@ -86,7 +94,7 @@ __global__ void __launch_bounds__(256) mlp2_kernel(const float* __restrict__ h1,
     const int i = lane + 32 * j;
     const bool ok = j < per_lane && i < C && o < C;
     wf[j] = ok ? __ldg(W2f + static_cast<size_t>(o) * C + i) : 0.f;
-    wg[j] = ok ? __ldg(W2g + static_cast<size_t>(o) * C + i) : 0.f;
+    wg[j] = W2g == W2f ? wf[j] : (ok ? __ldg(W2g + static_cast<size_t>(o) * C + i) : 0.f);      // base mode: one MLP
   }
   const int V = 2 * K;
   for (int v0 = 0; v0 < V; v0 += VCHUNK) {
@@ -94,18 +102,25 @@ __global__ void __launch_bounds__(256) mlp2_kernel(const float* __restrict__ h1,
     __syncthreads();
     for (int idx = threadIdx.x; idx < nv * C; idx += 256) xs[idx] = h1[static_cast<size_t>(v0) * C + idx];
     __syncthreads();
-    for (int vv = 0; vv < nv; ++vv) {
-      const int v = v0 + vv;
-      const bool fg = (v >> 1) < Kb;
-      float acc = 0.f;
+    float acc[VCHUNK];
 #pragma unroll
-      for (int j = 0; j < MAXC_REG; ++j)
-        if (j < per_lane) {
-          const int i = lane + 32 * j;
-          acc = fmaf(fg ? wf[j] : wg[j], i < C ? xs[vv * C + i] : 0.f, acc);
+    for (int vv = 0; vv < VCHUNK; ++vv) acc[vv] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXC_REG; ++j)
+      if (j < per_lane) {
+        const int i = lane + 32 * j;
+        if (i < C) {
+#pragma unroll
+          for (int vv = 0; vv < VCHUNK; ++vv)
+            if (vv < nv) acc[vv] = fmaf(((v0 + vv) >> 1) < Kb ? wf[j] : wg[j], xs[vv * C + i], acc[vv]);
         }
-      acc = warp_sum(acc);
-      if (lane == 0 && o < C) h2[static_cast<size_t>(v) * C + o] = fmaxf(acc, 0.f);
+      }
+#pragma unroll
+    for (int vv = 0; vv < VCHUNK; ++vv) acc[vv] = warp_sum(acc[vv]);
+    if (lane == 0 && o < C) {
+#pragma unroll
+      for (int vv = 0; vv < VCHUNK; ++vv)
+        if (vv < nv) h2[static_cast<size_t>(v0 + vv) * C + o] = fmaxf(acc[vv], 0.f);
     }
   }
 }
