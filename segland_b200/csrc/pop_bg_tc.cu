@@ -25,6 +25,8 @@
 // TMEM (2 x 256 columns), so the epilogue of one job overlaps the MMAs of the next.  Operands arrive
 // by TMA (SWIZZLE_128B) through a 4-stage mbarrier ring: 16 KB (A) + up to 32 KB (B) per stage; G1's
 // epilogue leaves through SWIZZLE_64B shared-memory staging and TMA bulk stores.
+// The default launch is the cta_group::2 form of the same schedule (bg_pair_kernel<DEDUP = true>, further down):
+// two CTAs share every weight tile and a pipeline stage holds one copy of every operand tile of a k-block.
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include "tma.cuh"
