@@ -142,7 +142,7 @@ class PopHead:
     def refresh(self):
         """Recompute s_hat / alpha / beta / folded weights; call after any weight update."""
         dev, C, K = self.device, self.C, self.K
-        protos = self.base_emb if self.novel_emb is None else torch.cat([self.base_emb, self.novel_emb], 0)
+        protos = (self.base_emb if self.novel_emb is None else torch.cat([self.base_emb, self.novel_emb], 0)).contiguous()
         fg = self.cls
         bg = self.cls_n if self.cls_n is not None else self.cls
         new = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
@@ -154,7 +154,7 @@ class PopHead:
         hf = f16 if f16 else (None,) * 2
         ws = new(_cabi.lib().sl_pop_prepare_ws_bytes(K, C) // 4)
         with torch.cuda.device(dev):
-            call('sl_pop_prepare', ptr(protos.contiguous()), K, self.Kb, C, ptr(fg[0]), ptr(fg[1]), ptr(fg[2]),
+            call('sl_pop_prepare', ptr(protos), K, self.Kb, C, ptr(fg[0]), ptr(fg[1]), ptr(fg[2]),
                  ptr(bg[0]), ptr(bg[1]), ptr(bg[2]), ptr(plan.s_hat), ptr(plan.alpha), ptr(plan.beta),
                  ptr(plan.W1p_t), ptr(plan.W2_t), ptr(sp[0]), ptr(sp[1]), ptr(sp[2]), ptr(sp[3]), ptr(hf[0]), ptr(hf[1]),
                  ptr(ws), _stream())
