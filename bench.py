@@ -335,9 +335,9 @@ def run_ours(args, rank, world, local_rank):
         'roofline': roofline,
         'stage_s': stage_s,
         'e2e': e2e,
-        # per step: 5 (prepare) + head (2 launches fused incl. the prototype transpose, else fg + bg) + upsample/argmax
-        # + confusion over (label, pred)
-        'gpu_launches': args.steps * 9,
+        # per step: 3 (prepare: {normalise + layer 1 + fold}, layer 2, layer 3; 5 with SL_PREP_SPLIT=1) + head (2 launches
+        # fused incl. the prototype transpose, else fg + bg) + upsample/argmax + confusion over (label, pred)
+        'gpu_launches': args.steps * ((5 if os.environ.get('SL_PREP_SPLIT', '')[:1] == '1' else 3) + 4),
         'clocks': clocks,
         'miou_total': float(mious[2]),
     }

@@ -39,6 +39,7 @@ extern "C" {
  *   SL_TC_PAIR=1        pair kernel with one (A, B) operand pair per MMA pass and pipeline stage (the schedule before the
  *                       de-duplicated stages; 4-10 % slower)
  *   SL_TC_SMALL=0       C <= 128: streaming kernel instead of the weights-resident narrow-head kernel
+ *   SL_PREP_SPLIT=1     sl_pop_prepare as five separate launches instead of three
  *   SL_POST_FUSED_CM=1  sl_upsample_argmax counts the confusion matrix inside the interpolation kernel
  *   SL_TC_DEBUG=<bits>  knock-outs inside the single-CTA kernel (timing experiments, results INVALID)
  *   SL_TAIL_FUSED=0     sl_tail_bn_relu_conv as two kernels (bf16 hi/lo planes in the workspace + generic GEMM)

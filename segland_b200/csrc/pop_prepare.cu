@@ -3,6 +3,7 @@
 //              :46-52,57-63 (classifier / classifier_n), :112,118 (bg = q - sum_k p_k s_k).
 // Three tiny kernels (K <= 31, C <= 1024): total work ~ K*C^2 FMA, negligible next to one tile.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace sl {
@@ -32,13 +33,14 @@ __global__ void __launch_bounds__(128) normalize_protos_kernel(const float* __re
 constexpr int VCHUNK = 8;          // input vectors staged per pass: 8 * C * 4 B <= 32 KB at C = 1024
 constexpr int MAXC_REG = 32;       // C <= 1024 -> at most 32 weights per lane
 
-// h1[v][o] = relu(+-W1x[o] . s_hat_k)        grid C/8, 256 threads
-__global__ void __launch_bounds__(256) mlp1_kernel(const float* __restrict__ s_hat, int K, int Kb, int C,
-                                                   const float* __restrict__ W1f, const float* __restrict__ W1g,
-                                                   float* __restrict__ h1) {
-  extern __shared__ float xs[];     // [VCHUNK][C]
+// h1[v][o] = relu(+-W1x[o] . s_hat_k)        C/8 CTAs of 256 threads (bx = CTA index among them)
+// nrm == nullptr: vecs holds s_hat; otherwise vecs holds the raw prototypes and s_hat_k[i] = vecs[k][i] / nrm[k] is
+// formed while staging (the same division normalize_protos_kernel performs, so the values are identical).
+__device__ __forceinline__ void mlp1_body(int bx, const float* __restrict__ vecs, const float* nrm, int K, int Kb, int C,
+                                          const float* __restrict__ W1f, const float* __restrict__ W1g,
+                                          float* __restrict__ h1, float* xs) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o = blockIdx.x * 8 + warp;
+  const int o = bx * 8 + warp;
   const int per_lane = (C + 31) / 32;
   float wf[MAXC_REG], wg[MAXC_REG];
 #pragma unroll
@@ -51,7 +53,14 @@ __global__ void __launch_bounds__(256) mlp1_kernel(const float* __restrict__ s_h
   for (int k0 = 0; k0 < K; k0 += VCHUNK) {
     const int nk = min(VCHUNK, K - k0);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nk * C; idx += 256) xs[idx] = s_hat[static_cast<size_t>(k0) * C + idx];
+    if (nrm == nullptr) {
+      for (int idx = threadIdx.x; idx < nk * C; idx += 256) xs[idx] = vecs[static_cast<size_t>(k0) * C + idx];
+    } else {
+      for (int kk = 0; kk < nk; ++kk) {
+        const float nk_ = nrm[k0 + kk];
+        for (int i = threadIdx.x; i < C; i += 256) xs[kk * C + i] = vecs[static_cast<size_t>(k0 + kk) * C + i] / nk_;
+      }
+    }
     __syncthreads();
     // all staged vectors at once: VCHUNK independent accumulation chains instead of one (the loop was latency-bound)
     float acc[VCHUNK];
@@ -78,6 +87,13 @@ __global__ void __launch_bounds__(256) mlp1_kernel(const float* __restrict__ s_h
         }
     }
   }
+}
+
+__global__ void __launch_bounds__(256) mlp1_kernel(const float* __restrict__ s_hat, int K, int Kb, int C,
+                                                   const float* __restrict__ W1f, const float* __restrict__ W1g,
+                                                   float* __restrict__ h1) {
+  extern __shared__ float xs[];     // [VCHUNK][C]
+  mlp1_body(blockIdx.x, s_hat, nullptr, K, Kb, C, W1f, W1g, h1, xs);
 }
 
 // h2[v][o] = relu(W2x[o] . h1[v])
@@ -143,28 +159,32 @@ __global__ void __launch_bounds__(128) mlp3_kernel(const float* __restrict__ h2,
 
 // W1' = W1 (I - S^T S):  row o of W1' = W1[o] - sum_k (W1[o] . s_k) s_k.   grid C, 128 threads.
 // Also emits the layouts both background paths want: transposed fp32 and split bf16.
-__global__ void __launch_bounds__(128) fold_weights_kernel(const float* __restrict__ s_hat, int K, int C,
-                                                           const float* __restrict__ W1, const float* __restrict__ W2,
-                                                           float* __restrict__ W1p_t, float* __restrict__ W2_t,
-                                                           uint16_t* __restrict__ W1p_hi, uint16_t* __restrict__ W1p_lo,
-                                                           uint16_t* __restrict__ W2_hi, uint16_t* __restrict__ W2_lo,
-                                                           uint16_t* __restrict__ W1p_f16, uint16_t* __restrict__ W2_f16) {
-  __shared__ float u[SL_MAX_CLASSES];
-  const int o = blockIdx.x;
+// THREADS threads fold row o; nrm as in mlp1_body (nullptr: vecs = s_hat, else vecs = raw prototypes, divided on the fly).
+// Per-element arithmetic (lane-strided dot products, class-ordered correction) does not depend on THREADS.
+template <int THREADS>
+__device__ __forceinline__ void fold_body(int o, const float* __restrict__ vecs, const float* nrm, int K, int C,
+                                          const float* __restrict__ W1, const float* __restrict__ W2,
+                                          float* __restrict__ W1p_t, float* __restrict__ W2_t,
+                                          uint16_t* __restrict__ W1p_hi, uint16_t* __restrict__ W1p_lo,
+                                          uint16_t* __restrict__ W2_hi, uint16_t* __restrict__ W2_lo,
+                                          uint16_t* __restrict__ W1p_f16, uint16_t* __restrict__ W2_f16, float* u) {
   const float* w1 = W1 + static_cast<size_t>(o) * C;
   const float* w2 = W2 + static_cast<size_t>(o) * C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = warp; k < K; k += 4) {
-    const float* s = s_hat + static_cast<size_t>(k) * C;
+  auto sv = [&](int k, int i) {
+    const float v = vecs[static_cast<size_t>(k) * C + i];
+    return nrm == nullptr ? v : v / nrm[k];
+  };
+  for (int k = warp; k < K; k += THREADS / 32) {
     float acc = 0.f;
-    for (int i = lane; i < C; i += 32) acc = fmaf(w1[i], s[i], acc);
+    for (int i = lane; i < C; i += 32) acc = fmaf(w1[i], sv(k, i), acc);
     acc = warp_sum(acc);
     if (lane == 0) u[k] = acc;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += 128) {
+  for (int i = threadIdx.x; i < C; i += THREADS) {
     float corr = 0.f;
-    for (int k = 0; k < K; ++k) corr = fmaf(u[k], s_hat[static_cast<size_t>(k) * C + i], corr);
+    for (int k = 0; k < K; ++k) corr = fmaf(u[k], sv(k, i), corr);
     const float a = w1[i] - corr;
     const float b = w2[i];
     if (W1p_t) W1p_t[static_cast<size_t>(i) * C + o] = a;
@@ -183,6 +203,61 @@ __global__ void __launch_bounds__(128) fold_weights_kernel(const float* __restri
       W2_f16[idx] = __half_as_ushort(__float2half_rn(b));
     }
   }
+}
+
+__global__ void __launch_bounds__(128) fold_weights_kernel(const float* __restrict__ s_hat, int K, int C,
+                                                           const float* __restrict__ W1, const float* __restrict__ W2,
+                                                           float* __restrict__ W1p_t, float* __restrict__ W2_t,
+                                                           uint16_t* __restrict__ W1p_hi, uint16_t* __restrict__ W1p_lo,
+                                                           uint16_t* __restrict__ W2_hi, uint16_t* __restrict__ W2_lo,
+                                                           uint16_t* __restrict__ W1p_f16, uint16_t* __restrict__ W2_f16) {
+  __shared__ float u[SL_MAX_CLASSES];
+  fold_body<128>(blockIdx.x, s_hat, nullptr, K, C, W1, W2, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo, W1p_f16, W2_f16, u);
+}
+
+// First launch of sl_pop_prepare: prototype normalisation, MLP layer 1 and the weight fold in ONE grid.  The three were
+// separate launches (normalise -> layer 1 -> ... and, at the end of the chain, the fold, which only needs s_hat); each
+// tiny kernel costs a launch + load-latency chain of 8-13 us, so the chain was 52 us for ~K C^2 FMAs.  Here every CTA
+// derives the K norms itself (K rows of C floats from L2) and divides while it reads, CTAs [0, nb1) run layer 1,
+// CTAs [nb1, nb1 + C) fold one weight row each, and CTA 0 also writes s_hat for the later stages.
+// The norms are evaluated exactly as normalize_protos_kernel does (128 threads: thread t sums i = t, t+128, ...; a
+// butterfly per warp; red[0] + red[1] + red[2] + red[3]): one warp per row, lane l playing threads l, l+32, l+64, l+96.
+__global__ void __launch_bounds__(256) prep_stage1_kernel(const float* __restrict__ protos, int K, int Kb, int C, int nb1,
+                                                          const float* __restrict__ W1f, const float* __restrict__ W1g,
+                                                          const float* __restrict__ W2g, float* __restrict__ s_hat,
+                                                          float* __restrict__ h1, float* __restrict__ W1p_t,
+                                                          float* __restrict__ W2_t, uint16_t* __restrict__ W1p_hi,
+                                                          uint16_t* __restrict__ W1p_lo, uint16_t* __restrict__ W2_hi,
+                                                          uint16_t* __restrict__ W2_lo, uint16_t* __restrict__ W1p_f16,
+                                                          uint16_t* __restrict__ W2_f16) {
+  extern __shared__ float xs[];     // [VCHUNK][C] (layer-1 CTAs)
+  __shared__ float nrm_s[SL_MAX_CLASSES];
+  __shared__ float u[SL_MAX_CLASSES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < K; k += 8) {
+    const float* row = protos + static_cast<size_t>(k) * C;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i0 = 0; i0 < C; i0 += 128) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + 32 * q + lane;
+        if (i < C) { const float v = row[i]; acc[q] = fmaf(v, v, acc[q]); }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) nrm_s[k] = fmaxf(sqrtf(acc[0] + acc[1] + acc[2] + acc[3]), 1e-12f);
+  }
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int k = 0; k < K; ++k)
+      for (int i = threadIdx.x; i < C; i += 256)
+        s_hat[static_cast<size_t>(k) * C + i] = protos[static_cast<size_t>(k) * C + i] / nrm_s[k];
+  if (static_cast<int>(blockIdx.x) < nb1)
+    mlp1_body(blockIdx.x, protos, nrm_s, K, Kb, C, W1f, W1g, h1, xs);
+  else
+    fold_body<256>(static_cast<int>(blockIdx.x) - nb1, protos, nrm_s, K, C, W1g, W2g, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi,
+                   W2_lo, W1p_f16, W2_f16, u);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -347,14 +422,28 @@ extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const f
   SL_CHECK_ARG(n_split == 0 || n_split == 4);
   SL_CHECK_ARG((W1p_f16 != nullptr) == (W2_f16 != nullptr));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  sl::normalize_protos_kernel<<<K, 128, 0, st>>>(protos, C, s_hat);
   float* h1 = ws;                                        // [2K][C]
   float* h2 = ws + static_cast<size_t>(2) * K * C;       // [2K][C]
   const size_t xs_bytes = static_cast<size_t>(sl::VCHUNK) * C * sizeof(float);
-  sl::mlp1_kernel<<<(C + 7) / 8, 256, xs_bytes, st>>>(s_hat, K, Kb, C, W1_fg, W1_bg, h1);
-  sl::mlp2_kernel<<<(C + 7) / 8, 256, xs_bytes, st>>>(h1, K, Kb, C, W2_fg, W2_bg, h2);
+  const int nb1 = (C + 7) / 8;
+  const bool fold = W1p_t || W2_t || n_split || W1p_f16;
+  // three launches: {normalise, layer 1, fold} -> layer 2 -> layer 3 (SL_PREP_SPLIT=1: the five separate launches)
+  static int split_launches = -1;
+  if (split_launches < 0) {
+    const char* pe = getenv("SL_PREP_SPLIT");
+    split_launches = (pe != nullptr && pe[0] == '1') ? 1 : 0;
+  }
+  if (split_launches) {
+    sl::normalize_protos_kernel<<<K, 128, 0, st>>>(protos, C, s_hat);
+    sl::mlp1_kernel<<<nb1, 256, xs_bytes, st>>>(s_hat, K, Kb, C, W1_fg, W1_bg, h1);
+  } else {
+    sl::prep_stage1_kernel<<<nb1 + (fold ? C : 0), 256, xs_bytes, st>>>(protos, K, Kb, C, nb1, W1_fg, W1_bg, W2_bg, s_hat, h1,
+                                                                         W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo, W1p_f16,
+                                                                         W2_f16);
+  }
+  sl::mlp2_kernel<<<nb1, 256, xs_bytes, st>>>(h1, K, Kb, C, W2_fg, W2_bg, h2);
   sl::mlp3_kernel<<<2 * K, 128, 0, st>>>(h2, Kb, C, w3_fg, w3_bg, alpha, beta);
-  if (W1p_t || W2_t || n_split || W1p_f16)
+  if (split_launches && fold)
     sl::fold_weights_kernel<<<C, 128, 0, st>>>(s_hat, K, C, W1_bg, W2_bg, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo,
                                                W1p_f16, W2_f16);
   return SL_LAUNCH_RESULT();
