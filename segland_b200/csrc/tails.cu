@@ -8,8 +8,10 @@
 //   sl_tail_bn_relu        _ConvBnReLU's bn + relu after _ASPP.fc's convolution, networks/deeplab_pop.py:12-29,61,66;
 //                          DoubleConv's last BN + ReLU in VGGUNet.up4, networks/vggunet_pop.py:19-20,79
 //   sl_tail_concat         torch.cat([x0, x1, x2, x3], 1) of HRFPN_Seg_Decoder, networks/seghr_pop.py:23-24
-// The LayerNorm and sum kernels are HBM-bound (4 B read + 2 B written per element); the 1x1 convolution runs on
-// tcgen05 through the generic split-bf16 GEMM of pop_bwd_tc.cu (EPI_TAIL).
+// The element-wise kernels are HBM-bound (4 B read + 2 B written per element).  The 1x1 convolution runs on tcgen05:
+// by default as the single fused kernel of tail_conv.cu; this file keeps the two-kernel form (BN/ReLU/split into bf16
+// planes here + the generic split-bf16 GEMM of pop_bwd_tc.cu with its EPI_TAIL epilogue) for shapes outside the fused
+// kernel's range and for A/B runs (SL_TAIL_FUSED=0).
 #include <stdlib.h>
 #include "common.cuh"
 
