@@ -60,6 +60,8 @@ extern "C" {
 
 #define SL_MAX_CLASSES 32   /* 1 + Kb + Kn must be <= 32 (OEM: 12)                    */
 #define SL_MAX_FUSE 16      /* fusemat model count M <= 16                            */
+#define SL_MAX_WINDOWS_1D 32 /* sliding-window origins per axis                       */
+#define SL_MAX_VIEWS 8      /* flipped views per window                               */
 
 SL_API int sl_abi_version(void);
 /* Static string for any code an entry point can return (SL_E* or cudaError_t). */
@@ -201,6 +203,23 @@ SL_API int sl_pop_head_tc(const uint16_t *feat, int B, int C, int N,
  */
 SL_API int sl_views_reduce(const float *views, int V, int B, int K, int h, int w,
                     const int *flip_host, float scale, float *out, void *stream);
+
+/* Sliding-window + flip aggregation of per-crop logits at feature resolution (spec: this repo -- north_star
+ * names "engine.py's sliding-window/flip aggregation", the reference has none: engine.py:23-143 is argparse/DDP
+ * only and eval_base.py:162-170 / eval_ft.py:162-172 run whole tiles).  A tile's canvas [h,w] (feature
+ * pixels) is covered by an ny x nx grid of crops of hc x wc feature pixels with ascending origins oy_host[ny],
+ * ox_host[nx] (first = 0, last = h - hc / w - wc: the last window is pulled back to the border, consecutive windows
+ * touch or overlap); every window has V views, view v flipped by flip_host[v] (bit0 = horizontal, bit1 = vertical).
+ *   crops  entry e = (gy*nx + gx)*V + v, image b, class k at crops + e*stride_e + b*stride_b + k*hc*wc (fp32,
+ *          [hc][wc] row-major): both [E,B,K,hc,wc] (stride_e = B*K*hc*wc, stride_b = K*hc*wc) and [B,E,K,hc,wc]
+ *          (stride_b = E*K*hc*wc, stride_e = K*hc*wc) layouts work.
+ *   canvas [B,K,h,w] fp32 = sum of the un-flipped covering crops, added in entry order, divided by their number
+ *          (OVERWRITTEN); it feeds sl_upsample_argmax.  count [h,w] fp32 or NULL receives the overlap counts.
+ * Gather formulation: no atomics, fixed summation order, bit-reproducible.
+ */
+SL_API int sl_window_accumulate(const float *crops, long long stride_e, long long stride_b, int B, int K,
+                         int hc, int wc, const int *oy_host, int ny, const int *ox_host, int nx,
+                         const int *flip_host, int V, int h, int w, float *canvas, float *count, void *stream);
 
 /* ---------------------------------------------------------------------------
  * (a4/a5) F.interpolate(bilinear, align_corners=True) -> argmax -> confusion

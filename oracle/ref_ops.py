@@ -235,6 +235,28 @@ def ref_fuse(mats, n_lists=None):
 
 
 # ------------------------------------------------------------------- whole hot path
+def ref_window_accumulate(crop_logits, origins_y, origins_x, flips, canvas_hw):
+    """spec: this repo (the reference has no sliding-window inference: engine.py:23-143, eval_ft.py:162-172).
+    The usual sliding-window composition written with PyTorch primitives: crop_logits [B,E,K,hc,wc] with entry
+    e = (gy*nx + gx)*V + v; every view is un-flipped (torch.flip; bit0 = width, bit1 = height), added into the canvas
+    at its window origin in entry order, and the canvas is divided by the overlap count."""
+    B, E, K, hc, wc = crop_logits.shape
+    h, w = canvas_hw
+    canvas = torch.zeros(B, K, h, w, dtype=torch.float32)
+    count = torch.zeros(h, w, dtype=torch.float32)
+    e = 0
+    for oy in origins_y:
+        for ox in origins_x:
+            for f in flips:
+                dims = [d for d, bit in ((-1, 1), (-2, 2)) if f & bit]
+                c = crop_logits[:, e].to(torch.float32)
+                canvas[:, :, oy:oy + hc, ox:ox + wc] += torch.flip(c, dims) if dims else c
+                count[oy:oy + hc, ox:ox + wc] += 1
+                e += 1
+    assert e == E
+    return canvas / count, count
+
+
 def ref_eval_tile(features, label, base_emb, novel_emb, cls, cls_n, out_size, n_classes):
     """One eval step of eval_base.py:166-178 / eval_ft.py:166-183 after the decoder:
     head -> upsample -> argmax -> confusion.  features [1,C,h,w] fp32 (bf16-rounded values),

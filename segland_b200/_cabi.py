@@ -26,6 +26,8 @@ _SIGNATURES = {
                        + [c_int, _P, _P],
     'sl_pop_prepare_bwd': [_P, c_int, c_int, c_int] + [_P] * 21,
     'sl_views_reduce': [_P, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_float, _P, _P],
+    'sl_window_accumulate': [_P, c_longlong, c_longlong, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, POINTER(c_int), c_int,
+                             POINTER(c_int), c_int, c_int, c_int, _P, _P, _P],
     'sl_upsample_argmax': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P],
     'sl_pseudo_label': [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     'sl_confusion': [_P, _P, c_longlong, c_int, c_int, _P, _P, _P],

@@ -13,7 +13,19 @@
 
 namespace sl {
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the caller's current device, queried once per device ordinal (B200: 148; a MIG slice or another
+// sm_100 SKU has fewer).  Persistent grids and per-CTA workspaces are sized from it, never from a constant.
+inline int num_sms() {
+  static int cache[64] = {};                   // benign race: every thread stores the same value
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev];
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    cache[dev] = n;
+  }
+  return n;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

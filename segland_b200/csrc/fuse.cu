@@ -92,7 +92,7 @@ extern "C" int sl_fuse_argmax(const float* const* mats_host, int M, int K, long 
   if (label) SL_CHECK_ALIGN(label, 4);
   const long long HW4 = HW / 4;
   long long blocks = (HW4 + 255) / 256;
-  const long long cap = static_cast<long long>(sl::kNumSMs) * 8;
+  const long long cap = static_cast<long long>(sl::num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto* cmu = reinterpret_cast<unsigned long long*>(cm);

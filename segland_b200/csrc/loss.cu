@@ -220,7 +220,7 @@ extern "C" size_t sl_upsample_ce_ws_bytes(int B, int K, int w, int H, int W) {
   // per-pixel log-sum-exp (fp32) + per-CTA partial sums (double) and counts (u64) + the backward's row-reduced
   // gradients [B][K][H][w] (fp32); 16-byte aligned sections
   const size_t lse = (static_cast<size_t>(B) * H * W * sizeof(float) + 15) / 16 * 16;
-  return lse + static_cast<size_t>(sl::kNumSMs) * 8 * (sizeof(double) + sizeof(unsigned long long)) +
+  return lse + static_cast<size_t>(sl::num_sms()) * 8 * (sizeof(double) + sizeof(unsigned long long)) +
          static_cast<size_t>(B) * K * H * w * sizeof(float);
 }
 
@@ -233,10 +233,10 @@ extern "C" int sl_upsample_ce_fwd(const float* logits_lr, int B, int K, int h, i
   const size_t lse_bytes = (static_cast<size_t>(B) * H * W * sizeof(float) + 15) / 16 * 16;
   float* lse = static_cast<float*>(ws);
   double* part_sum = reinterpret_cast<double*>(static_cast<char*>(ws) + lse_bytes);
-  unsigned long long* part_cnt = reinterpret_cast<unsigned long long*>(part_sum + sl::kNumSMs * 8);
+  unsigned long long* part_cnt = reinterpret_cast<unsigned long long*>(part_sum + sl::num_sms() * 8);
   // one thread per (row, source cell), CTAs stride over (image, 8-row group, 32-cell block) items
   long long blocks = static_cast<long long>(B) * ((H + 7) / 8) * ((w + 31) / 32);
-  if (blocks > sl::kNumSMs * 8) blocks = sl::kNumSMs * 8;
+  if (blocks > sl::num_sms() * 8) blocks = sl::num_sms() * 8;
   const int grid = static_cast<int>(blocks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float sy = sl::ac_scale(h, H), sx = sl::ac_scale(w, W);
@@ -260,7 +260,7 @@ extern "C" int sl_upsample_ce_bwd(const float* logits_lr, int B, int K, int h, i
   const float* lse = static_cast<const float*>(ws);
   const size_t lse_bytes = (static_cast<size_t>(B) * H * W * sizeof(float) + 15) / 16 * 16;
   float* r = reinterpret_cast<float*>(static_cast<char*>(ws) + lse_bytes +
-                                      static_cast<size_t>(sl::kNumSMs) * 8 * (sizeof(double) + sizeof(unsigned long long)));
+                                      static_cast<size_t>(sl::num_sms()) * 8 * (sizeof(double) + sizeof(unsigned long long)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float sy = sl::ac_scale(h, H), sx = sl::ac_scale(w, W);
   SL_CHECK_ARG(B <= 65535 && (H + 7) / 8 <= 65535);

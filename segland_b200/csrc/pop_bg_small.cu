@@ -333,7 +333,7 @@ int sl_pop_bg_small_launch(const uint16_t* feat, int B, int C, int N, const uint
     if ((rc = sl::tc::make_map(&m.w2h, W2_hi, 2, dims, box))) return rc;
     if ((rc = sl::tc::make_map(&m.w2l, W2_lo, 2, dims, box))) return rc;
   }
-  const int grid = p.m_tiles < sl::kNumSMs ? p.m_tiles : sl::kNumSMs;
+  const int grid = p.m_tiles < sl::num_sms() ? p.m_tiles : sl::num_sms();
   auto launch = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);

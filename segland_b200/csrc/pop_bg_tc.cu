@@ -853,7 +853,7 @@ __global__ void transpose_protos_kernel(const float* __restrict__ s_hat, int K, 
 
 // bytes the two-slot scratch of a full grid actually touches (fp16 mode stores one array, precise mode two)
 static size_t two_slot_scratch_bytes(int C, int h_f16) {
-  return static_cast<size_t>(sl::kNumSMs) * 2 * sl::tc::BLOCK_M * C * sizeof(uint16_t) * (h_f16 ? 1 : 2);
+  return static_cast<size_t>(sl::num_sms()) * 2 * sl::tc::BLOCK_M * C * sizeof(uint16_t) * (h_f16 ? 1 : 2);
 }
 
 static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint16_t* W1p_hi, const uint16_t* W1p_lo,
@@ -909,8 +909,8 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
     const char* dbg = getenv("SL_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
-  const int grid = p.m_tiles < sl::kNumSMs ? p.m_tiles : sl::kNumSMs;
-  const size_t ws_rows = static_cast<size_t>(sl::kNumSMs) * BLOCK_M * 2;   // laid out for two slots per CTA
+  const int grid = p.m_tiles < sl::num_sms() ? p.m_tiles : sl::num_sms();
+  const size_t ws_rows = static_cast<size_t>(sl::num_sms()) * BLOCK_M * 2;   // laid out for two slots per CTA
   uint16_t* h_hi = h1_ws;
   uint16_t* h_lo = h1_ws + ws_rows * C;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -960,7 +960,7 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
       if ((rc = make_map(&m.w2h, W2_hi, 2, wdims, wbox))) return rc;
       if ((rc = make_map(&m.w2l, W2_lo, 2, wdims, wbox))) return rc;
       const int pair_tiles = (p.m_tiles + 1) / 2;
-      int pgrid = 2 * (pair_tiles < sl::kNumSMs / 2 ? pair_tiles : sl::kNumSMs / 2);
+      int pgrid = 2 * (pair_tiles < sl::num_sms() / 2 ? pair_tiles : sl::num_sms() / 2);
       const bool dedup = pe == nullptr || atoi(pe) != 1;            // SL_TC_PAIR=1: the older one-(A, B)-pair-per-pass stages
       auto kern = dedup ? bg_pair_kernel<true> : bg_pair_kernel<false>;
       cudaError_t pe2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
@@ -992,7 +992,7 @@ extern "C" size_t sl_pop_bg_tc_ws_bytes(int B, int C, int N) {
   // per CTA: two slots x 128 rows x C channels x {hi, lo} bf16, sized for a full grid of 148 CTAs (large C uses
   // one slot only, so the touched footprint stays L2-sized); then [C][12] fp32 for the transposed prototypes
   // of the fused entry point
-  return static_cast<size_t>(sl::kNumSMs) * 2 * sl::tc::BLOCK_M * C * 2 * sizeof(uint16_t) +
+  return static_cast<size_t>(sl::num_sms()) * 2 * sl::tc::BLOCK_M * C * 2 * sizeof(uint16_t) +
          static_cast<size_t>(C) * 12 * sizeof(float);
 }
 

@@ -404,7 +404,7 @@ extern "C" int sl_pop_head_bwd(const uint16_t* feat, int B, int C, int N, const 
       dfeat_proj_kernel<<<dim3((N + 1023) / 1024, (C + 63) / 64, B), 256, 0, st>>>(gp, s_hat, C, N, K, d_feat);
     return SL_LAUNCH_RESULT();
   }
-  const int px_splits = max(1, min(BNpx / 512, 2 * sl::kNumSMs / (((C + BM - 1) / BM) * ((C + BN - 1) / BN))));
+  const int px_splits = max(1, min(BNpx / 512, 2 * sl::num_sms() / (((C + BM - 1) / BM) * ((C + BN - 1) / BN))));
   // h1 = relu(W1' q)
   sgemm<true, false>(BNpx, C, C, 1, fq, ColMajor{W1p, C}, EpiRelu{h1, C}, st);
   // z2 = W2 h1 -> dz2, h2

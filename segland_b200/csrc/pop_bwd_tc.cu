@@ -422,7 +422,7 @@ static int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
   const int items = p.m_tiles * p.n_tiles * p.k_chunks;
-  tc_gemm_kernel<EPI><<<items < sl::kNumSMs ? items : sl::kNumSMs, THREADS, SMEM_BYTES, st>>>(m, p);
+  tc_gemm_kernel<EPI><<<items < sl::num_sms() ? items : sl::num_sms(), THREADS, SMEM_BYTES, st>>>(m, p);
   return SL_LAUNCH_RESULT();
 }
 
@@ -520,7 +520,7 @@ int sl_pop_bwd_tc_run(const uint16_t* feat, int B, int C, int N, const float* s_
     p.out_hi = z2h; p.out_lo = z2l; p.w3 = w3; p.g = g_logits; p.dw3 = dw3;
     p.flag_count = flag_count; p.flag_list = flag_list; p.flag_cap = flag_cap;
     SL_TRY(launch<EPI_LAYER2>(m, p, st));
-    mask_fixup_kernel<<<2 * sl::kNumSMs, 256, 0, st>>>(flag_count, flag_list, flag_cap, W2, h1h, h1l, h1l2, w3, g_logits, C, N,
+    mask_fixup_kernel<<<2 * sl::num_sms(), 256, 0, st>>>(flag_count, flag_list, flag_cap, W2, h1h, h1l, h1l2, w3, g_logits, C, N,
                                                       Ktot, bg_ch, z2h, z2l);
   }
   {  // G3: dz1 = (dz2 W2) [h1 > 0]   (B = W2^T, K-major)
@@ -540,7 +540,7 @@ int sl_pop_bwd_tc_run(const uint16_t* feat, int B, int C, int N, const float* s_
     const long long extent = flat ? px : N;
     const int kb_total = static_cast<int>((extent + BLOCK_K - 1) / BLOCK_K);
     const int units = flat ? 1 : B;
-    int want = 2 * sl::kNumSMs / (mt_c * p.n_tiles * units);          // chunks per image (or in total when flat)
+    int want = 2 * sl::num_sms() / (mt_c * p.n_tiles * units);          // chunks per image (or in total when flat)
     if (want < 1) want = 1;
     if (want > kb_total) want = kb_total;
     p.chunk_kb = (kb_total + want - 1) / want;

@@ -173,7 +173,7 @@ static int launch_fg(const CUtensorMap& map_x, int B, int C, int N, const float*
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const long long items = static_cast<long long>(B) * ((N + FG_PX - 1) / FG_PX);
-  const int grid = static_cast<int>(items < kNumSMs ? items : kNumSMs);
+  const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
   kern<<<grid, FG_THREADS, smem, st>>>(map_x, B, C, N, s_hat, alpha, beta, K, k_base, logits, Ktot, map);
   return SL_LAUNCH_RESULT();
 }

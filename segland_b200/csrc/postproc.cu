@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(256) views_reduce_vec4_kernel(const float* __r
 
 static inline int grid_for(long long work_items, int per_sm) {
   long long blocks = (work_items + 255) / 256;
-  const long long cap = static_cast<long long>(kNumSMs) * per_sm;
+  const long long cap = static_cast<long long>(num_sms()) * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);

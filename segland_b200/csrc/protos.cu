@@ -196,7 +196,7 @@ extern "C" int sl_map_proto(const uint16_t* feat, const float* mask, int B, int 
                                                         mask_lr_ws, partial, n_chunks);
   // enough pixel splits to put ~48 warps on every SM, each at least 2048 pixels long
   const long long warps = static_cast<long long>(B) * ((C + sl::MAP_CH - 1) / sl::MAP_CH);
-  long long splits = (static_cast<long long>(sl::kNumSMs) * 48 + warps - 1) / warps;
+  long long splits = (static_cast<long long>(sl::num_sms()) * 48 + warps - 1) / warps;
   if (splits > sl::MAP_MAX_SPLITS) splits = sl::MAP_MAX_SPLITS;
   if (splits > (N + 2047) / 2048) splits = (N + 2047) / 2048;
   if (splits < 1) splits = 1;

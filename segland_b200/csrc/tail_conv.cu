@@ -344,7 +344,7 @@ int sl_tail_conv_fused_run(const float* x, int B, int Cin, int N, const float* b
   cudaError_t e = cudaFuncSetAttribute(tail_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (static_cast<long long>(p.m_tiles) * p.n_tiles >= (1ll << 31)) return SL_EINVAL;
-  const int grid = p.m_tiles < sl::kNumSMs ? p.m_tiles : sl::kNumSMs;
+  const int grid = p.m_tiles < sl::num_sms() ? p.m_tiles : sl::num_sms();
   tail_conv_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mh, ml, p);
   return SL_LAUNCH_RESULT();
 }

@@ -247,7 +247,7 @@ extern "C" int sl_tail_sum(const float* const* maps_host, int M, long long n, ui
   }
   const long long n8 = n / 8;
   const long long want = (n8 + 255) / 256;
-  const int grid = static_cast<int>(want < 8ll * sl::kNumSMs ? want : 8ll * sl::kNumSMs);
+  const int grid = static_cast<int>(want < 8ll * sl::num_sms() ? want : 8ll * sl::num_sms());
   sl::tails::sum_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ptrs, M, n8, feat_out);
   return SL_LAUNCH_RESULT();
 }
@@ -296,7 +296,7 @@ extern "C" int sl_tail_bn_relu_conv(const float* x, int B, int Cin, int N, const
   uint16_t* lo = hi + plane;
   const long long total8 = plane / 8;
   const long long want = (total8 + 255) / 256;
-  const int grid = static_cast<int>(want < 16ll * sl::kNumSMs ? want : 16ll * sl::kNumSMs);
+  const int grid = static_cast<int>(want < 16ll * sl::num_sms() ? want : 16ll * sl::num_sms());
   sl::tails::bn_relu_split_kernel<true><<<grid, 256, 0, st>>>(x, Cin, N / 8, total8, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
                                                         relu, hi, lo);
   const int rc = SL_LAUNCH_RESULT();
@@ -313,7 +313,7 @@ extern "C" int sl_tail_bn_relu(const float* x, int B, int C, int N, const float*
   SL_CHECK_ALIGN(x, 16); SL_CHECK_ALIGN(feat_out, 16);
   const long long total8 = static_cast<long long>(B) * C * N / 8;
   const long long want = (total8 + 255) / 256;
-  const int grid = static_cast<int>(want < 16ll * sl::kNumSMs ? want : 16ll * sl::kNumSMs);
+  const int grid = static_cast<int>(want < 16ll * sl::num_sms() ? want : 16ll * sl::num_sms());
   sl::tails::bn_relu_split_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, C, N / 8, total8, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, relu, feat_out, nullptr);
   return SL_LAUNCH_RESULT();
@@ -334,7 +334,7 @@ extern "C" int sl_tail_concat(const float* const* maps_host, const int* channels
   for (int m = 0; m < M; ++m) {
     const long long img8 = static_cast<long long>(channels_host[m]) * N / 8, total8 = img8 * B;
     const long long want = (total8 + 255) / 256;
-    const int grid = static_cast<int>(want < 16ll * sl::kNumSMs ? want : 16ll * sl::kNumSMs);
+    const int grid = static_cast<int>(want < 16ll * sl::num_sms() ? want : 16ll * sl::num_sms());
     sl::tails::concat_cast_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(maps_host[m], img8, total8,
                                                                                        c_total * N / 8, c_off * N / 8, feat_out);
     const int rc = SL_LAUNCH_RESULT();

@@ -1,0 +1,155 @@
+// sl_window_accumulate: sliding-window / flip aggregation of per-crop logits at feature resolution.
+//
+// spec: this repo.  BASELINE.json's north_star names "engine.py's sliding-window/flip aggregation", but the reference
+// has none: engine.py:23-143 is argparse + DDP helpers and eval_base.py:162-170 / eval_ft.py:162-172 run one whole
+// tile per forward.  The operator is therefore defined here, as the composition every sliding-window
+// evaluator uses (crop grid with a last window pulled back to the border, overlap-count normalisation, flipped views
+// un-flipped before the sum), and tested against that composition written with PyTorch primitives.
+//
+//   canvas[b,k,y,x] = ( sum over entries e = (gy, gx, v) covering (y, x), in index order,
+//                        of unflip_v(crops[e,b,k])[y - oy[gy], x - ox[gx]] ) / count[y,x]
+//
+// It is a gather: every crop element is read exactly once and every canvas element written exactly once, there are
+// no atomics and the summation order is fixed, so the result is bit-reproducible and equal, bit for bit, to
+// `canvas[..., oy:oy+hc, ox:ox+wc] += unflip(crop)` applied entry by entry followed by `canvas / count`.
+// HBM-bound: algorithmic bytes = E*B*K*hc*wc*4 read + B*K*h*w*4 written.
+#include "common.cuh"
+
+namespace sl {
+
+struct WinPlan {
+  int ny, nx, V;
+  int oy[SL_MAX_WINDOWS_1D];
+  int ox[SL_MAX_WINDOWS_1D];
+  int flip[SL_MAX_VIEWS];
+};
+
+// windows whose origin o satisfies o <= p < o + len: origins ascend, so the range is contiguous
+__device__ __forceinline__ void cover_range(const int* o, int n, int len, int p, int& lo, int& hi) {
+  lo = n; hi = -1;
+  for (int g = 0; g < n; ++g)
+    if (o[g] <= p && p < o[g] + len) { if (g < lo) lo = g; hi = g; }
+}
+
+// One thread = 4 consecutive canvas columns of one row, for PLANES consecutive (b, k) planes: the covering
+// ranges are worked out once per thread.  VEC: ox % 4 == 0, wc % 4 == 0, w % 4 == 0 and 16-byte aligned pointers.
+template <bool VEC>
+__global__ void __launch_bounds__(256) window_accumulate_kernel(
+    const float* __restrict__ crops, long long stride_e, long long stride_b, int B, int K, int hc, int wc,
+    const __grid_constant__ WinPlan pl, int h, int w, int planes_per_thread, float* __restrict__ canvas,
+    float* __restrict__ count) {
+  const int wq = (w + 3) >> 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= wq * h) return;
+  const int y = q / wq, x0 = (q - y * wq) * 4;
+  int gy_lo, gy_hi, gx_lo[4], gx_hi[4];
+  cover_range(pl.oy, pl.ny, hc, y, gy_lo, gy_hi);
+  if (VEC) {
+    cover_range(pl.ox, pl.nx, wc, x0, gx_lo[0], gx_hi[0]);       // origins and widths are multiples of 4: one range
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cover_range(pl.ox, pl.nx, wc, min(x0 + j, w - 1), gx_lo[j], gx_hi[j]);
+  }
+  const int ny_cov = max(0, gy_hi - gy_lo + 1);
+  float cnt[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cnt[j] = static_cast<float>(ny_cov * max(0, gx_hi[VEC ? 0 : j] - gx_lo[VEC ? 0 : j] + 1) * pl.V);
+  const int total_planes = B * K;
+  const int p_begin = blockIdx.y * planes_per_thread, p_end = min(total_planes, p_begin + planes_per_thread);
+  if (count != nullptr && p_begin == 0) {
+    if (VEC) *reinterpret_cast<float4*>(count + static_cast<size_t>(y) * w + x0) = make_float4(cnt[0], cnt[1], cnt[2], cnt[3]);
+    else
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (x0 + j < w) count[static_cast<size_t>(y) * w + x0 + j] = cnt[j];
+  }
+  const size_t chw = static_cast<size_t>(hc) * wc;
+  for (int p = p_begin; p < p_end; ++p) {
+    const int b = p / K, k = p - b * K;
+    const float* plane0 = crops + static_cast<size_t>(b) * stride_b + static_cast<size_t>(k) * chw;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+      const int ry = y - pl.oy[gy];
+      if (VEC) {
+        for (int gx = gx_lo[0]; gx <= gx_hi[0]; ++gx) {
+          const int rx = x0 - pl.ox[gx];
+          const float* ent = plane0 + static_cast<size_t>((gy * pl.nx + gx) * pl.V) * stride_e;
+          for (int v = 0; v < pl.V; ++v, ent += stride_e) {
+            const int f = pl.flip[v];
+            const int ys = (f & 2) ? hc - 1 - ry : ry;
+            const int xs = (f & 1) ? wc - 4 - rx : rx;
+            const float4 t = ld_stream_f4(ent + static_cast<size_t>(ys) * wc + xs);
+            acc[0] += (f & 1) ? t.w : t.x; acc[1] += (f & 1) ? t.z : t.y;
+            acc[2] += (f & 1) ? t.y : t.z; acc[3] += (f & 1) ? t.x : t.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (x0 + j >= w) continue;
+          for (int gx = gx_lo[j]; gx <= gx_hi[j]; ++gx) {
+            const int rx = x0 + j - pl.ox[gx];
+            const float* ent = plane0 + static_cast<size_t>((gy * pl.nx + gx) * pl.V) * stride_e;
+            for (int v = 0; v < pl.V; ++v, ent += stride_e) {
+              const int f = pl.flip[v];
+              const int ys = (f & 2) ? hc - 1 - ry : ry;
+              const int xs = (f & 1) ? wc - 1 - rx : rx;
+              acc[j] += __ldg(ent + static_cast<size_t>(ys) * wc + xs);
+            }
+          }
+        }
+      }
+    }
+    float* dst = canvas + (static_cast<size_t>(p) * h + y) * w + x0;
+    if (VEC) {
+      __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0] / cnt[0], acc[1] / cnt[1], acc[2] / cnt[2], acc[3] / cnt[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (x0 + j < w) dst[j] = acc[j] / cnt[j];
+    }
+  }
+}
+
+}  // namespace sl
+
+extern "C" int sl_window_accumulate(const float* crops, long long stride_e, long long stride_b, int B, int K, int hc,
+                                    int wc, const int* oy_host, int ny, const int* ox_host, int nx,
+                                    const int* flip_host, int V, int h, int w, float* canvas, float* count,
+                                    void* stream) {
+  SL_CHECK_PTR(crops); SL_CHECK_PTR(canvas); SL_CHECK_PTR(oy_host); SL_CHECK_PTR(ox_host); SL_CHECK_PTR(flip_host);
+  SL_CHECK_ARG(B >= 1 && K >= 1 && hc >= 1 && wc >= 1 && h >= hc && w >= wc);
+  SL_CHECK_ARG(ny >= 1 && ny <= SL_MAX_WINDOWS_1D && nx >= 1 && nx <= SL_MAX_WINDOWS_1D && V >= 1 && V <= SL_MAX_VIEWS);
+  SL_CHECK_ARG(stride_e >= 0 && stride_b >= 0 && static_cast<long long>(B) * K < (1ll << 24));
+  sl::WinPlan pl;
+  pl.ny = ny; pl.nx = nx; pl.V = V;
+  bool vec = (w % 4 == 0) && (wc % 4 == 0) && (stride_e % 4 == 0) && (stride_b % 4 == 0) &&
+             (static_cast<long long>(hc) * wc % 4 == 0) &&
+             reinterpret_cast<uintptr_t>(crops) % 16 == 0 && reinterpret_cast<uintptr_t>(canvas) % 16 == 0 &&
+             (count == nullptr || reinterpret_cast<uintptr_t>(count) % 16 == 0);
+  // every canvas row / column must be covered: origins ascend from 0, consecutive windows touch or overlap, and the
+  // last one ends at the border (the usual "pull the last window back" plan)
+  for (int g = 0; g < SL_MAX_WINDOWS_1D; ++g) { pl.oy[g] = g < ny ? oy_host[g] : 0; pl.ox[g] = g < nx ? ox_host[g] : 0; }
+  SL_CHECK_ARG(pl.oy[0] == 0 && pl.ox[0] == 0 && pl.oy[ny - 1] + hc == h && pl.ox[nx - 1] + wc == w);
+  for (int g = 1; g < ny; ++g) SL_CHECK_ARG(pl.oy[g] >= pl.oy[g - 1] && pl.oy[g] <= pl.oy[g - 1] + hc);
+  for (int g = 1; g < nx; ++g) SL_CHECK_ARG(pl.ox[g] >= pl.ox[g - 1] && pl.ox[g] <= pl.ox[g - 1] + wc);
+  for (int g = 0; g < nx; ++g) vec = vec && (pl.ox[g] % 4 == 0);
+  for (int v = 0; v < SL_MAX_VIEWS; ++v) {
+    pl.flip[v] = v < V ? flip_host[v] : 0;
+    SL_CHECK_ARG(pl.flip[v] >= 0 && pl.flip[v] <= 3);
+  }
+  const long long quads = static_cast<long long>(h) * ((w + 3) / 4);
+  SL_CHECK_ARG(quads < (1ll << 31));
+  const int planes = B * K;
+  // enough CTAs to fill the machine several times over, as few plane groups as that allows (the covering ranges are
+  // computed once per thread and reused for all of its planes)
+  const long long bx = (quads + 255) / 256;
+  int groups = static_cast<int>((8ll * sl::num_sms() + bx - 1) / bx);
+  if (groups < 1) groups = 1;
+  if (groups > planes) groups = planes;
+  if (groups > 65535) groups = 65535;
+  const int ppt = (planes + groups - 1) / groups;
+  const dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>((planes + ppt - 1) / ppt));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec) sl::window_accumulate_kernel<true><<<grid, 256, 0, st>>>(crops, stride_e, stride_b, B, K, hc, wc, pl, h, w, ppt, canvas, count);
+  else sl::window_accumulate_kernel<false><<<grid, 256, 0, st>>>(crops, stride_e, stride_b, B, K, hc, wc, pl, h, w, ppt, canvas, count);
+  return SL_LAUNCH_RESULT();
+}

@@ -386,6 +386,100 @@ def aggregate_views(views, flips, scale=None):
     return out
 
 
+class WindowPlan:
+    """Sliding-window crop grid over one tile (spec: this repo; north_star names "engine.py's sliding-window/flip
+    aggregation" but the reference evaluates whole tiles, engine.py:23-143, eval_ft.py:162-172).
+
+    tile_hw, crop_hw and stride_hw are in IMAGE pixels, model_stride is the network's output stride (8 for the
+    ResNet models, 4 for Swin/ConvNeXt/LSK/HRNet).  Window origins follow the usual rule: a regular
+    grid of step `stride_hw`, the last window pulled back so that it ends at the tile border (so the last step can
+    be ragged).  Everything must be a multiple of model_stride so that crops stitch on the feature grid."""
+
+    def __init__(self, tile_hw, crop_hw, stride_hw=None, model_stride=8):
+        th, tw = int(tile_hw[0]), int(tile_hw[1])
+        ch, cw = int(crop_hw[0]), int(crop_hw[1])
+        sh, sw = (ch, cw) if stride_hw is None else (int(stride_hw[0]), int(stride_hw[1]))
+        s = int(model_stride)
+        if min(th, tw, ch, cw, sh, sw, s) < 1 or ch > th or cw > tw:
+            raise ValueError('WindowPlan: sizes must be positive and the crop no larger than the tile')
+        if sh > ch or sw > cw:
+            raise ValueError('WindowPlan: a stride larger than the crop leaves pixels uncovered')
+        for v in (th, tw, ch, cw, sh, sw):
+            if v % s:
+                raise ValueError(f'WindowPlan: tile, crop and stride must be multiples of the model stride {s}')
+        self.tile_hw, self.crop_hw, self.stride_hw, self.model_stride = (th, tw), (ch, cw), (sh, sw), s
+        self.origins_y = self._origins(th, ch, sh)
+        self.origins_x = self._origins(tw, cw, sw)
+        if max(len(self.origins_y), len(self.origins_x)) > 32:
+            raise ValueError('WindowPlan: more than 32 windows per axis')
+
+    @staticmethod
+    def _origins(size, crop, stride):
+        n = max(size - crop + stride - 1, 0) // stride + 1
+        return [min(i * stride, size - crop) for i in range(n)]
+
+    @property
+    def n_windows(self):
+        return len(self.origins_y) * len(self.origins_x)
+
+    def windows(self):
+        """(y, x) image-pixel origin of every window, row-major: the entry order window_accumulate expects."""
+        return [(y, x) for y in self.origins_y for x in self.origins_x]
+
+    @property
+    def canvas_hw(self):
+        return (self.tile_hw[0] // self.model_stride, self.tile_hw[1] // self.model_stride)
+
+    @property
+    def crop_lr_hw(self):
+        return (self.crop_hw[0] // self.model_stride, self.crop_hw[1] // self.model_stride)
+
+    def crop(self, images, flips=(0,)):
+        """images [B,...,H,W] -> [B, n_windows*len(flips), ..., ch, cw]: the crops (and their flipped views) in entry
+        order, i.e. what a backbone is fed (plain slicing/flip; host-side plumbing, any device)."""
+        out = []
+        for (y, x) in self.windows():
+            c = images[..., y:y + self.crop_hw[0], x:x + self.crop_hw[1]]
+            for f in flips:
+                dims = [d for d, bit in ((-1, 1), (-2, 2)) if f & bit]
+                out.append(torch.flip(c, dims) if dims else c)
+        return torch.stack(out, dim=1)
+
+
+def window_accumulate(crop_logits, plan, flips=(0,), layout='bekhw', want_count=False, out=None):
+    """Stitch per-crop low-res logits into one canvas per tile (spec: this repo, see WindowPlan): the un-flipped
+    crops are summed at feature resolution in entry order and divided by the overlap count -- the result is bit-equal
+    to `canvas[..., y:y+hc, x:x+wc] += unflip(crop)` per entry followed by `canvas / count`.
+    crop_logits fp32 CUDA, layout 'bekhw' = [B,E,K,hc,wc] (a batch of tiles, each with its E = n_windows*len(flips)
+    crops, entry e = window*len(flips) + view) or 'ebkhw' = [E,B,K,hc,wc].  Returns canvas [B,K,h,w] fp32 (and the
+    count plane [h,w] when want_count); feed it to upsample_argmax."""
+    crop_logits = _cuda(crop_logits, torch.float32)
+    if crop_logits.dim() != 5 or layout not in ('bekhw', 'ebkhw'):
+        raise ValueError("crop_logits must be 5-D with layout 'bekhw' or 'ebkhw'")
+    if layout == 'bekhw':
+        B, E, K, hc, wc = crop_logits.shape
+        stride_b, stride_e = E * K * hc * wc, K * hc * wc
+    else:
+        E, B, K, hc, wc = crop_logits.shape
+        stride_e, stride_b = B * K * hc * wc, K * hc * wc
+    V = len(flips)
+    if E != plan.n_windows * V or (hc, wc) != plan.crop_lr_hw:
+        raise ValueError(f'expected {plan.n_windows * V} entries of {plan.crop_lr_hw} feature pixels, got {E} of {(hc, wc)}')
+    h, w = plan.canvas_hw
+    s = plan.model_stride
+    dev = crop_logits.device
+    if out is None:
+        out = torch.empty(B, K, h, w, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (B, K, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError(f'out must be a contiguous fp32 [{B},{K},{h},{w}] tensor')
+    count = torch.empty(h, w, dtype=torch.float32, device=dev) if want_count else None
+    oy, ox = [y // s for y in plan.origins_y], [x // s for x in plan.origins_x]
+    with torch.cuda.device(dev):
+        call('sl_window_accumulate', ptr(crop_logits), stride_e, stride_b, B, K, hc, wc, int_array(oy), len(oy),
+             int_array(ox), len(ox), int_array(flips), V, h, w, ptr(out), ptr(count), _stream())
+    return (out, count) if want_count else out
+
+
 # ================================================================== dense post-processing
 def upsample_argmax(logits, size, label=None, cm=None, ignore_label=IGNORE_LABEL, want_pred=True,
                     want_conf=False, want_probs=False, want_logits=False):
