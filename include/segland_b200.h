@@ -34,13 +34,18 @@ extern "C" {
 
 #define SL_ABI_VERSION 1
 
-/* Environment switches read by the library (debugging and A/B measurements only; defaults are the fast paths):
+/* Environment switches read by the library (debugging and A/B measurements only; defaults are the fast paths).
+ * They are read ONCE per process (no getenv on the launch path); sl_env_reload() re-reads them.
+ *   SL_POST_PRUNE=0     sl_upsample_argmax's prediction-only path on the row-cached kernel instead of the per-cell
+ *                       class-pruning kernel (identical results)
  *   SL_TC_PAIR=0        background MLP on the single-CTA tcgen05 kernel instead of the cta_group::2 pair kernel
  *   SL_TC_PAIR=1        pair kernel with one (A, B) operand pair per MMA pass and pipeline stage (the schedule before the
  *                       de-duplicated stages; 4-10 % slower)
  *   SL_TC_SMALL=0       C <= 128: streaming kernel instead of the weights-resident narrow-head kernel
  *   SL_PREP_SPLIT=1     sl_pop_prepare as five separate launches instead of three
- *   SL_POST_FUSED_CM=1  sl_upsample_argmax counts the confusion matrix inside the interpolation kernel
+ *   SL_POST_FUSED_CM=1/0 sl_upsample_argmax counts the confusion matrix inside the interpolation kernel (1) or in a
+ *                       second launch over (label, pred) (0); default: inside for the pruning kernel, second launch for
+ *                       the row-cached kernel
  *   SL_TC_DEBUG=<bits>  knock-outs inside the single-CTA kernel (timing experiments, results INVALID)
  *   SL_TAIL_FUSED=0     sl_tail_bn_relu_conv as two kernels (bf16 hi/lo planes in the workspace + generic GEMM)
  *   SL_SMALL_DBG=<ptr>  device pointer (decimal) of a 64x16 int64 buffer receiving per-tile cycle stamps of CTA 0
@@ -68,6 +73,8 @@ SL_API int sl_abi_version(void);
 SL_API const char *sl_error_string(int code);
 /* 0 iff the current device is compute capability 10.x; SL_EUNSUPPORTED otherwise. */
 SL_API int sl_check_device(void);
+/* Re-read the SL_* environment switches (they are otherwise cached at first use). */
+SL_API int sl_env_reload(void);
 
 /* ---------------------------------------------------------------------------
  * (a1/a2) POP head -- GFSS_Model.orthogonal_decompose + classifier/classifier_n

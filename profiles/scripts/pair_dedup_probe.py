@@ -31,7 +31,7 @@ for C, T, hw, prec in ((512, 32, 128, 'precise'), (512, 32, 128, 'balanced'), (1
     head = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n, bg_mode='tc', tc_precision=prec)
     outs, times = {}, {}
     for mode in ('1', '2'):
-        os.environ['SL_TC_PAIR'] = mode
+        os.environ['SL_TC_PAIR'] = mode; __import__('segland_b200._cabi', fromlist=['x']).lib().sl_env_reload()
         lg = torch.empty(T, 12, hw, hw, device='cuda')
         head(f, out=lg)
         torch.cuda.synchronize()
@@ -40,4 +40,4 @@ for C, T, hw, prec in ((512, 32, 128, 'precise'), (512, 32, 128, 'balanced'), (1
     d = (outs['1'] - outs['2']).abs().max().item() / outs['1'].abs().max().item()
     print(f'C={C:4d} T={T:3d} hw={hw} {prec:9s} rel diff {d:.2e}   pair {times["1"]:.4f} ms   dedup {times["2"]:.4f} ms   '
           f'({times["1"] / times["2"]:.3f}x)')
-os.environ.pop('SL_TC_PAIR', None)
+os.environ.pop('SL_TC_PAIR', None); __import__('segland_b200._cabi', fromlist=['x']).lib().sl_env_reload()

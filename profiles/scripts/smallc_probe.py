@@ -11,7 +11,7 @@ for C in (96, 192):
         for dbg in ('0', '1', '2', '3', '4', '7'):
             if pair == '1' and dbg != '0':
                 continue
-            os.environ['SL_TC_PAIR'] = pair; os.environ['SL_TC_DEBUG'] = dbg
+            os.environ['SL_TC_PAIR'] = pair; os.environ['SL_TC_DEBUG'] = dbg; __import__('segland_b200._cabi', fromlist=['x']).lib().sl_env_reload()
             for _ in range(3): head.bg_tc(feats, lg)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)

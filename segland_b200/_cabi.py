@@ -16,6 +16,7 @@ _SIGNATURES = {
     # name: argtypes (restype is c_int unless noted)
     'sl_abi_version': [],
     'sl_check_device': [],
+    'sl_env_reload': [],
     'sl_pop_prepare': [_P, c_int, c_int, c_int] + [_P] * 19,
     'sl_pop_fg_lowres': [_P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int, POINTER(c_int), _P],
     'sl_pop_bg_simt': [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P],
@@ -85,6 +86,17 @@ def lib():
             raise ImportError(f'{LIB_PATH}: ABI version {handle.sl_abi_version()} != 1; rebuild')
         _lib = handle
     return _lib
+
+
+def set_env(**switches):
+    """Set (value) or clear (None) SL_* environment switches and make the library re-read them: the library caches
+    its switches at first use, so changing os.environ alone has no effect on a loaded library."""
+    for k, v in switches.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = str(v)
+    lib().sl_env_reload()
 
 
 def exported_names():

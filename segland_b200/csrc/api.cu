@@ -1,6 +1,35 @@
 // Library-level entry points: ABI version, error strings, device check.
 #include "common.cuh"
 
+namespace sl {
+static Env g_env;
+static bool g_env_loaded = false;
+static void load_env() {
+  auto geti = [](const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v != nullptr && *v != '\0' ? atoi(v) : dflt;
+  };
+  Env e;
+  e.tc_pair = geti("SL_TC_PAIR", -1);
+  e.tc_small = geti("SL_TC_SMALL", -1);
+  e.tc_debug = geti("SL_TC_DEBUG", 0);
+  e.prep_split = geti("SL_PREP_SPLIT", 0);
+  e.post_fused_cm = geti("SL_POST_FUSED_CM", -1);
+  e.post_prune = geti("SL_POST_PRUNE", 1);
+  e.tail_fused = geti("SL_TAIL_FUSED", 1);
+  const char* d = getenv("SL_SMALL_DBG");
+  e.small_dbg = d != nullptr ? static_cast<long long>(strtoull(d, nullptr, 10)) : 0;
+  g_env = e;
+  g_env_loaded = true;
+}
+const Env& env() {
+  if (!g_env_loaded) load_env();          // benign race: every thread computes the same values
+  return g_env;
+}
+}  // namespace sl
+
+extern "C" int sl_env_reload(void) { sl::load_env(); return SL_OK; }
+
 extern "C" int sl_abi_version(void) { return SL_ABI_VERSION; }
 
 extern "C" const char* sl_error_string(int code) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "../../include/segland_b200.h"
 
 #define SL_CHECK_PTR(p) do { if ((p) == nullptr) return SL_ENULL; } while (0)
@@ -26,6 +27,20 @@ inline int num_sms() {
   }
   return n;
 }
+
+// Environment switches (A/B measurements and debugging only; see include/segland_b200.h).  They are read once per
+// process -- a launch never calls getenv -- and again only when the caller asks (sl_env_reload).
+struct Env {
+  int tc_pair;          // SL_TC_PAIR       (-1 = unset)
+  int tc_small;         // SL_TC_SMALL      (-1 = unset)
+  int tc_debug;         // SL_TC_DEBUG      (0)
+  int prep_split;       // SL_PREP_SPLIT    (0)
+  int post_fused_cm;    // SL_POST_FUSED_CM (-1 = unset)
+  int post_prune;       // SL_POST_PRUNE    (1)
+  int tail_fused;       // SL_TAIL_FUSED    (1)
+  long long small_dbg;  // SL_SMALL_DBG     (0)
+};
+const Env& env();       // api.cu
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -304,10 +304,7 @@ int sl_pop_bg_small_launch(const uint16_t* feat, int B, int C, int N, const uint
   p.tiles_per_image = (N + BLOCK_M - 1) / BLOCK_M;
   p.m_tiles = B * p.tiles_per_image;
   p.N = N; p.Ktot = Ktot; p.ch = ch; p.w3 = w3_bg; p.logits = logits;
-  {
-    const char* de = getenv("SL_SMALL_DBG");                   // device pointer (decimal) of a 64 x 16 int64 buffer
-    p.dbg = de ? reinterpret_cast<long long*>(strtoull(de, nullptr, 10)) : nullptr;
-  }
+  p.dbg = reinterpret_cast<long long*>(sl::env().small_dbg);   // SL_SMALL_DBG: device pointer of a 64 x 16 int64 buffer
   const size_t w_bytes = (static_cast<size_t>(4) * p.kblocks * C * 128 + 1023) / 1024 * 1024;
   const size_t h_bytes = 0;                                             // the hidden tile lives in tensor memory
   const size_t x_slot = static_cast<size_t>(p.kblocks) * KB_TILE;

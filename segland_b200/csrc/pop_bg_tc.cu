@@ -881,8 +881,7 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
 
   // narrow heads (Swin: C = 96 / 128): weights-resident kernel, hidden tile in shared memory (pop_bg_small.cu)
   if (K == 0 && precision == SL_TC_PRECISE && C <= 128 && C % 32 == 0) {
-    const char* se = getenv("SL_TC_SMALL");
-    if (se == nullptr || atoi(se) != 0)
+    if (sl::env().tc_small != 0)
       return sl_pop_bg_small_launch(feat, B, C, N, W1p_hi, W1p_lo, W2_hi, W2_lo, w3_bg, logits, Ktot, ch,
                                     static_cast<cudaStream_t>(stream));
   }
@@ -905,10 +904,7 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
   // one-tile look-ahead needs two scratch slots per CTA; use it while both slots of the whole grid stay well
   // inside L2 (measured: 38.8 MB stays resident, 77.6 MB spills 0.9 GB per 32-tile step to HBM)
   p.lookahead = two_slot_scratch_bytes(C, p.h_f16) <= (40u << 20) ? 1 : 0;
-  {
-    const char* dbg = getenv("SL_TC_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
-  }
+  p.debug = sl::env().tc_debug;
   const int grid = p.m_tiles < sl::num_sms() ? p.m_tiles : sl::num_sms();
   const size_t ws_rows = static_cast<size_t>(sl::num_sms()) * BLOCK_M * 2;   // laid out for two slots per CTA
   uint16_t* h_hi = h1_ws;
@@ -949,8 +945,8 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
   }
   // cta_group::2 variant for the background-only launch: a CTA pair shares every weight tile
   {
-    const char* pe = getenv("SL_TC_PAIR");
-    const bool use_pair = KQ == 0 && p.m_tiles >= 2 && (pe == nullptr || atoi(pe) != 0);
+    const int pe = sl::env().tc_pair;
+    const bool use_pair = KQ == 0 && p.m_tiles >= 2 && pe != 0;
     if (use_pair) {
       // each CTA loads half of B: box rows = NT/2
       cuuint64_t wdims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(C)};
@@ -961,7 +957,7 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
       if ((rc = make_map(&m.w2l, W2_lo, 2, wdims, wbox))) return rc;
       const int pair_tiles = (p.m_tiles + 1) / 2;
       int pgrid = 2 * (pair_tiles < sl::num_sms() / 2 ? pair_tiles : sl::num_sms() / 2);
-      const bool dedup = pe == nullptr || atoi(pe) != 1;            // SL_TC_PAIR=1: the older one-(A, B)-pair-per-pass stages
+      const bool dedup = pe != 1;                                    // SL_TC_PAIR=1: the older one-(A, B)-pair-per-pass stages
       auto kern = dedup ? bg_pair_kernel<true> : bg_pair_kernel<false>;
       cudaError_t pe2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
       if (pe2 != cudaSuccess) return static_cast<int>(pe2);

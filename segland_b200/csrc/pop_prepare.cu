@@ -428,12 +428,7 @@ extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const f
   const int nb1 = (C + 7) / 8;
   const bool fold = W1p_t || W2_t || n_split || W1p_f16;
   // three launches: {normalise, layer 1, fold} -> layer 2 -> layer 3 (SL_PREP_SPLIT=1: the five separate launches)
-  static int split_launches = -1;
-  if (split_launches < 0) {
-    const char* pe = getenv("SL_PREP_SPLIT");
-    split_launches = (pe != nullptr && pe[0] == '1') ? 1 : 0;
-  }
-  if (split_launches) {
+  if (sl::env().prep_split == 1) {
     sl::normalize_protos_kernel<<<K, 128, 0, st>>>(protos, C, s_hat);
     sl::mlp1_kernel<<<nb1, 256, xs_bytes, st>>>(s_hat, K, Kb, C, W1_fg, W1_bg, h1);
   } else {
@@ -443,7 +438,7 @@ extern "C" int sl_pop_prepare(const float* protos, int K, int Kb, int C, const f
   }
   sl::mlp2_kernel<<<nb1, 256, xs_bytes, st>>>(h1, K, Kb, C, W2_fg, W2_bg, h2);
   sl::mlp3_kernel<<<2 * K, 128, 0, st>>>(h2, Kb, C, w3_fg, w3_bg, alpha, beta);
-  if (split_launches && fold)
+  if (sl::env().prep_split == 1 && fold)
     sl::fold_weights_kernel<<<C, 128, 0, st>>>(s_hat, K, C, W1_bg, W2_bg, W1p_t, W2_t, W1p_hi, W1p_lo, W2_hi, W2_lo,
                                                W1p_f16, W2_f16);
   return SL_LAUNCH_RESULT();

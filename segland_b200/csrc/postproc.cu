@@ -727,6 +727,10 @@ __global__ void __launch_bounds__(256) views_reduce_vec4_kernel(const float* __r
   }
 }
 
+int launch_upsample_prune(const float* logits_lr, int B, int K, int h, int w, int H, int W, float sy, float sx,
+                          const uint8_t* label, int ignore_label, uint8_t* pred, unsigned long long* cm,
+                          cudaStream_t st);                      // post_prune.cu
+
 static inline int grid_for(long long work_items, int per_sm) {
   long long blocks = (work_items + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * per_sm;
@@ -766,8 +770,20 @@ extern "C" int sl_upsample_argmax(const float* logits_lr, int B, int K, int h, i
     // instruction issue, and on noisy predictions (runs of equal (label, pred) pairs broken every few pixels) the
     // in-kernel histogram cost 0.073 ms per 32 tiles against 0.046 ms for the separate pass.  Without a pred buffer
     // the counting stays fused.
-    const char* fe = getenv("SL_POST_FUSED_CM");                       // 1: keep the counting inside the kernel (A/B runs)
-    const bool split_cm = cm != nullptr && pred != nullptr && !(fe != nullptr && atoi(fe) != 0);
+    const int fused_env = sl::env().post_fused_cm;                     // 1 / 0: force the counting inside / outside the kernel
+    const int prune_env = sl::env().post_prune;                        // 0: always the row-cached kernel (A/B runs)
+    if (prune_env != 0 && pred != nullptr && !conf && !probs && !logits_hr) {
+      // prediction-only path: per-cell class pruning (post_prune.cu), confusion counted in the same pass
+      const bool fused = cm != nullptr && fused_env != 0;
+      const int rc = sl::launch_upsample_prune(logits_lr, B, K, h, w, H, W, sy, sx, fused ? label : nullptr, ignore_label,
+                                               pred, fused ? cmu : nullptr, st);
+      if (rc != -100) {
+        if (rc != 0 || cm == nullptr || fused) return rc;
+        sl::confusion_kernel<<<sl::grid_for((px + 15) / 16, 8), 256, 0, st>>>(label, pred, px, K, ignore_label, cmu, nullptr);
+        return SL_LAUNCH_RESULT();
+      }
+    }
+    const bool split_cm = cm != nullptr && pred != nullptr && fused_env != 1;
     const uint8_t* k_label = split_cm ? nullptr : label;
     unsigned long long* k_cm = split_cm ? nullptr : cmu;
     const int rc = big ? sl::launch_rows<256>(logits_lr, B, K, h, w, H, W, rows, sy, sx, k_label, ignore_label, pred, conf,

@@ -277,12 +277,7 @@ extern "C" int sl_tail_bn_relu_conv(const float* x, int B, int Cin, int N, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // Default: the fused kernel of tail_conv.cu (BN/ReLU/split applied to the A operand on the SM, no intermediate
   // planes).  SL_TAIL_FUSED=0, or a shape outside its range (Cin > 1024), takes the two-kernel path below.
-  static int fused = -1;
-  if (fused < 0) {
-    const char* fe = getenv("SL_TAIL_FUSED");
-    fused = (fe != nullptr && fe[0] == '0') ? 0 : 1;
-  }
-  if (fused) {
+  if (sl::env().tail_fused != 0) {
     const int frc = sl_tail_conv_fused_run(x, B, Cin, N, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, relu, W_hi, W_lo, bias,
                                            Cout, feat_out, st);
     if (frc != SL_EINVAL) return frc;
