@@ -36,8 +36,8 @@ extern "C" {
 
 /* Environment switches read by the library (debugging and A/B measurements only; defaults are the fast paths).
  * They are read ONCE per process (no getenv on the launch path); sl_env_reload() re-reads them.
- *   SL_POST_PRUNE=0     sl_upsample_argmax's prediction-only path on the row-cached kernel instead of the per-cell
- *                       class-pruning kernel (identical results)
+ *   SL_POST_PRUNE=1     sl_upsample_argmax's prediction-only path on the per-cell class-pruning kernel (post_prune.cu)
+ *                       instead of the row-cached kernel: identical results; see profiles/ for when it pays
  *   SL_TC_PAIR=0        background MLP on the single-CTA tcgen05 kernel instead of the cta_group::2 pair kernel
  *   SL_TC_PAIR=1        pair kernel with one (A, B) operand pair per MMA pass and pipeline stage (the schedule before the
  *                       de-duplicated stages; 4-10 % slower)
@@ -137,13 +137,17 @@ SL_API int sl_pop_bg_simt(const uint16_t *feat, int B, int C, int N,
  *   precision  SL_TC_PRECISE  split-bf16 operands, 2 + 3 MMA passes: ~5e-6 of the fp32 reference.
  *              SL_TC_BALANCED layer 1 split-bf16 (2 passes), layer 2 single-pass fp16 (3 passes):
  *                             ~3e-4 relative to the tensor maximum.  Needs W2_f16.
- *              The fp16 mode requires |relu(W1' q)| < 65504 (fp16 range).
+ *              SL_TC_MID      layer 1 split-bf16 (2 passes), layer 2 with the hidden layer split into fp16 hi + lo
+ *                             planes against single fp16 weights (2 passes, 4 in total): the only rounding left is
+ *                             W2 -> fp16 (2^-12 per weight).  Needs W2_f16.  See profiles/r2_pass_probe.txt.
+ *              The fp16 modes require |relu(W1' q)| < 65504 (fp16 range).
  *   Unused weight pointers for the chosen mode may be NULL.
  *   h1_ws: scratch for the hidden layer, sl_pop_bg_tc_ws_bytes(B, C, N) bytes, 128-byte aligned
  *          (two 128-pixel tiles per SM; it stays L2-resident).
  */
 #define SL_TC_PRECISE 0
 #define SL_TC_BALANCED 1
+#define SL_TC_MID 2
 SL_API size_t sl_pop_bg_tc_ws_bytes(int B, int C, int N);
 SL_API int sl_pop_bg_tc(const uint16_t *feat, int B, int C, int N,
                  const uint16_t *W1p_hi, const uint16_t *W1p_lo,

@@ -36,7 +36,7 @@ struct Env {
   int tc_debug;         // SL_TC_DEBUG      (0)
   int prep_split;       // SL_PREP_SPLIT    (0)
   int post_fused_cm;    // SL_POST_FUSED_CM (-1 = unset)
-  int post_prune;       // SL_POST_PRUNE    (1)
+  int post_prune;       // SL_POST_PRUNE    (0)
   int tail_fused;       // SL_TAIL_FUSED    (1)
   long long small_dbg;  // SL_SMALL_DBG     (0)
 };

@@ -67,7 +67,10 @@ struct Params {
   int Ktot, ch;         // logits layout
   int l1_passes;        // 2: split-bf16 W1' (hi, lo)
   int lookahead;        // 1: two scratch slots, layer 1 runs one tile ahead of layer 2 (scratch small enough for L2)
-  int h_f16;            // hidden layer stored as one fp16 tile (layer 2 = 1 pass) instead of bf16 hi/lo (3 passes)
+  int h_f16;            // hidden layer stored as fp16 (balanced / mid) instead of bf16 (precise)
+  int h_lo;             // a second, residual plane of the hidden layer is stored (precise: bf16 lo; mid: fp16 lo)
+  int l2_passes;        // layer-2 MMA passes: 3 precise (h_hi W2hi + h_lo W2hi + h_hi W2lo), 2 mid (h_hi W2 + h_lo W2, fp16),
+                        // 1 balanced (h W2, fp16)
   const float* w3;
   float* logits;
   // fused foreground projections (KQ > 0): s_hat transposed [C][4*KQ], alpha/beta [K], output channel map
@@ -180,7 +183,7 @@ bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
       };
       auto load_g2 = [&](int s) {
         // ---- layer 2: k-blocks outer (in the order layer 1 produced their columns), passes inner
-        const int l2_passes = p.h_f16 ? 1 : 3;
+        const int l2_passes = p.l2_passes;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           int ready = -1;                                      // layer-1 n-tiles known to have landed
           for (int kb = 0; kb < kblocks; ++kb) {
@@ -215,7 +218,7 @@ bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MAX_NT);
         const uint32_t idesc = g2 ? idesc_g2 : idesc_g1;
         uint32_t accumulate = 0;
-        const int iters = (g2 ? (p.h_f16 ? 1 : 3) : p.l1_passes) * kblocks;
+        const int iters = (g2 ? p.l2_passes : p.l1_passes) * kblocks;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -252,7 +255,7 @@ bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
       const int pm = static_cast<int>(threadIdx.x) - 32 * (2 + EPI_WARPS);      // 0..127
       const bool pleader = pm == 0;
       const int V = p.n_tiles * p.l1_passes;
-      const int l2_uses = p.n_tiles * (p.h_f16 ? 1 : 3) * kblocks;
+      const int l2_uses = p.n_tiles * p.l2_passes * kblocks;
       // byte offset of (channel 0, pixel pm) inside a stage; channel c adds c*128 and XORs the 16-byte chunk
       const uint32_t px_blk = static_cast<uint32_t>(pm >> 6) * (A_BYTES / 2);
       const uint32_t px_chunk = static_cast<uint32_t>((pm & 63) >> 3), px_in = static_cast<uint32_t>(pm & 7) * 2u;
@@ -374,7 +377,14 @@ bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
               const __half2 h2 = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * j]), 0.f),
                                                    fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
               hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[j] = 0u;
+              if (p.h_lo) {                                     // mid mode: fp16 residual plane
+                const float2 back = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * j]), 0.f) - back.x,
+                                                     fmaxf(__uint_as_float(r[2 * j + 1]), 0.f) - back.y);
+                lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+              } else {
+                lo[j] = 0u;
+              }
             }
           } else {
 #pragma unroll
@@ -414,7 +424,7 @@ bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
             }
           };
           stage_and_store(hi, &maps.hh_st);
-          if (!p.h_f16) stage_and_store(lo, &maps.hl_st);
+          if (p.h_lo) stage_and_store(lo, &maps.hl_st);
         }
       } else if (half == 0) {
         if (nt == 0) logit = 0.f;
@@ -634,7 +644,7 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
         }
       };
       auto load_g2 = [&](int s) {
-        const int l2_passes = p.h_f16 ? 1 : 3;
+        const int l2_passes = p.l2_passes;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           int ready = -1;
           for (int kb = 0; kb < kblocks; ++kb) {
@@ -645,16 +655,16 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
                 fence_proxy_async_all();
               }
             if constexpr (DEDUP) {
-              const bool split = l2_passes == 3;
-              stage_wait((split ? 2u : 1u) * (A_BYTES + b_bytes));
+              const bool two_a = p.h_lo != 0, two_b = l2_passes == 3;
+              stage_wait((two_a ? 2u : 1u) * A_BYTES + (two_b ? 2u : 1u) * b_bytes);
               const uint32_t sa = base + stage * STG_BYTES, sb = sa + 2 * A_BYTES;
               const int brow = nt * p.NT + static_cast<int>(rank) * half_nt;
               tma_load_2d_pair(sa, &maps.hh_ld, full_bar(stage), kb * BLOCK_K, ws_row0_of(s), L2_EVICT_LAST);
               tma_load_2d_pair(sb, &maps.w2h, full_bar(stage), kb * BLOCK_K, brow, L2_EVICT_LAST);
-              if (split) {
+              if (two_a)
                 tma_load_2d_pair(sa + A_BYTES, &maps.hl_ld, full_bar(stage), kb * BLOCK_K, ws_row0_of(s), L2_EVICT_LAST);
+              if (two_b)
                 tma_load_2d_pair(sb + B_BYTES_MAX / 2, &maps.w2l, full_bar(stage), kb * BLOCK_K, brow, L2_EVICT_LAST);
-              }
               stage_next();
             } else {
               for (int pass = 0; pass < l2_passes; ++pass) {
@@ -685,7 +695,7 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MAX_NT);
         const uint32_t idesc = g2 ? idesc_g2 : idesc_g1;
         uint32_t accumulate = 0;
-        const int passes = g2 ? (p.h_f16 ? 1 : 3) : p.l1_passes;
+        const int passes = g2 ? p.l2_passes : p.l1_passes;
         const int iters = DEDUP ? kblocks : passes * kblocks;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(full_bar(stage), phase);
@@ -756,7 +766,14 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
               const __half2 h2 = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * j]), 0.f),
                                                    fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
               hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[j] = 0u;
+              if (p.h_lo) {                                     // mid mode: fp16 residual plane
+                const float2 back = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * j]), 0.f) - back.x,
+                                                     fmaxf(__uint_as_float(r[2 * j + 1]), 0.f) - back.y);
+                lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+              } else {
+                lo[j] = 0u;
+              }
             }
           } else {
 #pragma unroll
@@ -790,7 +807,7 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
             }
           };
           stage_and_store(hi, &maps.hh_st);
-          if (!p.h_f16) stage_and_store(lo, &maps.hl_st);
+          if (p.h_lo) stage_and_store(lo, &maps.hl_st);
         }
       } else if (half == 0) {
         if (nt == 0) logit = 0.f;
@@ -852,8 +869,8 @@ __global__ void transpose_protos_kernel(const float* __restrict__ s_hat, int K, 
 }  // namespace sl
 
 // bytes the two-slot scratch of a full grid actually touches (fp16 mode stores one array, precise mode two)
-static size_t two_slot_scratch_bytes(int C, int h_f16) {
-  return static_cast<size_t>(sl::num_sms()) * 2 * sl::tc::BLOCK_M * C * sizeof(uint16_t) * (h_f16 ? 1 : 2);
+static size_t two_slot_scratch_bytes(int C, int one_plane) {
+  return static_cast<size_t>(sl::num_sms()) * 2 * sl::tc::BLOCK_M * C * sizeof(uint16_t) * (one_plane ? 1 : 2);
 }
 
 static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint16_t* W1p_hi, const uint16_t* W1p_lo,
@@ -862,7 +879,7 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
                           const float* alpha, const float* beta, int K, const int* fg_ch_host, void* stream) {
   using namespace sl::tc;
   // (a bf16-feature x fp16-weight single pass for layer 1 was tried: tcgen05 kind::f16 traps on mixed A/B formats)
-  SL_CHECK_ARG(precision == SL_TC_PRECISE || precision == SL_TC_BALANCED);
+  SL_CHECK_ARG(precision == SL_TC_PRECISE || precision == SL_TC_BALANCED || precision == SL_TC_MID);
   SL_CHECK_PTR(feat); SL_CHECK_PTR(w3_bg); SL_CHECK_PTR(h1_ws); SL_CHECK_PTR(logits);
   SL_CHECK_PTR(W1p_hi); SL_CHECK_PTR(W1p_lo);
   if (precision == SL_TC_PRECISE) { SL_CHECK_PTR(W2_hi); SL_CHECK_PTR(W2_lo); } else { SL_CHECK_PTR(W2_f16); }
@@ -901,9 +918,11 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
   p.logits = logits;
   p.l1_passes = 2;
   p.h_f16 = precision == SL_TC_PRECISE ? 0 : 1;
+  p.h_lo = precision == SL_TC_BALANCED ? 0 : 1;
+  p.l2_passes = precision == SL_TC_PRECISE ? 3 : precision == SL_TC_MID ? 2 : 1;
   // one-tile look-ahead needs two scratch slots per CTA; use it while both slots of the whole grid stay well
   // inside L2 (measured: 38.8 MB stays resident, 77.6 MB spills 0.9 GB per 32-tile step to HBM)
-  p.lookahead = two_slot_scratch_bytes(C, p.h_f16) <= (40u << 20) ? 1 : 0;
+  p.lookahead = two_slot_scratch_bytes(C, p.h_lo ? 0 : 1) <= (40u << 20) ? 1 : 0;
   p.debug = sl::env().tc_debug;
   const int grid = p.m_tiles < sl::num_sms() ? p.m_tiles : sl::num_sms();
   const size_t ws_rows = static_cast<size_t>(sl::num_sms()) * BLOCK_M * 2;   // laid out for two slots per CTA

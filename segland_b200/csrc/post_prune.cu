@@ -85,250 +85,259 @@ struct CmRun {
 
 // Classes that can be the argmax somewhere in a cell, from the cell's four corner values get(corner, k) (see the
 // header comment for the argument); bit 31 flags a cell with a non-finite / huge value (all classes kept).
+//   pass 1, O(K): with m_k / M_k the smallest / largest corner of class k and c0 the class with the largest m, every
+//           class whose M lies below m_c0 is preceded by c0 at every pixel (a special case of the corner rule);
+//   pass 2, only when 2..4 classes are left: the corner rule itself between the remaining pairs.
+// Any superset of the true survivors gives the same prediction, so both passes may stop early.
 template <int KT, class Get>
 __device__ __forceinline__ uint32_t survivor_mask(int K, Get get) {
   constexpr int KU = KT > 0 ? KT : 1;
   const int Kn = KT > 0 ? KT : K;
-  float mx = 0.f, z = 0.f, lead_v = -INFINITY;
-  int lead = 0;                                                 // first maximum at corner 0
+  float mx = 0.f, z = 0.f, lead_m = -INFINITY;
+  int lead = 0;                                                 // first class with the largest minimum corner
 #pragma unroll(KU)
   for (int k = 0; k < Kn; ++k) {
     const float a = get(0, k), b = get(1, k), c = get(2, k), d = get(3, k);
-    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a), fabsf(b)), fmaxf(fabsf(c), fabsf(d))));
+    const float hi = fmaxf(fmaxf(a, b), fmaxf(c, d)), lo = fminf(fminf(a, b), fminf(c, d));
+    mx = fmaxf(mx, fmaxf(fabsf(hi), fabsf(lo)));
     z += (a - a) + (b - b) + (c - c) + (d - d);                 // 0 for finite values, NaN for NaN / inf (fmaxf drops NaNs)
-    if (a > lead_v) { lead_v = a; lead = k; }
+    if (lo > lead_m) { lead_m = lo; lead = k; }
   }
   const uint32_t all = (1u << Kn) - 1u;                         // K <= 31
   if (!(z == 0.f) || !(mx < 1e37f)) return all | PR_NF;
   const float margin = fmaxf(mx * 1.9073486328125e-6f /* 2^-19 */, 1e-30f);
-  auto beats = [&](int c, int j) {                              // c precedes j at every pixel of the cell
-    bool r = true;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) r = r && (c < j ? get(q, c) >= get(q, j) : get(q, c) - get(q, j) >= margin);
-    return r;
-  };
-  // common case first: the leading class precedes every other class
-  bool single = true;
-  if constexpr (KT > 0) {
-    // `lead` is a run-time index: select its corner values once so the register arrays keep static indices
-    float lv[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      lv[q] = get(q, 0);
-#pragma unroll
-      for (int k = 1; k < KT; ++k) lv[q] = (k == lead) ? get(q, k) : lv[q];
-    }
-#pragma unroll
-    for (int j = 0; j < KT; ++j) {
-      bool r = true;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) r = r && (lead < j ? lv[q] >= get(q, j) : lv[q] - get(q, j) >= margin);
-      single = single && (j == lead || r);
-    }
-  } else {
-    for (int j = 0; j < Kn; ++j) single = single && (j == lead || beats(lead, j));
-  }
-  if (single) return 1u << lead;
-  uint32_t mask = 0u;
+  uint32_t S = 0u;
 #pragma unroll(KU)
-  for (int j = 0; j < Kn; ++j) {
-    bool dead = false;
-#pragma unroll(KU)
-    for (int c = 0; c < Kn; ++c)
-      if (c != j) dead = dead || beats(c, j);
-    if (!dead) mask |= 1u << j;
+  for (int k = 0; k < Kn; ++k) {
+    const float hi = fmaxf(fmaxf(get(0, k), get(1, k)), fmaxf(get(2, k), get(3, k)));
+    // kept unless the leading class precedes it: weakly when the leader has the lower index, by the margin otherwise
+    const bool dead = k != lead && (lead < k ? lead_m >= hi : lead_m - hi >= margin);
+    if (!dead) S |= 1u << k;
   }
-  return mask;
+  const int ns = __popc(S);
+  if (ns >= 2 && ns <= 4) {
+    const uint32_t S0 = S;
+    for (uint32_t js = S0; js; js &= js - 1u) {
+      const int j = __ffs(js) - 1;
+      const float j0 = get(0, j), j1 = get(1, j), j2 = get(2, j), j3 = get(3, j);
+      for (uint32_t cs = S0 & ~(1u << j); cs; cs &= cs - 1u) {
+        const int c = __ffs(cs) - 1;
+        const float c0 = get(0, c), c1 = get(1, c), c2 = get(2, c), c3 = get(3, c);
+        const bool beats = c < j ? (c0 >= j0 && c1 >= j1 && c2 >= j2 && c3 >= j3)
+                                 : (c0 - j0 >= margin && c1 - j1 >= margin && c2 - j2 >= margin && c3 - j3 >= margin);
+        if (beats) { S &= ~(1u << j); break; }
+      }
+    }
+  }
+  return S;
 }
 
-// KT > 0: compile-time class count (loops unrolled, corner values in registers); KT == 0: any K <= SL_MAX_CLASSES.
+// Persistent kernel: a CTA walks work units u = blockIdx.x, blockIdx.x + gridDim.x, ...; unit = (image, band, column
+// chunk of 1024 pixels).  The source rows of unit i+1 are copied global -> shared (cp.async) while unit i is processed;
+// the confusion histogram lives in shared memory for the whole kernel and is flushed once per CTA.
+// KT > 0: compile-time class count (loops unrolled); KT == 0: any K <= 31.
 template <int KT>
 __global__ void __launch_bounds__(PR_THREADS, 3) upsample_prune_kernel(
     const float* __restrict__ logits_lr, int K_rt, int h, int w, int H, int W, float sy, float sx,
     const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred,
-    unsigned long long* __restrict__ cm, int ncols_alloc) {
+    unsigned long long* __restrict__ cm, int ncols_alloc, int n_chunks, int n_units) {
   const int K = KT > 0 ? KT : K_rt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: raw [2][K][ncols_alloc] fp32 | mask [ncols_alloc] u32 | lists [4][2*PR_THREADS] u16 | hist [K*K] u32
-  float* raw = reinterpret_cast<float*>(smem_raw);
-  uint32_t* cmask = reinterpret_cast<uint32_t*>(raw + 2 * K * ncols_alloc);
+  // layout: raw [2 buffers][2 rows][K][ncols_alloc] fp32 | mask [ncols_alloc] u32 | lists [4][2*PR_THREADS] u16 | hist [K*K] u32
+  float* raw_all = reinterpret_cast<float*>(smem_raw);
+  const int raw_stride = 2 * K * ncols_alloc;
+  uint32_t* cmask = reinterpret_cast<uint32_t*>(raw_all + 2 * raw_stride);
   uint16_t* lists = reinterpret_cast<uint16_t*>(cmask + ncols_alloc);
   unsigned int* hist = reinterpret_cast<unsigned int*>(lists + 4 * 2 * PR_THREADS);
   __shared__ int list_n[4];
+  __shared__ int band_rows[2];                                  // y_lo, y_hi of the current unit
   __shared__ float row_l0[PR_MAX_BAND], row_l1[PR_MAX_BAND];
 
   const int tid = threadIdx.x;
-  const int b = blockIdx.z, band = blockIdx.y;
   const bool do_cm = cm != nullptr;
-  const int X0 = blockIdx.x * (PR_THREADS * 4);
-  const int X1 = min(W, X0 + PR_THREADS * 4);
-  const int y_lo = first_dst(sy, band, h, H), y_hi = first_dst(sy, band + 1, h, H);   // rows [y_lo, y_hi)
-  const int R = y_hi - y_lo;
-  if (R <= 0) return;
-  const int row1 = min(band + 1, h - 1);
-  const int c_lo = src_coord(sx, X0, w).i0;
-  const SrcCoord c_last = src_coord(sx, X1 - 1, w);
-  const int c_hi = c_last.i0 + c_last.step;
-  const int ncols = c_hi - c_lo + 1;                            // <= ncols_alloc by construction of the launch
-
-  if (tid < 4) list_n[tid] = 0;
-  if (tid < R) {
-    const SrcCoord cy = src_coord(sy, y_lo + tid, h);
-    row_l0[tid] = cy.l0; row_l1[tid] = cy.l1;
-  }
+  const size_t hw = static_cast<size_t>(h) * w;
   if (do_cm) for (int i = tid; i < K * K; i += PR_THREADS) hist[i] = 0u;
-  {  // stage the two source rows of every class (coalesced; the low-res logits are L2-resident)
-    const size_t hw = static_cast<size_t>(h) * w;
-    const float* p0 = logits_lr + static_cast<size_t>(b) * K * hw + static_cast<size_t>(band) * w + c_lo;
-    const float* p1 = logits_lr + static_cast<size_t>(b) * K * hw + static_cast<size_t>(row1) * w + c_lo;
-    for (int k = 0; k < K; ++k, p0 += hw, p1 += hw)
-      for (int c = tid; c < ncols; c += PR_THREADS) {
-        raw[(0 * K + k) * ncols_alloc + c] = __ldg(p0 + c);
-        raw[(1 * K + k) * ncols_alloc + c] = __ldg(p1 + c);
-      }
-  }
-  __syncthreads();
 
-  // ---- survivor mask per cell (cell c = source columns c, min(c + 1, c_hi))
-  for (int c = tid; c < ncols; c += PR_THREADS) {
-    const int c1 = min(c + 1, ncols - 1);
-    const float* q0 = raw + c;
-    const float* q1 = raw + c1;
-    if constexpr (KT > 0) {
-      float v[4][KT];                                           // corner values in registers
-#pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        v[0][k] = q0[(0 * KT + k) * ncols_alloc]; v[1][k] = q1[(0 * KT + k) * ncols_alloc];
-        v[2][k] = q0[(1 * KT + k) * ncols_alloc]; v[3][k] = q1[(1 * KT + k) * ncols_alloc];
+  struct Unit { int b, band, X0, X1, c_lo, ncols; };
+  auto decode = [&](int u) {
+    Unit q;
+    const int chunk = u % n_chunks;
+    const int t = u / n_chunks;
+    q.band = t % h; q.b = t / h;
+    q.X0 = chunk * (PR_THREADS * 4);
+    q.X1 = min(W, q.X0 + PR_THREADS * 4);
+    q.c_lo = src_coord(sx, q.X0, w).i0;
+    const SrcCoord c_last = src_coord(sx, q.X1 - 1, w);
+    q.ncols = c_last.i0 + c_last.step - q.c_lo + 1;             // <= ncols_alloc by construction of the launch
+    return q;
+  };
+  auto stage = [&](const Unit& q, int buf) {                    // the two source rows of every class -> shared (async)
+    const int row1 = min(q.band + 1, h - 1);
+    const float* p0 = logits_lr + static_cast<size_t>(q.b) * K * hw + static_cast<size_t>(q.band) * w + q.c_lo;
+    const float* p1 = logits_lr + static_cast<size_t>(q.b) * K * hw + static_cast<size_t>(row1) * w + q.c_lo;
+    const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(raw_all + buf * raw_stride));
+    for (int k = 0; k < K; ++k, p0 += hw, p1 += hw)
+      for (int c = tid; c < q.ncols; c += PR_THREADS) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * ((0 * K + k) * ncols_alloc + c)), "l"(p0 + c) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * ((1 * K + k) * ncols_alloc + c)), "l"(p1 + c) : "memory");
       }
-      cmask[c] = survivor_mask<KT>(KT, [&](int corner, int k) { return v[corner][k]; });
-    } else {
-      cmask[c] = survivor_mask<0>(K, [&](int corner, int k) {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  CmRun run; run.bin = 0; run.cnt = 0;
+  int u = blockIdx.x, buf = 0;
+  if (u < n_units) stage(decode(u), 0);
+  for (; u < n_units; u += gridDim.x, buf ^= 1) {
+    const Unit q = decode(u);
+    const float* raw = raw_all + buf * raw_stride;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                            // this unit's rows have landed; the previous unit is done
+    if (u + gridDim.x < n_units) stage(decode(u + gridDim.x), buf ^ 1);
+    if (tid >= PR_THREADS - 32) {       // the last warp (it rarely owns cells): the band's output rows and their weights
+      const int ln = tid - (PR_THREADS - 32);
+      int yl = 0, yh = 0;
+      if (ln == 0) { yl = first_dst(sy, q.band, h, H); yh = first_dst(sy, q.band + 1, h, H); }
+      yl = __shfl_sync(0xffffffffu, yl, 0); yh = __shfl_sync(0xffffffffu, yh, 0);
+      if (ln == 0) { band_rows[0] = yl; band_rows[1] = yh; }
+      if (ln < yh - yl && ln < PR_MAX_BAND) {
+        const SrcCoord cy = src_coord(sy, yl + ln, h);
+        row_l0[ln] = cy.l0; row_l1[ln] = cy.l1;
+      }
+      if (ln < 4) list_n[ln] = 0;
+    }
+    // ---- survivor mask per cell (cell c = source columns c, min(c + 1, ncols - 1))
+    for (int c = tid; c < q.ncols; c += PR_THREADS) {
+      const float* q0 = raw + c;
+      const float* q1 = raw + min(c + 1, q.ncols - 1);
+      cmask[c] = survivor_mask<KT>(K, [&](int corner, int k) {
         return ((corner & 1) ? q1 : q0)[((corner >> 1) * K + k) * ncols_alloc];
       });
     }
-  }
-  __syncthreads();
-
-  // ---- one strip (4 output columns x the band's rows) per thread
-  const int x0 = X0 + tid * 4;
-  const bool col_ok = x0 < W;                                   // W % 4 == 0
-  CmRun run; run.bin = 0; run.cnt = 0;
-  const int nchunks = (R + PR_ROWS - 1) / PR_ROWS;
-  if (col_ok) {
-    const int ca = src_coord(sx, x0, w).i0 - c_lo, cb = src_coord(sx, x0 + 3, w).i0 - c_lo;
-    uint32_t m = 0u;
-    for (int c = ca; c <= cb; ++c) m |= cmask[c];
-    const int nc = __popc(m & ~PR_NF);
-    if (nc == 1 && !(m & PR_NF)) {
-      const uint32_t pw = static_cast<uint32_t>(__ffs(m) - 1) * 0x01010101u;
-      const size_t pix = (static_cast<size_t>(b) * H + y_lo) * W + x0;
-      uint32_t lw[PR_MAX_BAND];
-      if (do_cm) {
+    __syncthreads();
+    const int y_lo = band_rows[0], R = band_rows[1] - band_rows[0];
+    const int nchunks = (R + PR_ROWS - 1) / PR_ROWS;
+    if (R > 0) {
+      // ---- one strip (4 output columns x the band's rows) per thread
+      const int x0 = q.X0 + tid * 4;
+      if (x0 < W) {                                             // W % 4 == 0
+        const int ca = src_coord(sx, x0, w).i0 - q.c_lo, cb = src_coord(sx, x0 + 3, w).i0 - q.c_lo;
+        uint32_t m = 0u;
+        for (int c = ca; c <= cb; ++c) m |= cmask[c];
+        const int nc = __popc(m & ~PR_NF);
+        if (nc == 1 && !(m & PR_NF)) {
+          const uint32_t pw = static_cast<uint32_t>(__ffs(m) - 1) * 0x01010101u;
+          const size_t pix = (static_cast<size_t>(q.b) * H + y_lo) * W + x0;
+          uint32_t lw[PR_MAX_BAND];
+          if (do_cm) {
 #pragma unroll
-        for (int r = 0; r < PR_MAX_BAND; ++r)
-          if (r < R) lw[r] = __ldg(reinterpret_cast<const uint32_t*>(label + pix + static_cast<size_t>(r) * W));
+            for (int r = 0; r < PR_MAX_BAND; ++r)
+              if (r < R) lw[r] = __ldg(reinterpret_cast<const uint32_t*>(label + pix + static_cast<size_t>(r) * W));
+          }
+#pragma unroll
+          for (int r = 0; r < PR_MAX_BAND; ++r)
+            if (r < R) *reinterpret_cast<uint32_t*>(pred + pix + static_cast<size_t>(r) * W) = pw;
+          if (do_cm) {
+#pragma unroll
+            for (int r = 0; r < PR_MAX_BAND; ++r)
+              if (r < R) run.add_word(hist, lw[r], pw, K, ignore_label);
+          }
+        } else {
+          const int bucket = (m & PR_NF) ? 3 : nc <= 2 ? 0 : nc <= 4 ? 1 : 2;
+          const int slot = atomicAdd(&list_n[bucket], nchunks);
+          for (int qq = 0; qq < nchunks; ++qq)
+            lists[bucket * 2 * PR_THREADS + slot + qq] = static_cast<uint16_t>(tid | (qq << 8));
+        }
       }
-#pragma unroll
-      for (int r = 0; r < PR_MAX_BAND; ++r)
-        if (r < R) *reinterpret_cast<uint32_t*>(pred + pix + static_cast<size_t>(r) * W) = pw;
-      if (do_cm) {
-#pragma unroll
-        for (int r = 0; r < PR_MAX_BAND; ++r)
-          if (r < R) run.add_word(hist, lw[r], pw, K, ignore_label);
-      }
-    } else {
-      const int bucket = (m & PR_NF) ? 3 : nc <= 2 ? 0 : nc <= 4 ? 1 : 2;
-      const int slot = atomicAdd(&list_n[bucket], nchunks);
-      for (int q = 0; q < nchunks; ++q) lists[bucket * 2 * PR_THREADS + slot + q] = static_cast<uint16_t>(tid | (q << 8));
     }
-  }
-  __syncthreads();
+    __syncthreads();
+    if (R <= 0) continue;
 
-  // ---- queued strips, one (strip, row chunk) item per thread and turn; items of one bucket run together
-  for (int bucket = 0; bucket < 4; ++bucket) {
-    const int n_items = list_n[bucket];
-    for (int it = tid; it < n_items; it += PR_THREADS) {
-      const int item = lists[bucket * 2 * PR_THREADS + it];
-      const int st = item & 0xff, r0 = (item >> 8) * PR_ROWS;
-      const int nr = min(PR_ROWS, R - r0);
-      const int xs0 = X0 + st * 4;
-      int xi[4], xn[4];
-      float xl0[4], xl1[4];
-      uint32_t m = 0u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const SrcCoord c = src_coord(sx, xs0 + j, w);
-        xi[j] = c.i0 - c_lo; xn[j] = xi[j] + c.step; xl0[j] = c.l0; xl1[j] = c.l1;
-      }
-      for (int c = xi[0]; c <= xi[3]; ++c) m |= cmask[c];
-      float best[PR_ROWS][4];
-      uint32_t idx[PR_ROWS];                                    // four class indices per row, one byte each
-#pragma unroll
-      for (int r = 0; r < PR_ROWS; ++r) {
-        idx[r] = 0u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) best[r][j] = -INFINITY;
-      }
-      const bool nf = (m & PR_NF) != 0u;
-      uint32_t todo = nf ? (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)) : m;
-      bool first = !nf;
-      while (todo) {
-        const int k = __ffs(todo) - 1;
-        todo &= todo - 1u;
-        const uint32_t kk = static_cast<uint32_t>(k) * 0x01010101u;
-        const float* t = raw + (0 * K + k) * ncols_alloc;
-        const float* u = raw + (1 * K + k) * ncols_alloc;
-        float top[4], bot[4];
+    // ---- queued strips, one (strip, row chunk) item per thread and turn; items of one bucket run together
+    for (int bucket = 0; bucket < 4; ++bucket) {
+      const int n_items = list_n[bucket];
+      for (int it = tid; it < n_items; it += PR_THREADS) {
+        const int item = lists[bucket * 2 * PR_THREADS + it];
+        const int st = item & 0xff, r0 = (item >> 8) * PR_ROWS;
+        const int nr = min(PR_ROWS, R - r0);
+        const int xs0 = q.X0 + st * 4;
+        int xi[4], xn[4];
+        float xl0[4], xl1[4];
+        uint32_t m = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          // l0x*a + l1x*b as nvcc contracts it in the row-cached kernel: fma(l0x, a, l1x*b)
-          top[j] = __fmaf_rn(xl0[j], t[xi[j]], __fmul_rn(xl1[j], t[xn[j]]));
-          bot[j] = __fmaf_rn(xl0[j], u[xi[j]], __fmul_rn(xl1[j], u[xn[j]]));
+          const SrcCoord c = src_coord(sx, xs0 + j, w);
+          xi[j] = c.i0 - q.c_lo; xn[j] = xi[j] + c.step; xl0[j] = c.l0; xl1[j] = c.l1;
         }
+        for (int c = xi[0]; c <= xi[3]; ++c) m |= cmask[c];
+        float best[PR_ROWS][4];
+        uint32_t idx[PR_ROWS];                                  // four class indices per row, one byte each
+#pragma unroll
+        for (int r = 0; r < PR_ROWS; ++r) {
+          idx[r] = 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) best[r][j] = -INFINITY;
+        }
+        const bool nf = (m & PR_NF) != 0u;
+        uint32_t todo = nf ? ((1u << K) - 1u) : m;
+        bool first = !nf;
+        while (todo) {
+          const int k = __ffs(todo) - 1;
+          todo &= todo - 1u;
+          const uint32_t kk = static_cast<uint32_t>(k) * 0x01010101u;
+          const float* t = raw + (0 * K + k) * ncols_alloc;
+          const float* v1 = raw + (1 * K + k) * ncols_alloc;
+          float top[4], bot[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // l0x*a + l1x*b as nvcc contracts it in the row-cached kernel: fma(l0x, a, l1x*b)
+            top[j] = __fmaf_rn(xl0[j], t[xi[j]], __fmul_rn(xl1[j], t[xn[j]]));
+            bot[j] = __fmaf_rn(xl0[j], v1[xi[j]], __fmul_rn(xl1[j], v1[xn[j]]));
+          }
+#pragma unroll
+          for (int r = 0; r < PR_ROWS; ++r) {
+            if (r < nr) {
+              const float l0 = row_l0[r0 + r], l1 = row_l1[r0 + r];
+              // l0y*top + l1y*bot on packed pairs: mul then fma, the same products and sums as the row-cached kernel
+              float2 v01 = pr_mul2(make_float2(l0, l0), make_float2(top[0], top[1]));
+              float2 v23 = pr_mul2(make_float2(l0, l0), make_float2(top[2], top[3]));
+              v01 = pr_fma2(make_float2(l1, l1), make_float2(bot[0], bot[1]), v01);
+              v23 = pr_fma2(make_float2(l1, l1), make_float2(bot[2], bot[3]), v23);
+              const float v[4] = {v01.x, v01.y, v23.x, v23.y};
+              if (first) {
+                idx[r] = kk;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) best[r][j] = v[j];
+              } else if (!nf) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (v[j] > best[r][j]) { best[r][j] = v[j]; idx[r] = (idx[r] & ~(0xffu << (8 * j))) | (kk & (0xffu << (8 * j))); }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)                    // np.argmax: first maximum, NaN counts as maximal
+                  if (v[j] > best[r][j] || (v[j] != v[j] && best[r][j] == best[r][j])) {
+                    best[r][j] = v[j];
+                    idx[r] = (idx[r] & ~(0xffu << (8 * j))) | (kk & (0xffu << (8 * j)));
+                  }
+              }
+            }
+          }
+          first = false;
+        }
+        const size_t pix = (static_cast<size_t>(q.b) * H + y_lo + r0) * W + xs0;
 #pragma unroll
         for (int r = 0; r < PR_ROWS; ++r) {
           if (r < nr) {
-            const float l0 = row_l0[r0 + r], l1 = row_l1[r0 + r];
-            // l0y*top + l1y*bot on packed pairs: mul then fma, the same products and sums as the row-cached kernel
-            float2 v01 = pr_mul2(make_float2(l0, l0), make_float2(top[0], top[1]));
-            float2 v23 = pr_mul2(make_float2(l0, l0), make_float2(top[2], top[3]));
-            v01 = pr_fma2(make_float2(l1, l1), make_float2(bot[0], bot[1]), v01);
-            v23 = pr_fma2(make_float2(l1, l1), make_float2(bot[2], bot[3]), v23);
-            const float v[4] = {v01.x, v01.y, v23.x, v23.y};
-            if (first) {
-              idx[r] = kk;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) best[r][j] = v[j];
-            } else if (!nf) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (v[j] > best[r][j]) { best[r][j] = v[j]; idx[r] = (idx[r] & ~(0xffu << (8 * j))) | (kk & (0xffu << (8 * j))); }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)                      // np.argmax: first maximum, NaN counts as maximal
-                if (v[j] > best[r][j] || (v[j] != v[j] && best[r][j] == best[r][j])) {
-                  best[r][j] = v[j];
-                  idx[r] = (idx[r] & ~(0xffu << (8 * j))) | (kk & (0xffu << (8 * j)));
-                }
-            }
+            const uint32_t pw = idx[r];
+            *reinterpret_cast<uint32_t*>(pred + pix + static_cast<size_t>(r) * W) = pw;
+            if (do_cm)
+              run.add_word(hist, __ldg(reinterpret_cast<const uint32_t*>(label + pix + static_cast<size_t>(r) * W)), pw, K,
+                           ignore_label);
           }
-        }
-        first = false;
-      }
-      const size_t pix = (static_cast<size_t>(b) * H + y_lo + r0) * W + xs0;
-#pragma unroll
-      for (int r = 0; r < PR_ROWS; ++r) {
-        if (r < nr) {
-          const uint32_t pw = idx[r];
-          *reinterpret_cast<uint32_t*>(pred + pix + static_cast<size_t>(r) * W) = pw;
-          if (do_cm)
-            run.add_word(hist, __ldg(reinterpret_cast<const uint32_t*>(label + pix + static_cast<size_t>(r) * W)), pw, K,
-                         ignore_label);
         }
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (do_cm) {
     run.flush(hist);
     __syncthreads();
@@ -347,16 +356,21 @@ int launch_upsample_prune(const float* logits_lr, int B, int K, int h, int w, in
   if (!(sx > 0.f && sx <= 0.5f && sy > 0.1f && sy <= 0.5f)) return -100;
   if (static_cast<int>(1.f / sy) + 2 > sl::PR_MAX_BAND) return -100;
   const int ncols_alloc = static_cast<int>(PR_THREADS * 4 * sx) + 4;
-  const size_t smem = static_cast<size_t>(2) * K * ncols_alloc * 4 + static_cast<size_t>(ncols_alloc) * 4 +
+  const size_t smem = static_cast<size_t>(4) * K * ncols_alloc * 4 + static_cast<size_t>(ncols_alloc) * 4 +
                       4 * 2 * PR_THREADS * 2 + static_cast<size_t>(K) * K * 4;
   if (smem > 160 * 1024) return -100;
-  const dim3 grid((W / 4 + PR_THREADS - 1) / PR_THREADS, h, B);
+  const int n_chunks = (W / 4 + PR_THREADS - 1) / PR_THREADS;
+  const long long units = static_cast<long long>(B) * h * n_chunks;
+  if (units >= (1ll << 31)) return -100;
+  const int per_sm = smem <= 72 * 1024 ? 3 : smem <= 110 * 1024 ? 2 : 1;
+  const int grid = static_cast<int>(units < static_cast<long long>(num_sms()) * per_sm ? units : static_cast<long long>(num_sms()) * per_sm);
   auto launch = [&](auto kern) {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (e != cudaSuccess) return static_cast<int>(e);
     }
-    kern<<<grid, PR_THREADS, smem, st>>>(logits_lr, K, h, w, H, W, sy, sx, label, ignore_label, pred, cm, ncols_alloc);
+    kern<<<grid, PR_THREADS, smem, st>>>(logits_lr, K, h, w, H, W, sy, sx, label, ignore_label, pred, cm, ncols_alloc,
+                                        n_chunks, static_cast<int>(units));
     return SL_LAUNCH_RESULT();
   };
   if (K == 8) return launch(upsample_prune_kernel<8>);

@@ -31,80 +31,78 @@ __device__ __forceinline__ void cover_range(const int* o, int n, int len, int p,
     if (o[g] <= p && p < o[g] + len) { if (g < lo) lo = g; hi = g; }
 }
 
-// One thread = 4 consecutive canvas columns of one row, for PLANES consecutive (b, k) planes: the covering
-// ranges are worked out once per thread.  VEC: ox % 4 == 0, wc % 4 == 0, w % 4 == 0 and 16-byte aligned pointers.
+// One thread = 4 consecutive canvas columns of one row of one (b, k) plane.  The covering entries are walked as one
+// flat index and loaded four at a time (independent loads, then added in entry order), so a thread keeps four
+// requests in flight at ~40 registers.  VEC: ox % 4 == 0, wc % 4 == 0, w % 4 == 0 and 16-byte aligned pointers.
 template <bool VEC>
 __global__ void __launch_bounds__(256) window_accumulate_kernel(
-    const float* __restrict__ crops, long long stride_e, long long stride_b, int B, int K, int hc, int wc,
-    const __grid_constant__ WinPlan pl, int h, int w, int planes_per_thread, float* __restrict__ canvas,
-    float* __restrict__ count) {
+    const float* __restrict__ crops, long long stride_e, long long stride_b, int K, int hc, int wc,
+    const __grid_constant__ WinPlan pl, int h, int w, float* __restrict__ canvas, float* __restrict__ count) {
   const int wq = (w + 3) >> 2;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= wq * h) return;
   const int y = q / wq, x0 = (q - y * wq) * 4;
-  int gy_lo, gy_hi, gx_lo[4], gx_hi[4];
+  const int p = blockIdx.y, b = p / K, k = p - b * K;
+  int gy_lo, gy_hi;
   cover_range(pl.oy, pl.ny, hc, y, gy_lo, gy_hi);
+  const int nyc = max(0, gy_hi - gy_lo + 1);
+  const float* plane = crops + static_cast<size_t>(b) * stride_b + static_cast<size_t>(k) * hc * wc;
+  float* dst = canvas + (static_cast<size_t>(p) * h + y) * w + x0;
+  constexpr int NB = 4;                                          // entries loaded per batch
   if (VEC) {
-    cover_range(pl.ox, pl.nx, wc, x0, gx_lo[0], gx_hi[0]);       // origins and widths are multiples of 4: one range
+    int gx_lo, gx_hi;
+    cover_range(pl.ox, pl.nx, wc, x0, gx_lo, gx_hi);             // origins and widths are multiples of 4: one range
+    const int nxc = max(0, gx_hi - gx_lo + 1), nxv = nxc * pl.V, n = nyc * nxv;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i0 = 0; i0 < n; i0 += NB) {
+      float4 t[NB];
+      bool fl[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int i = min(i0 + j, n - 1);
+        const int iy = i / nxv, r = i - iy * nxv, ix = r / pl.V, v = r - ix * pl.V;
+        const int gy = gy_lo + iy, gx = gx_lo + ix, f = pl.flip[v];
+        const int ry = y - pl.oy[gy], rx = x0 - pl.ox[gx];
+        const int ys = (f & 2) ? hc - 1 - ry : ry, xs = (f & 1) ? wc - 4 - rx : rx;
+        fl[j] = f & 1;
+        t[j] = ld_stream_f4(plane + static_cast<size_t>((gy * pl.nx + gx) * pl.V + v) * stride_e + static_cast<size_t>(ys) * wc + xs);
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (i0 + j < n) {
+          acc.x += fl[j] ? t[j].w : t[j].x; acc.y += fl[j] ? t[j].z : t[j].y;
+          acc.z += fl[j] ? t[j].y : t[j].z; acc.w += fl[j] ? t[j].x : t[j].w;
+        }
+    }
+    const float cnt = static_cast<float>(n);
+    __stcs(reinterpret_cast<float4*>(dst), make_float4(acc.x / cnt, acc.y / cnt, acc.z / cnt, acc.w / cnt));
+    if (count != nullptr && p == 0) *reinterpret_cast<float4*>(count + static_cast<size_t>(y) * w + x0) = make_float4(cnt, cnt, cnt, cnt);
   } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cover_range(pl.ox, pl.nx, wc, min(x0 + j, w - 1), gx_lo[j], gx_hi[j]);
-  }
-  const int ny_cov = max(0, gy_hi - gy_lo + 1);
-  float cnt[4];
+    for (int jx = 0; jx < 4; ++jx) {
+      const int x = x0 + jx;
+      if (x >= w) break;
+      int gx_lo, gx_hi;
+      cover_range(pl.ox, pl.nx, wc, x, gx_lo, gx_hi);
+      const int nxc = max(0, gx_hi - gx_lo + 1), nxv = nxc * pl.V, n = nyc * nxv;
+      float acc = 0.f;
+      for (int i0 = 0; i0 < n; i0 += NB) {
+        float t[NB];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) cnt[j] = static_cast<float>(ny_cov * max(0, gx_hi[VEC ? 0 : j] - gx_lo[VEC ? 0 : j] + 1) * pl.V);
-  const int total_planes = B * K;
-  const int p_begin = blockIdx.y * planes_per_thread, p_end = min(total_planes, p_begin + planes_per_thread);
-  if (count != nullptr && p_begin == 0) {
-    if (VEC) *reinterpret_cast<float4*>(count + static_cast<size_t>(y) * w + x0) = make_float4(cnt[0], cnt[1], cnt[2], cnt[3]);
-    else
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (x0 + j < w) count[static_cast<size_t>(y) * w + x0 + j] = cnt[j];
-  }
-  const size_t chw = static_cast<size_t>(hc) * wc;
-  for (int p = p_begin; p < p_end; ++p) {
-    const int b = p / K, k = p - b * K;
-    const float* plane0 = crops + static_cast<size_t>(b) * stride_b + static_cast<size_t>(k) * chw;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int gy = gy_lo; gy <= gy_hi; ++gy) {
-      const int ry = y - pl.oy[gy];
-      if (VEC) {
-        for (int gx = gx_lo[0]; gx <= gx_hi[0]; ++gx) {
-          const int rx = x0 - pl.ox[gx];
-          const float* ent = plane0 + static_cast<size_t>((gy * pl.nx + gx) * pl.V) * stride_e;
-          for (int v = 0; v < pl.V; ++v, ent += stride_e) {
-            const int f = pl.flip[v];
-            const int ys = (f & 2) ? hc - 1 - ry : ry;
-            const int xs = (f & 1) ? wc - 4 - rx : rx;
-            const float4 t = ld_stream_f4(ent + static_cast<size_t>(ys) * wc + xs);
-            acc[0] += (f & 1) ? t.w : t.x; acc[1] += (f & 1) ? t.z : t.y;
-            acc[2] += (f & 1) ? t.y : t.z; acc[3] += (f & 1) ? t.x : t.w;
-          }
+        for (int j = 0; j < NB; ++j) {
+          const int i = min(i0 + j, n - 1);
+          const int iy = i / nxv, r = i - iy * nxv, ix = r / pl.V, v = r - ix * pl.V;
+          const int gy = gy_lo + iy, gx = gx_lo + ix, f = pl.flip[v];
+          const int ry = y - pl.oy[gy], rx = x - pl.ox[gx];
+          const int ys = (f & 2) ? hc - 1 - ry : ry, xs = (f & 1) ? wc - 1 - rx : rx;
+          t[j] = __ldg(plane + static_cast<size_t>((gy * pl.nx + gx) * pl.V + v) * stride_e + static_cast<size_t>(ys) * wc + xs);
         }
-      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (x0 + j >= w) continue;
-          for (int gx = gx_lo[j]; gx <= gx_hi[j]; ++gx) {
-            const int rx = x0 + j - pl.ox[gx];
-            const float* ent = plane0 + static_cast<size_t>((gy * pl.nx + gx) * pl.V) * stride_e;
-            for (int v = 0; v < pl.V; ++v, ent += stride_e) {
-              const int f = pl.flip[v];
-              const int ys = (f & 2) ? hc - 1 - ry : ry;
-              const int xs = (f & 1) ? wc - 1 - rx : rx;
-              acc[j] += __ldg(ent + static_cast<size_t>(ys) * wc + xs);
-            }
-          }
-        }
+        for (int j = 0; j < NB; ++j) if (i0 + j < n) acc += t[j];
       }
-    }
-    float* dst = canvas + (static_cast<size_t>(p) * h + y) * w + x0;
-    if (VEC) {
-      __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0] / cnt[0], acc[1] / cnt[1], acc[2] / cnt[2], acc[3] / cnt[3]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (x0 + j < w) dst[j] = acc[j] / cnt[j];
+      const float cnt = static_cast<float>(n);
+      dst[jx] = acc / cnt;
+      if (count != nullptr && p == 0) count[static_cast<size_t>(y) * w + x] = cnt;
     }
   }
 }
@@ -139,17 +137,10 @@ extern "C" int sl_window_accumulate(const float* crops, long long stride_e, long
   const long long quads = static_cast<long long>(h) * ((w + 3) / 4);
   SL_CHECK_ARG(quads < (1ll << 31));
   const int planes = B * K;
-  // enough CTAs to fill the machine several times over, as few plane groups as that allows (the covering ranges are
-  // computed once per thread and reused for all of its planes)
-  const long long bx = (quads + 255) / 256;
-  int groups = static_cast<int>((8ll * sl::num_sms() + bx - 1) / bx);
-  if (groups < 1) groups = 1;
-  if (groups > planes) groups = planes;
-  if (groups > 65535) groups = 65535;
-  const int ppt = (planes + groups - 1) / groups;
-  const dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>((planes + ppt - 1) / ppt));
+  SL_CHECK_ARG(planes <= 65535);
+  const dim3 grid(static_cast<unsigned>((quads + 255) / 256), static_cast<unsigned>(planes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (vec) sl::window_accumulate_kernel<true><<<grid, 256, 0, st>>>(crops, stride_e, stride_b, B, K, hc, wc, pl, h, w, ppt, canvas, count);
-  else sl::window_accumulate_kernel<false><<<grid, 256, 0, st>>>(crops, stride_e, stride_b, B, K, hc, wc, pl, h, w, ppt, canvas, count);
+  if (vec) sl::window_accumulate_kernel<true><<<grid, 256, 0, st>>>(crops, stride_e, stride_b, K, hc, wc, pl, h, w, canvas, count);
+  else sl::window_accumulate_kernel<false><<<grid, 256, 0, st>>>(crops, stride_e, stride_b, K, hc, wc, pl, h, w, canvas, count);
   return SL_LAUNCH_RESULT();
 }

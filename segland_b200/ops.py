@@ -69,10 +69,11 @@ class PopHead:
     tc_precision: 'precise' (split-bf16, 5 MMA passes, ~5e-6 of fp32; the default and the mode the
              parity claims are made for) or 'balanced' (layer 2 in single-pass fp16, 3 passes, ~4e-4
              relative to the tensor maximum: inside the 1e-3 logit bound, but near-tie argmax flips
-             become ~100x more frequent); see include/segland_b200.h.
+             become ~100x more frequent) or 'mid' (hidden layer as fp16 hi + lo against fp16 W2, 4 passes);
+             see include/segland_b200.h and profiles/r2_pass_probe.txt.
     """
 
-    TC_PRECISIONS = {'precise': 0, 'balanced': 1}
+    TC_PRECISIONS = {'precise': 0, 'balanced': 1, 'mid': 2}
 
     def __init__(self, base_emb, classifier, novel_emb=None, classifier_n=None, device=None, bg_mode='auto',
                  tc_precision='precise', fuse=False):
