@@ -298,6 +298,12 @@ SL_API int sl_map_proto(const uint16_t *feat, const float *mask, int B, int C, i
 SL_API int sl_orth_loss(const float *rows, int Kr, const float *others, int Ko, int C,
                  float *proto_sim, float *loss, float *grad_rows, void *stream);
 
+/* (a8) OrthLoss.get_orth_loss(proto_sim), loss/criterion.py:37-43, on a proto_sim matrix [Kr,Kc] fp32 the caller
+ *   built (the model does, pspnet_pop.py:185-186,234-239): loss [1] = mean |proto_sim[i][j]| over j > i, and, unless
+ *   NULL, grad_sim [Kr,Kc] = d loss / d proto_sim (sign / count on the selected entries, 0 elsewhere).
+ */
+SL_API int sl_orth_from_sim(const float *proto_sim, int Kr, int Kc, float *loss, float *grad_sim, void *stream);
+
 /* (f-1) segmentation cross-entropy tail of OrthLoss.forward / CELoss.forward,
  *   loss/criterion.py:17-19,51-52:
  *     scale_pred = F.interpolate(pred, target.shape[1:], mode='bilinear', align_corners=True)
@@ -307,6 +313,8 @@ SL_API int sl_orth_loss(const float *rows, int Kr, const float *others, int Ko, 
  *       log-sum-exp there; the backward reads it and uses the rest for its row-reduced gradients
  *       (same buffer, same shapes).
  *   fwd: loss [1] fp32 (NaN when every pixel is ignored, like torch), n_valid [1] int64.
+ *        A target outside [0,K) that is not ignore_label makes nn.CrossEntropyLoss raise a device assert; here the
+ *        loss (and every gradient) becomes NaN and n_valid = -(number of such targets).
  *   bwd: grad_out [1] fp32 = d(objective)/d(loss); grad_logits_lr [B,K,h,w] fp32 is OVERWRITTEN.
  *   Both directions are deterministic (no floating-point atomics).
  */

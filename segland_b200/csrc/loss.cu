@@ -45,14 +45,14 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
                                                      float* __restrict__ lse_out, double* __restrict__ part_sum,
                                                      unsigned long long* __restrict__ part_cnt) {
   __shared__ double red_s[8];
-  __shared__ unsigned int red_c[8];
+  __shared__ unsigned long long red_c[8];
   // work item = (image, group of 8 output rows, block of 32 source cells); thread = (cell, row) inside it
   const int jb_n = (w + 31) / 32, yg_n = (H + 7) / 8;
   const int items = B * yg_n * jb_n;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int hw = h * w;
   double acc = 0.0;
-  unsigned int cnt = 0;
+  unsigned int cnt = 0, bad = 0;                              // bad: targets outside [0,K) that are not ignore_index
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int jb = item % jb_n, t2 = item / jb_n;
     const int yg = t2 % yg_n, b = t2 / yg_n;
@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
       if (ti >= 0) {
         acc += static_cast<double>(lse - vt);
         ++cnt;
+      } else if (t != ignore) {
+        ++bad;
       }
     }
   }
@@ -103,8 +105,13 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
   for (int o = 16; o > 0; o >>= 1) {
     acc += __shfl_xor_sync(0xffffffffu, acc, o);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
   }
-  if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = acc; red_c[threadIdx.x >> 5] = cnt; }
+  // valid count in the low 40 bits, out-of-range count above (a label map has far fewer than 2^40 pixels)
+  if ((threadIdx.x & 31) == 0) {
+    red_s[threadIdx.x >> 5] = acc;
+    red_c[threadIdx.x >> 5] = static_cast<unsigned long long>(cnt) + (static_cast<unsigned long long>(bad) << 40);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
@@ -128,8 +135,11 @@ __global__ void ce_finish_kernel(const double* __restrict__ part_sum, const unsi
     c += __shfl_xor_sync(0xffffffffu, c, o);
   }
   if (threadIdx.x == 0) {
-    loss[0] = c ? static_cast<float>(t / static_cast<double>(c)) : nanf("");   // torch: mean over zero elements = nan
-    n_valid[0] = static_cast<long long>(c);
+    const unsigned long long n_ok = c & ((1ull << 40) - 1ull), n_bad = c >> 40;
+    // nn.CrossEntropyLoss raises a device assert for a target outside [0,K) that is not ignore_index; here the loss
+    // becomes NaN and n_valid = -(number of such targets), so wrong labels cannot train silently.
+    loss[0] = (n_ok && !n_bad) ? static_cast<float>(t / static_cast<double>(n_ok)) : nanf("");   // torch: mean over zero elements = nan
+    n_valid[0] = n_bad ? -static_cast<long long>(n_bad) : static_cast<long long>(n_ok);
   }
 }
 
@@ -201,7 +211,7 @@ __global__ void __launch_bounds__(256) ce_bwd_cols_kernel(const float* __restric
   const int i = static_cast<int>(t1 % h);
   const long long bk = t1 / h;
   const long long nv = n_valid[0];
-  const float scale = nv > 0 ? grad_out[0] / static_cast<float>(nv) : 0.f;
+  const float scale = nv > 0 ? grad_out[0] / static_cast<float>(nv) : nv < 0 ? nanf("") : 0.f;   // nv < 0: bad targets
   const float* col = r_in + static_cast<size_t>(bk) * H * w + j;
   const int y_mid = cell_begin(sy, i, h, H);
   const int y_lo = i > 0 ? cell_begin(sy, i - 1, h, H) : y_mid, y_hi = cell_begin(sy, i + 1, h, H) - 1;

@@ -180,7 +180,36 @@ __global__ void __launch_bounds__(256) orth_loss_kernel(const float* __restrict_
   }
 }
 
+// OrthLoss.get_orth_loss (loss/criterion.py:37-43) on a proto_sim matrix the model already built:
+// mean |sim[i][j]| over j > i (the entries torch.triu(ones_like(sim), diagonal=1) == 1 selects), summed in row-major
+// order by one thread (<= 32 x 64 values), plus d loss / d sim = sign(sim) / M on those entries.
+__global__ void orth_from_sim_kernel(const float* __restrict__ sim, int Kr, int Kc, float* __restrict__ loss,
+                                     float* __restrict__ grad_sim) {
+  int M = 0;
+  for (int i = 0; i < Kr; ++i) M += max(0, Kc - 1 - i);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < Kr; ++i)
+      for (int j = i + 1; j < Kc; ++j) t += fabsf(sim[i * Kc + j]);
+    loss[0] = M > 0 ? t / static_cast<float>(M) : nanf("");   // torch: mean of an empty selection is nan
+  }
+  if (grad_sim == nullptr) return;
+  const float invM = M > 0 ? 1.f / static_cast<float>(M) : 0.f;
+  for (int p = threadIdx.x; p < Kr * Kc; p += blockDim.x) {
+    const int i = p / Kc, j = p - i * Kc;
+    const float v = sim[p];
+    grad_sim[p] = j > i ? (v > 0.f ? invM : (v < 0.f ? -invM : 0.f)) : 0.f;
+  }
+}
+
 }  // namespace sl
+
+extern "C" int sl_orth_from_sim(const float* proto_sim, int Kr, int Kc, float* loss, float* grad_sim, void* stream) {
+  SL_CHECK_PTR(proto_sim); SL_CHECK_PTR(loss);
+  SL_CHECK_ARG(Kr >= 1 && Kr <= SL_MAX_CLASSES && Kc >= 1 && Kc <= 2 * SL_MAX_CLASSES);
+  sl::orth_from_sim_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(proto_sim, Kr, Kc, loss, grad_sim);
+  return SL_LAUNCH_RESULT();
+}
 
 extern "C" int sl_map_proto(const uint16_t* feat, const float* mask, int B, int C, int h, int w, int H, int W,
                             float* mask_lr_ws, float* per_image, float* proto, void* stream) {

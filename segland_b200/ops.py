@@ -18,6 +18,7 @@ from ._cabi import call, int_array, ptr, ptr_array
 
 IGNORE_LABEL = 255           # dataset/oem.py:15
 MAX_CLASSES = 32
+MAX_CHANNELS = 512           # sl_pop_fg_lowres / sl_pop_head_bwd: C % 8 == 0, C <= 512
 
 
 def _stream():
@@ -32,6 +33,34 @@ def _cuda(t, dtype=None):
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.contiguous()
+
+
+def _first_cuda_device(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if torch.is_tensor(a):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, (list, tuple)):
+            for b in a:
+                if torch.is_tensor(b) and b.is_cuda:
+                    return b.device
+    return None
+
+
+def _on_input_device(fn):
+    """Run an operator with the CUDA device of its first CUDA tensor argument current: the library launches on the
+    caller's current device and stream, so a tensor on another GPU must not be launched from the wrong context.
+    CPU-only arguments keep the caller's current device (they are uploaded there)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _first_cuda_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def check_device():
@@ -63,8 +92,9 @@ class PopHead:
     [bg, base_1..Kb, novel_1..Kn] (pspnet_pop.py:159).  In ft mode the background and novel
     channels use classifier_n, base channels use classifier (pspnet_pop.py:150-157).
 
-    bg_mode: 'tc'   tcgen05 tensor-core MLP (C % 32 == 0, C <= 512; any N % 8 == 0)
-             'simt' exact fp32 CUDA-core MLP (any C % 8 == 0, C <= 768)
+    Shapes: C % 8 == 0 and 8 <= C <= 512 (the foreground kernel's limit; `PopHead.supports(C)`), any h*w.
+    bg_mode: 'tc'   tcgen05 tensor-core MLP (C % 32 == 0, 32 <= C <= 512; any N % 8 == 0)
+             'simt' exact fp32 CUDA-core MLP (any supported C)
              'auto' tc when the shape allows, else simt
     tc_precision: 'precise' (split-bf16, 5 MMA passes, ~5e-6 of fp32; the default and the mode the
              parity claims are made for) or 'balanced' (layer 2 in single-pass fp16, 3 passes, ~4e-4
@@ -88,6 +118,9 @@ class PopHead:
         self.K = self.Kb + self.Kn
         if not (1 <= self.K < MAX_CLASSES):
             raise ValueError(f'1 + Kb + Kn must be <= {MAX_CLASSES}')
+        if not self.supports(self.C):
+            raise ValueError(f'PopHead needs C % 8 == 0 and 8 <= C <= {MAX_CHANNELS} (got C={self.C}): the foreground '
+                             'and backward kernels stage 8-channel TMA boxes and keep <= 512 prototypes columns on chip')
         self.cls = self._mlp(classifier, f32)
         if self.Kn:
             if classifier_n is None:
@@ -106,8 +139,23 @@ class PopHead:
         # warps' shared-memory reads compete with the MMA operand reads -- so it is off by default.
         self.fuse = bool(fuse)
         self._plan = None
-        self._h1_ws = None
+        self._h1_ws = {}                 # (device index, stream handle) -> hidden-layer scratch of the tensor-core kernel
         self.refresh()
+
+    @staticmethod
+    def supports(C):
+        """Channel counts the head kernels take (sl_pop_fg_lowres / sl_pop_head_bwd: C % 8 == 0, C <= 512).  Of the
+        reference's backbones only seghr_pop with hr-w18 (d_model 270) and hr-w48 (720) fall outside; patch() leaves
+        those models on the reference's own forward."""
+        return C % 8 == 0 and 8 <= C <= MAX_CHANNELS
+
+    def _scratch(self, feats, need_bytes):
+        """Per-(device, stream) scratch: two streams driving one PopHead must not share hidden-layer tiles."""
+        key = (feats.device.index, _stream())
+        ws = self._h1_ws.get(key)
+        if ws is None or ws.numel() * 2 < need_bytes:
+            ws = self._h1_ws[key] = torch.empty(need_bytes // 2, dtype=torch.int16, device=feats.device)
+        return ws
 
     # -- construction helpers ------------------------------------------------------------
     def _mlp(self, ws, f32):
@@ -175,26 +223,24 @@ class PopHead:
         """Launch the tensor-core background MLP on bf16 features [B,C,h,w] into out[:,0]."""
         B, C, h, w = feats.shape
         N = h * w
-        need = _cabi.lib().sl_pop_bg_tc_ws_bytes(B, C, N)
-        if self._h1_ws is None or self._h1_ws.numel() * 2 < need or self._h1_ws.device != feats.device:
-            self._h1_ws = torch.empty(need // 2, dtype=torch.int16, device=feats.device)
         p = self._plan
-        call('sl_pop_bg_tc', ptr(feats), B, C, N, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
-             ptr(p.split[3]), ptr(p.f16[1]), ptr(p.w3_bg), self.TC_PRECISIONS[self.tc_precision],
-             ptr(self._h1_ws), ptr(out), out.shape[1], 0, _stream())
+        with torch.cuda.device(feats.device):
+            ws = self._scratch(feats, _cabi.lib().sl_pop_bg_tc_ws_bytes(B, C, N))
+            call('sl_pop_bg_tc', ptr(feats), B, C, N, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
+                 ptr(p.split[3]), ptr(p.f16[1]), ptr(p.w3_bg), self.TC_PRECISIONS[self.tc_precision],
+                 ptr(ws), ptr(out), out.shape[1], 0, _stream())
 
     def head_tc(self, feats, out):
         """One launch for the whole head (K <= 12): background MLP on tcgen05 + foreground logits from the
         same shared-memory feature tiles."""
         B, C, h, w = feats.shape
         N = h * w
-        need = _cabi.lib().sl_pop_bg_tc_ws_bytes(B, C, N)
-        if self._h1_ws is None or self._h1_ws.numel() * 2 < need or self._h1_ws.device != feats.device:
-            self._h1_ws = torch.empty(need // 2, dtype=torch.int16, device=feats.device)
         p = self._plan
-        call('sl_pop_head_tc', ptr(feats), B, C, N, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
-             ptr(p.split[3]), ptr(p.f16[1]), ptr(p.w3_bg), self.TC_PRECISIONS[self.tc_precision], ptr(p.s_hat),
-             ptr(p.alpha), ptr(p.beta), self.K, self._ch_map, ptr(self._h1_ws), ptr(out), out.shape[1], 0, _stream())
+        with torch.cuda.device(feats.device):
+            ws = self._scratch(feats, _cabi.lib().sl_pop_bg_tc_ws_bytes(B, C, N))
+            call('sl_pop_head_tc', ptr(feats), B, C, N, ptr(p.split[0]), ptr(p.split[1]), ptr(p.split[2]),
+                 ptr(p.split[3]), ptr(p.f16[1]), ptr(p.w3_bg), self.TC_PRECISIONS[self.tc_precision], ptr(p.s_hat),
+                 ptr(p.alpha), ptr(p.beta), self.K, self._ch_map, ptr(ws), ptr(out), out.shape[1], 0, _stream())
 
     def fused_ok(self, N):
         return self.K <= 12 and self._use_tc(N)
@@ -202,8 +248,9 @@ class PopHead:
     def bg_simt(self, feats, out):
         B, C, h, w = feats.shape
         p = self._plan
-        call('sl_pop_bg_simt', ptr(feats), B, C, h * w, ptr(p.W1p_t), ptr(p.W2_t), ptr(p.w3_bg),
-             ptr(out), out.shape[1], 0, _stream())
+        with torch.cuda.device(feats.device):
+            call('sl_pop_bg_simt', ptr(feats), B, C, h * w, ptr(p.W1p_t), ptr(p.W2_t), ptr(p.w3_bg),
+                 ptr(out), out.shape[1], 0, _stream())
 
     # -- forward ---------------------------------------------------------------------------
     def __call__(self, features, out=None, fg_only=False):
@@ -212,6 +259,8 @@ class PopHead:
         fg_only skips the background MLP and leaves channel 0 untouched (stage-S timing)."""
         if features.dim() != 4 or features.shape[1] != self.C:
             raise ValueError(f'features must be [B,{self.C},h,w], got {tuple(features.shape)}')
+        if not features.is_cuda:
+            features = features.to(self.device, non_blocking=True)
         feats = _cuda(features, torch.bfloat16)
         B, C, h, w = feats.shape
         N = h * w
@@ -229,12 +278,14 @@ class PopHead:
         if out is None:
             out = torch.empty(B, Ktot, h, w, dtype=torch.float32, device=feats.device)
         p = self._plan
-        st = _stream()
+        if feats.device != self.device:
+            raise ValueError(f'features live on {feats.device}, this head on {self.device}')
         if not fg_only and self.fuse and self.fused_ok(N):
             self.head_tc(feats, out)
             return out
-        call('sl_pop_fg_lowres', ptr(feats), B, C, N, ptr(p.s_hat), ptr(p.alpha), ptr(p.beta), self.K,
-             ptr(out), Ktot, self._ch_map, st)
+        with torch.cuda.device(feats.device):
+            call('sl_pop_fg_lowres', ptr(feats), B, C, N, ptr(p.s_hat), ptr(p.alpha), ptr(p.beta), self.K,
+                 ptr(out), Ktot, self._ch_map, _stream())
         if not fg_only:
             if self._use_tc(N):
                 self.bg_tc(feats, out)
@@ -324,6 +375,7 @@ class _PopHeadTrainFn(torch.autograd.Function):
                 shp(gbg[0], s1), shp(gbg[1], s2), shp(gbg[2], s3), None)
 
 
+@_on_input_device
 def pop_head_train(features, base_emb, classifier, novel_emb=None, classifier_n=None, bg_mode='auto'):
     """The head of forward_novel / forward_base with autograd (networks/pspnet_pop.py:199-219, :169-182):
     features [B,C,h,w] (any float dtype; cast to bf16 for the kernels, gradients flow back if it requires
@@ -374,6 +426,7 @@ def forward_base_train(features, mask, base_emb, classifier, criterion=None, bg_
     return criterion(preds, mask, proto_sim=torch.matmul(cls_emb, cls_emb.t()))
 
 
+@_on_input_device
 def aggregate_views(views, flips, scale=None):
     """Test-time view aggregation (spec: this repo; the reference has none).
     views [V,B,K,h,w] fp32 logits of V views of the same tiles; flips[v] in {0,1,2,3}
@@ -447,6 +500,7 @@ class WindowPlan:
         return torch.stack(out, dim=1)
 
 
+@_on_input_device
 def window_accumulate(crop_logits, plan, flips=(0,), layout='bekhw', want_count=False, out=None):
     """Stitch per-crop low-res logits into one canvas per tile (spec: this repo, see WindowPlan): the un-flipped
     crops are summed at feature resolution in entry order and divided by the overlap count -- the result is bit-equal
@@ -482,6 +536,7 @@ def window_accumulate(crop_logits, plan, flips=(0,), layout='bekhw', want_count=
 
 
 # ================================================================== dense post-processing
+@_on_input_device
 def upsample_argmax(logits, size, label=None, cm=None, ignore_label=IGNORE_LABEL, want_pred=True,
                     want_conf=False, want_probs=False, want_logits=False):
     """F.interpolate(logits, size, mode='bilinear', align_corners=True) -> argmax(dim=1) -> uint8
@@ -517,6 +572,7 @@ def upsample_argmax(logits, size, label=None, cm=None, ignore_label=IGNORE_LABEL
     return out
 
 
+@_on_input_device
 def confusion_update(cm, gt, pred, ignore_label=IGNORE_LABEL):
     """cm[gt, pred] += 1 over all pixels with gt != ignore_label (device-resident accumulation).
     gt/pred: uint8 tensors of equal shape.  Returns the number of out-of-range labels skipped
@@ -557,6 +613,7 @@ def miou_from_confusion(confusion_matrix, base_classes):
     return base, novel, total, miou_array
 
 
+@_on_input_device
 def intersectionAndUnionGPU(output, target, K, ignore_index=IGNORE_LABEL):
     """utils/pyt_utils.py:293-305, same signature, return values and side effect:
     output/target int64 CUDA tensors of equal shape; output[target == ignore] = ignore IN PLACE;
@@ -576,6 +633,7 @@ def intersectionAndUnionGPU(output, target, K, ignore_index=IGNORE_LABEL):
     return inter, uni, tgt
 
 
+@_on_input_device
 def pseudo_label(preds2_base, mask_b, n_base):
     """pspnet_pop.py:221-231: label the background (== 0) pixels of the base images' masks with
     argmax(upsample(classifier_n outputs)), shifting novel indices by n_base.  preds2_base
@@ -590,6 +648,7 @@ def pseudo_label(preds2_base, mask_b, n_base):
 
 
 # ======================================================================== prototypes / loss
+@_on_input_device
 def masked_average_pooling(feature, mask, return_per_image=False):
     """networks/pspnet.py:7-15: feature [B,C,h,w] (cast to bf16), mask [B,1,H,W] float ->
     [1,1,C] fp32: mean over images of sum(f * m_lr) / (sum(m_lr) + 1e-5), m_lr = bilinear
@@ -631,6 +690,7 @@ class _OrthLossFn(torch.autograd.Function):
         return grad * g_loss, None
 
 
+@_on_input_device
 def orth_loss(rows, others=None):
     """proto_sim + OrthLoss.get_orth_loss (loss/criterion.py:37-43) in one kernel.
     Base training (pspnet_pop.py:185-186): orth_loss(base_emb) -> sim [Kb,Kb].
@@ -640,6 +700,33 @@ def orth_loss(rows, others=None):
     if not rows.is_cuda:
         raise ValueError('orth_loss needs CUDA tensors')
     return _OrthLossFn.apply(rows, others)
+
+
+class _OrthFromSimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, proto_sim):
+        sim = proto_sim.detach().to(torch.float32).contiguous()
+        Kr, Kc = sim.shape
+        loss = torch.empty(1, dtype=torch.float32, device=sim.device)
+        grad = torch.empty_like(sim)
+        call('sl_orth_from_sim', ptr(sim), Kr, Kc, ptr(loss), ptr(grad), _stream())
+        ctx.save_for_backward(grad)
+        ctx.in_dtype = proto_sim.dtype
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g).to(ctx.in_dtype)
+
+
+@_on_input_device
+def get_orth_loss(proto_sim, is_ft=False):
+    """OrthLoss.get_orth_loss (loss/criterion.py:37-43), same arguments (is_ft is unused there too): the mean absolute
+    value of proto_sim's entries above the diagonal, one launch, differentiable w.r.t. proto_sim."""
+    if not proto_sim.is_cuda or proto_sim.dim() != 2:
+        raise ValueError('get_orth_loss takes a 2-D CUDA proto_sim matrix')
+    return _OrthFromSimFn.apply(proto_sim)
 
 
 class _SegCEFn(torch.autograd.Function):
@@ -672,6 +759,7 @@ class _SegCEFn(torch.autograd.Function):
         return grad.to(ctx.in_dtype), None, None
 
 
+@_on_input_device
 def seg_cross_entropy(preds, target, ignore_index=IGNORE_LABEL):
     """The segmentation term of OrthLoss.forward / CELoss.forward (loss/criterion.py:17-19, :51-52):
     CrossEntropyLoss(ignore_index, 'mean') of the align-corners bilinear up-sampling of `preds`
@@ -686,11 +774,10 @@ def seg_cross_entropy(preds, target, ignore_index=IGNORE_LABEL):
 
 def orth_loss_forward(preds, target, is_ft=False, proto_sim=None, aux_preds=None, ignore_index=IGNORE_LABEL, w=10.0):
     """OrthLoss.forward (loss/criterion.py:45-65) with the same arguments and loss-dict keys: the seg /
-    aux cross-entropy terms run fused; the orthogonality term reads the (tiny) proto_sim matrix the
-    model built, exactly as OrthLoss.get_orth_loss does (loss/criterion.py:37-43)."""
+    aux cross-entropy terms run fused; the orthogonality term is get_orth_loss on the (tiny) proto_sim matrix the
+    model built (sl_orth_from_sim; loss/criterion.py:37-43)."""
     seg_loss = seg_cross_entropy(preds, target, ignore_index)
-    eye_sim = torch.triu(torch.ones_like(proto_sim), diagonal=1)
-    orth = torch.abs(proto_sim[eye_sim == 1]).mean()
+    orth = get_orth_loss(proto_sim, is_ft)
     if aux_preds is not None:
         aux_loss = seg_cross_entropy(aux_preds, target, ignore_index)
         total = seg_loss + orth * w + 0.4 * aux_loss
@@ -700,6 +787,7 @@ def orth_loss_forward(preds, target, is_ft=False, proto_sim=None, aux_preds=None
 
 
 # =================================================================================== fusion
+@_on_input_device
 def fuse_logits(mats, n_lists=None, label=None, cm=None, ignore_label=IGNORE_LABEL, want_fused=False):
     """fusemat.py:42-48 for one tile (or a batch laid out as one long pixel axis): mats is the
     list of per-model logit stacks [K,H,W] (or [K,...]) fp32, summed in list order, divided by
@@ -740,6 +828,7 @@ def _tail_in(x):
     return x
 
 
+@_on_input_device
 def layernorm_tail(x, weight, bias, eps=1e-5, out=None):
     """The last line of FPN_Seg_OCR_Decoder.forward (networks/convnext_pop.py:27):
     `self.norm(feats.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)` with nn.LayerNorm(C), returned as the contiguous bf16
@@ -793,6 +882,7 @@ class ConvTail:
         with torch.cuda.device(self.device):
             call('sl_tail_conv_prepare', ptr(W), self.C_out, self.C_in, ptr(self.W_hi), ptr(self.W_lo), _stream())
 
+    @_on_input_device
     def __call__(self, x, out=None):
         x = _tail_in(x)
         B, C, h, w = x.shape
@@ -808,6 +898,7 @@ class ConvTail:
         return out
 
 
+@_on_input_device
 def sum_tail(maps, out=None):
     """`torch.stack(fpn_outs, dim=-1).sum(-1)` (networks/swin_pop.py:169-172, lsk_pop.py:163-165) as bf16 features:
     maps is the list of same-shape fp32 [B,C,h,w] FPN outputs (already interpolated), added in list order."""
@@ -820,6 +911,7 @@ def sum_tail(maps, out=None):
     return out
 
 
+@_on_input_device
 def bn_relu_tail(x, bn, relu=True, out=None):
     """Inference BatchNorm2d -> ReLU as bf16 features: the tail of _ASPP.fc (`_ConvBnReLU`, networks/deeplab_pop.py:12-29,
     61,66) and of VGGUNet.up4's DoubleConv (networks/vggunet_pop.py:19-20).  x is the convolution's fp32 output;
@@ -839,6 +931,7 @@ def bn_relu_tail(x, bn, relu=True, out=None):
     return out
 
 
+@_on_input_device
 def concat_tail(maps, out=None):
     """`torch.cat([x[0], x1, x2, x3], 1)` of HRFPN_Seg_Decoder (networks/seghr_pop.py:23-24) as bf16 features:
     maps are fp32 [B,C_m,h,w] tensors of one spatial size (already interpolated)."""

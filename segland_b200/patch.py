@@ -14,17 +14,29 @@ replaces, in place,
     features directly (`patch(tails=False)` disables it).  Training-mode calls on CUDA tensors -- `forward_novel` (`ft_pop.py:252`,
     `pspnet_pop.py:191-245`) and `forward_base` with a criterion (`train_base.py:259`, `:161-189`) -- run
     the same head with autograd (`ops.forward_novel_train` / `ops.forward_base_train`: forward kernels +
-    `sl_pop_head_bwd`), so gradients reach `novel_emb`, `classifier_n`, `classifier`, `base_emb` and the
-    decoder exactly as in the reference; `patch(train=False)` keeps training on the reference's forward.
-  * `utils.pyt_utils.get_confusion_matrix` and `utils.pyt_utils.intersectionAndUnionGPU`;
-  * `loss.criterion.OrthLoss.forward`: the seg / aux cross-entropy terms run fused with the up-sampling
-    (`loss/criterion.py:51-52,57-58`), differentiable, so training loops keep working.
-The scripts (`eval_base.py`, `eval_ft.py`, `ft_pop.py`, `train_base.py`) need no edits: they look these
-names up at call time.  `unpatch()` restores the originals.
+    `sl_pop_head_bwd`) when `patch(train=True)` is given, so gradients reach `novel_emb`, `classifier_n`,
+    `classifier`, `base_emb` and the decoder as in the reference.  It is OPT-IN: the kernels read bf16 features
+    (north_star's format), whereas the reference's `orthogonal_decompose` up-casts to fp32 under
+    `autocast(enabled=False)` (`pspnet_pop.py:95,105`), so training numerics differ at the 2^-9 level of the feature
+    rounding; the default `patch()` leaves training-mode forwards on the reference.
+  * `utils.pyt_utils.get_confusion_matrix` and `utils.pyt_utils.intersectionAndUnionGPU` -- in the module AND in
+    every already-imported module that bound them with `from utils.pyt_utils import ...` (`eval_base.py:16`,
+    `eval_ft.py:16`, `ft_pop.py`, `train_base.py` do), so the order of `patch()` and the script's imports does not
+    matter;
+  * `loss.criterion.OrthLoss.forward` and `OrthLoss.get_orth_loss`: the seg / aux cross-entropy terms run fused
+    with the up-sampling (`loss/criterion.py:51-52,57-58`) and the orthogonality term in one launch
+    (`loss/criterion.py:37-43`), both differentiable, so training loops keep working.
+Models whose channel count the head kernels do not take (`ops.PopHead.supports`: C % 8 == 0, C <= 512 -- of the
+reference's backbones only seghr_pop with hr-w18, d_model 270, and hr-w48, d_model 720) stay on the reference's own
+forward.  What `patch()` does NOT replace: the scripts' inline post-processing (`eval_base.py:168-178`,
+`eval_ft.py:168-183`: `F.interpolate` -> `.cpu()` -> `np.argmax`) is code inside the scripts' loops, not a function,
+so it keeps running as written; the fused up-sample/argmax/confusion path needs the three-line edit shown in
+INTEGRATION.md (`sweep.TileEvaluator`).  `unpatch()` restores the originals.
 """
 from __future__ import annotations
 
 import importlib
+import sys
 
 import torch
 
@@ -187,8 +199,8 @@ def _mlp_weights(seq):
 
 def _make_forward(orig_forward):
     def forward(self, img, mask=None, img_b=None, mask_b=None):
-        if not img.is_cuda:
-            return orig_forward(self, img, mask, img_b, mask_b)
+        if not img.is_cuda or not ops.PopHead.supports(self.base_emb.shape[-1]):
+            return orig_forward(self, img, mask, img_b, mask_b)      # CPU tensors, or a width the kernels do not take
         is_ft = bool(getattr(self, 'is_ft', False))
         if is_ft and self.training:                                   # forward_novel (pspnet_pop.py:191-245)
             if not _train_enabled[0] or img_b is None or mask_b is None:
@@ -210,13 +222,28 @@ def _make_forward(orig_forward):
     return forward
 
 
-_train_enabled = [True]
+_train_enabled = [False]
 _tails_enabled = [True]
 
 
-def patch(verbose=False, train=True, tails=True):
+def _rebind_everywhere(name, original, replacement, done):
+    """`from utils.pyt_utils import name` copies the binding into the importing module: rebind every such copy."""
+    for mod_name, mod in list(sys.modules.items()):
+        if mod is None or mod_name.startswith('segland_b200'):
+            continue
+        try:
+            if mod.__dict__.get(name) is original:
+                _originals.append((mod, name, original))
+                setattr(mod, name, replacement)
+                done.append(f'{mod_name}.{name}')
+        except Exception:                                              # noqa: BLE001  (lazy / odd modules)
+            continue
+
+
+def patch(verbose=False, train=False, tails=True):
     """Install the B200 path into every importable reference module.  Returns the list of patched names.
-    train=False leaves training-mode forwards (forward_novel, forward_base with a criterion) on the reference.
+    train=True also routes training-mode forwards (forward_novel, forward_base with a criterion) through the head
+    kernels + sl_pop_head_bwd (bf16 features: opt-in, see the module docstring).
     tails=False keeps the decoders entirely stock (fp32 features, cast by the head)."""
     ops.check_device()
     _train_enabled[0] = bool(train)
@@ -237,9 +264,7 @@ def patch(verbose=False, train=True, tails=True):
         pu = importlib.import_module('utils.pyt_utils')
         for fn in ('get_confusion_matrix', 'intersectionAndUnionGPU'):
             if getattr(pu, fn, None) is not getattr(ops, fn):
-                _originals.append((pu, fn, getattr(pu, fn)))
-                setattr(pu, fn, getattr(ops, fn))
-                done.append(f'utils.pyt_utils.{fn}')
+                _rebind_everywhere(fn, getattr(pu, fn), getattr(ops, fn), done)
     except Exception:                                                  # noqa: BLE001
         pass
     try:
@@ -254,6 +279,15 @@ def patch(verbose=False, train=True, tails=True):
             _originals.append((crit.OrthLoss, 'forward', _orig_orth))
             crit.OrthLoss.forward = orth_forward
             done.append('loss.criterion.OrthLoss.forward')
+
+            def get_orth_loss(self, proto_sim, is_ft=False):
+                if not proto_sim.is_cuda:
+                    return _orig_get(self, proto_sim, is_ft)
+                return ops.get_orth_loss(proto_sim, is_ft)
+            _orig_get = crit.OrthLoss.get_orth_loss
+            _originals.append((crit.OrthLoss, 'get_orth_loss', _orig_get))
+            crit.OrthLoss.get_orth_loss = get_orth_loss
+            done.append('loss.criterion.OrthLoss.get_orth_loss')
     except Exception:                                                  # noqa: BLE001
         pass
     if verbose:

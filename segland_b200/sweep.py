@@ -97,6 +97,62 @@ def prototype_mean_all_reduce_(per_image_sum, count, group=None):
     return per_image_sum / count.to(per_image_sum.dtype)
 
 
+def novel_prototypes_from_support(features, masks, class_of_tile, n_novel, group=None):
+    """Novel-class prototypes from a (sharded) support set -- north_star's "masked-average-pooling prototype
+    generation and novel-prototype update from the 5-shot support set" (spec: this repo; the reference defines
+    masked_average_pooling, networks/pspnet.py:7-15, but learns novel_emb by SGD).
+    features [n,C,h,w] bf16 and masks [n,1,H,W] float are THIS rank's support tiles, class_of_tile [n] (int64, values
+    in [0,n_novel)) their novel-class indices.  Every image lives wholly on one rank (MAP is a mean of per-image
+    ratios); ranks exchange per-class sums of per-image prototypes and shot counts in one all-reduce each.
+    Returns novel_emb [n_novel,C] fp32 (rows of classes without a shot anywhere are zero)."""
+    dev = features.device
+    C = features.shape[1]
+    sums = torch.zeros(n_novel, C, dtype=torch.float32, device=dev)
+    cnt = torch.zeros(n_novel, dtype=torch.float32, device=dev)
+    if features.shape[0] > 0:
+        _, per_image = ops.masked_average_pooling(features, masks, return_per_image=True)
+        idx = class_of_tile.to(dev, torch.int64)
+        sums.index_add_(0, idx, per_image)
+        cnt.index_add_(0, idx, torch.ones_like(idx, dtype=torch.float32))
+    all_reduce_sum_(sums, group)
+    all_reduce_sum_(cnt, group)
+    return sums / cnt.clamp_min(1.0).unsqueeze(1)
+
+
+class GraphedTileStep:
+    """TileEvaluator.step captured once as a CUDA graph for a fixed batch shape (the reference's operating point is
+    one tile per forward, scripts/evaluate_oem.sh:16-17, eval_ft.py:162-167): a replay costs one graph launch instead
+    of four kernel launches plus their host-side set-up, so the per-tile latency is the kernels' own time.
+    `run(features, labels)` copies the batch into the graph's static input buffers (device-to-device, or H2D from
+    pinned memory) and replays; outputs are the graph's static tensors (valid until the next run)."""
+
+    def __init__(self, evaluator: TileEvaluator, feat_shape, want_pred=True, with_labels=True, **kw):
+        self.ev = evaluator
+        dev = evaluator.head.device
+        B = int(feat_shape[0])
+        self.feats = torch.zeros(tuple(feat_shape), dtype=torch.bfloat16, device=dev)
+        self.labels = torch.full((B, *evaluator.out_size), ops.IGNORE_LABEL, dtype=torch.uint8, device=dev) \
+            if with_labels else None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            cm_before = evaluator.cm.clone()
+            for _ in range(2):                                   # warm-up: allocations, lazy module loads, plan caches
+                evaluator.step(self.feats, self.labels, want_pred=want_pred, **kw)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.out = evaluator.step(self.feats, self.labels, want_pred=want_pred, **kw)
+            evaluator.cm.copy_(cm_before)                        # the warm-up calls counted ignore-only labels: nothing, but be exact
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def run(self, features, labels=None):
+        self.feats.copy_(features, non_blocking=True)
+        if labels is not None and self.labels is not None:
+            self.labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 class LogitBank:
     """Device-resident replacement for the .mat round trip between evaluation and fusion:
     eval_base.py:168,190-191 up-samples every tile's logits to full resolution and dumps them with

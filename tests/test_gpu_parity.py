@@ -452,8 +452,14 @@ def test_patch_installs_into_reference_shaped_modules(ops, golden):
     saved = {k: sys.modules.get(k) for k in ('networks', 'networks.pspnet_pop', 'utils', 'utils.pyt_utils')}
     sys.modules.update({'networks': nets, 'networks.pspnet_pop': mod, 'utils': utils, 'utils.pyt_utils': pu})
     try:
-        done = slp.patch()
+        done = slp.patch()                                               # default: training forwards stay on the reference
         assert 'networks.pspnet_pop.GFSS_Model.forward' in done and 'utils.pyt_utils.get_confusion_matrix' in done
+        probe = GFSS_Model().cuda().train()
+        z1 = torch.zeros(1, C, 8, 8, device='cuda')
+        assert probe(z1, torch.zeros(1, 64, 64, dtype=torch.long, device='cuda'), z1,
+                     torch.zeros(1, 64, 64, dtype=torch.long, device='cuda')) == 'reference path'
+        slp.unpatch()
+        done = slp.patch(train=True)
         model = GFSS_Model().cuda().eval()
         feats = bf16_from_bits(z['feats_bf16_bits']).cuda()
         out = model(feats)

@@ -168,13 +168,27 @@ def test_patch_installs_into_the_real_reference_when_present(monkeypatch):
     from segland_b200 import ops, patch as slp
     gen_golden.import_reference()
     monkeypatch.setattr(ops, 'check_device', lambda: None)
+    # a script that bound the metric functions with `from utils.pyt_utils import ...` BEFORE patch() ran
+    # (eval_base.py:16, eval_ft.py:16): its copies must be rebound too, and restored by unpatch()
+    import types
+    import utils.pyt_utils as pu
+    orig_cm, orig_iu = pu.get_confusion_matrix, pu.intersectionAndUnionGPU
+    script = types.ModuleType('fake_eval_script')
+    exec('from utils.pyt_utils import get_confusion_matrix, intersectionAndUnionGPU', script.__dict__)
+    sys.modules['fake_eval_script'] = script
     try:
         done = slp.patch()
         for name in slp.MODEL_MODULES:
             assert f'networks.{name}.GFSS_Model.forward' in done, name
         for name in ('utils.pyt_utils.get_confusion_matrix', 'utils.pyt_utils.intersectionAndUnionGPU',
-                     'loss.criterion.OrthLoss.forward'):
-            assert name in done
+                     'loss.criterion.OrthLoss.forward', 'loss.criterion.OrthLoss.get_orth_loss',
+                     'fake_eval_script.get_confusion_matrix', 'fake_eval_script.intersectionAndUnionGPU'):
+            assert name in done, name
+        assert script.get_confusion_matrix is ops.get_confusion_matrix is pu.get_confusion_matrix
+        assert script.intersectionAndUnionGPU is ops.intersectionAndUnionGPU
+        assert slp._train_enabled == [False]                          # training-mode forwards are opt-in
+        # widths outside the kernels' range stay on the reference (hr-w18: 270, hr-w48: 720); hr-w32's 480 is in
+        assert not ops.PopHead.supports(270) and not ops.PopHead.supports(720) and ops.PopHead.supports(480)
         import networks.pspnet_pop as pp
         st = synth.make_head_state(64, 7, 4, seed=1)
         model = gen_golden.build_ref_model(pp, st).eval()
@@ -208,6 +222,8 @@ def test_patch_installs_into_the_real_reference_when_present(monkeypatch):
         assert 'bottleneck.0.weight' in psp.state_dict() and not any('_sl' in k for k in psp.state_dict())
     finally:
         slp.unpatch()
+        assert script.get_confusion_matrix is orig_cm and pu.intersectionAndUnionGPU is orig_iu
+        sys.modules.pop('fake_eval_script', None)
         sys.path[:] = [p for p in sys.path if p != ref]
         for k in [k for k in sys.modules if k.split('.')[0] in ('networks', 'loss', 'utils', 'timm', 'engine', 'dataset')]:
             sys.modules.pop(k, None)
