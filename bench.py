@@ -263,7 +263,7 @@ class LaunchCounter:
     launches at the benchmarked shapes, from the sources; checked against the ncu launch list under profiles/)."""
     PER_CALL = {'sl_pop_prepare': 3, 'sl_pop_fg_lowres': 1, 'sl_pop_bg_tc': 1, 'sl_pop_bg_simt': 1, 'sl_pop_head_tc': 2,
                 'sl_upsample_argmax': 1, 'sl_confusion': 1, 'sl_views_reduce': 1, 'sl_window_accumulate': 1,
-                'sl_map_proto': 3, 'sl_orth_loss': 1, 'sl_orth_from_sim': 1, 'sl_fuse_argmax': 1, 'sl_pseudo_label': 1,
+                'sl_map_proto': 3, 'sl_orth_loss': 1, 'sl_orth_from_sim': 1, 'sl_fuse_argmax': 1, 'sl_fuse_argmax_tiles': 0, 'sl_pseudo_label': 1,
                 'sl_inter_union': 3}
 
     def __init__(self):
@@ -773,20 +773,20 @@ def run_config4(rank, world, dev, peaks, args):
     preds = []
 
     def sweep_once():
-        for t in range(n_local):
-            ops.fuse_logits([m[t] for m in mats], label=labels[t], cm=cm)
+        if n_local:
+            ops.fuse_logits_sweep(mats, labels=labels, cm=cm)
         sweep.all_reduce_sum_(cm)
 
     reps = max(3, args.steps // 4)
     t_sweep = max_over_ranks(time_loop(sweep_once, reps, warm=1), world, dev)
     byts = n_local * (M * K * 4 + 2) * TILE * TILE
-    t_local = time_loop(lambda: [ops.fuse_logits([m[t] for m in mats], label=labels[t], cm=cm) for t in range(n_local)], reps, warm=1)
+    t_local = time_loop(lambda: ops.fuse_logits_sweep(mats, labels=labels, cm=cm), reps, warm=1) if n_local else 1.0
     gbs = byts / t_local / 1e9
     miou = ops.miou_from_confusion(cm, KB)[2]
     del mats, labels, preds
     torch.cuda.empty_cache()
     return {'workload': f'{n_tiles} tiles x M=3 x [12,1024,1024] fp32 logits + u8 labels, sharded by rank ({n_local} on rank 0), '
-                        'one sl_fuse_argmax launch per tile (sum, /M, argmax, confusion), one int64 all-reduce per sweep',
+                        'one sl_fuse_argmax_tiles call per sweep (per tile: sum, /M, argmax, confusion), one int64 all-reduce per sweep',
             'tiles_per_s': n_tiles / t_sweep, 'ms_per_sweep': 1e3 * t_sweep, 'scaling': 'strong (80 tiles shared by all ranks)',
             'roofline': {'bound': 'hbm', 'kernel': 'fuse_argmax_kernel (sl_fuse_argmax)', 'achieved': gbs, 'peak': peaks['hbm_gbs'],
                          'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'bytes_per_sweep_rank0': byts},

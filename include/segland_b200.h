@@ -338,6 +338,13 @@ SL_API int sl_fuse_argmax(const float *const *mats_host, int M, int K, long long
                    uint8_t *pred, float *fused,
                    const uint8_t *label, int ignore_label, long long *cm, void *stream);
 
+/* A whole sweep in one call: mats_host[m] is [T,K,HW] (model m, all tiles, tile-major); pred [T,HW], fused [T,K,HW]
+ * or NULL, label [T,HW] or NULL; every tile is fused exactly as by sl_fuse_argmax, cm accumulates over the sweep.
+ */
+SL_API int sl_fuse_argmax_tiles(const float *const *mats_host, int M, int T, int K, long long HW, int divisor,
+                         uint8_t *pred, float *fused, const uint8_t *label, int ignore_label, long long *cm,
+                         void *stream);
+
 /* ---------------------------------------------------------------------------
  * (f-4) decoder tails: the last operators of the reference's decoders, emitting the head's bf16 NCHW features
  *   directly, so the fp32 feature tensor makes no round trip through HBM between decoder and head (the

@@ -35,6 +35,7 @@ _SIGNATURES = {
     'sl_inter_union': [_P, _P, c_longlong, c_int, c_int, _P, _P, _P, _P, _P],
     'sl_map_proto': [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     'sl_orth_loss': [_P, c_int, _P, c_int, c_int, _P, _P, _P, _P],
+    'sl_fuse_argmax_tiles': [POINTER(_P), c_int, c_int, c_int, c_longlong, c_int, _P, _P, _P, c_int, _P, _P],
     'sl_orth_from_sim': [_P, c_int, c_int, _P, _P, _P],
     'sl_fuse_argmax': [POINTER(_P), c_int, c_int, c_longlong, c_int, _P, _P, _P, c_int, _P, _P],
     'sl_upsample_ce_fwd': [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P],

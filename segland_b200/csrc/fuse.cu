@@ -109,3 +109,25 @@ extern "C" int sl_fuse_argmax(const float* const* mats_host, int M, int K, long 
 #undef SL_FUSE_LAUNCH
   return SL_LAUNCH_RESULT();
 }
+
+// A sweep of T tiles in one call: mats_host[m] is model m's stack for all tiles, [T,K,HW] (tile-major, as an eval sweep
+// writes it); tile t is fused exactly as sl_fuse_argmax fuses one tile (one launch per tile, queued back to back from C,
+// so the host cost per tile is a kernel launch, not a Python call).
+extern "C" int sl_fuse_argmax_tiles(const float* const* mats_host, int M, int T, int K, long long HW, int divisor,
+                                    uint8_t* pred, float* fused, const uint8_t* label, int ignore_label, long long* cm,
+                                    void* stream) {
+  SL_CHECK_PTR(mats_host);
+  SL_CHECK_ARG(T >= 0 && M >= 1 && M <= SL_MAX_FUSE);
+  const float* tile_ptrs[SL_MAX_FUSE];
+  for (int t = 0; t < T; ++t) {
+    for (int m = 0; m < M; ++m) {
+      SL_CHECK_PTR(mats_host[m]);
+      tile_ptrs[m] = mats_host[m] + static_cast<size_t>(t) * K * HW;
+    }
+    const int rc = sl_fuse_argmax(tile_ptrs, M, K, HW, divisor, pred + static_cast<size_t>(t) * HW,
+                                  fused ? fused + static_cast<size_t>(t) * K * HW : nullptr,
+                                  label ? label + static_cast<size_t>(t) * HW : nullptr, ignore_label, cm, stream);
+    if (rc != 0) return rc;
+  }
+  return SL_OK;
+}

@@ -31,52 +31,71 @@ __device__ __forceinline__ void cover_range(const int* o, int n, int len, int p,
     if (o[g] <= p && p < o[g] + len) { if (g < lo) lo = g; hi = g; }
 }
 
-// One thread = 4 consecutive canvas columns of one row of one (b, k) plane.  The covering entries are walked as one
-// flat index and loaded four at a time (independent loads, then added in entry order), so a thread keeps four
-// requests in flight at ~40 registers.  VEC: ox % 4 == 0, wc % 4 == 0, w % 4 == 0 and 16-byte aligned pointers.
+// overlap count -> exact division: powers of two multiply by the (exact) reciprocal, bit-identical to the IEEE
+// division and ~10 instructions cheaper; other counts divide
+__device__ __forceinline__ float div_count(float a, float cnt, float inv, bool pow2) { return pow2 ? a * inv : a / cnt; }
+
+// One thread = 4 consecutive canvas columns of one row, for PC = 4 consecutive class planes of one image: the covering
+// window ranges are worked out once, the (gy, gx, view) loops are nested (no divisions, mostly warp-uniform) and every
+// entry issues four independent 16-byte loads, one per plane; per plane the entries are added in index order.
+// VEC: ox % 4 == 0, wc % 4 == 0, w % 4 == 0 and 16-byte aligned pointers.
 template <bool VEC>
 __global__ void __launch_bounds__(256) window_accumulate_kernel(
     const float* __restrict__ crops, long long stride_e, long long stride_b, int K, int hc, int wc,
     const __grid_constant__ WinPlan pl, int h, int w, float* __restrict__ canvas, float* __restrict__ count) {
+  constexpr int PC = 4;
   const int wq = (w + 3) >> 2;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= wq * h) return;
   const int y = q / wq, x0 = (q - y * wq) * 4;
-  const int p = blockIdx.y, b = p / K, k = p - b * K;
+  const int kchunks = (K + PC - 1) / PC;
+  const int b = blockIdx.y / kchunks, k0 = (blockIdx.y - b * kchunks) * PC;
+  const int nk = min(PC, K - k0);
   int gy_lo, gy_hi;
   cover_range(pl.oy, pl.ny, hc, y, gy_lo, gy_hi);
-  const int nyc = max(0, gy_hi - gy_lo + 1);
-  const float* plane = crops + static_cast<size_t>(b) * stride_b + static_cast<size_t>(k) * hc * wc;
-  float* dst = canvas + (static_cast<size_t>(p) * h + y) * w + x0;
-  constexpr int NB = 4;                                          // entries loaded per batch
+  const int chw = hc * wc;
+  const float* img = crops + static_cast<size_t>(b) * stride_b + static_cast<size_t>(k0) * chw;
+  float* dst = canvas + ((static_cast<size_t>(b) * K + k0) * h + y) * w + x0;
+  const size_t plane_out = static_cast<size_t>(h) * w;
+  const bool first_plane = blockIdx.y == 0;
   if (VEC) {
     int gx_lo, gx_hi;
     cover_range(pl.ox, pl.nx, wc, x0, gx_lo, gx_hi);             // origins and widths are multiples of 4: one range
-    const int nxc = max(0, gx_hi - gx_lo + 1), nxv = nxc * pl.V, n = nyc * nxv;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i0 = 0; i0 < n; i0 += NB) {
-      float4 t[NB];
-      bool fl[NB];
+    float4 acc[PC];
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int i = min(i0 + j, n - 1);
-        const int iy = i / nxv, r = i - iy * nxv, ix = r / pl.V, v = r - ix * pl.V;
-        const int gy = gy_lo + iy, gx = gx_lo + ix, f = pl.flip[v];
-        const int ry = y - pl.oy[gy], rx = x0 - pl.ox[gx];
-        const int ys = (f & 2) ? hc - 1 - ry : ry, xs = (f & 1) ? wc - 4 - rx : rx;
-        fl[j] = f & 1;
-        t[j] = ld_stream_f4(plane + static_cast<size_t>((gy * pl.nx + gx) * pl.V + v) * stride_e + static_cast<size_t>(ys) * wc + xs);
-      }
+    for (int i = 0; i < PC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+      const int ry = y - pl.oy[gy];
+      for (int gx = gx_lo; gx <= gx_hi; ++gx) {
+        const int rx = x0 - pl.ox[gx];
+        const float* ent = img + static_cast<size_t>((gy * pl.nx + gx) * pl.V) * stride_e;
+        for (int v = 0; v < pl.V; ++v, ent += stride_e) {
+          const int f = pl.flip[v];
+          const int ys = (f & 2) ? hc - 1 - ry : ry, xs = (f & 1) ? wc - 4 - rx : rx;
+          const float* src = ent + ys * wc + xs;
+          float4 t[PC];
 #pragma unroll
-      for (int j = 0; j < NB; ++j)
-        if (i0 + j < n) {
-          acc.x += fl[j] ? t[j].w : t[j].x; acc.y += fl[j] ? t[j].z : t[j].y;
-          acc.z += fl[j] ? t[j].y : t[j].z; acc.w += fl[j] ? t[j].x : t[j].w;
+          for (int i = 0; i < PC; ++i) t[i] = ld_stream_f4(src + min(i, nk - 1) * chw);
+          if (f & 1) {
+#pragma unroll
+            for (int i = 0; i < PC; ++i) { acc[i].x += t[i].w; acc[i].y += t[i].z; acc[i].z += t[i].y; acc[i].w += t[i].x; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < PC; ++i) { acc[i].x += t[i].x; acc[i].y += t[i].y; acc[i].z += t[i].z; acc[i].w += t[i].w; }
+          }
         }
+      }
     }
-    const float cnt = static_cast<float>(n);
-    __stcs(reinterpret_cast<float4*>(dst), make_float4(acc.x / cnt, acc.y / cnt, acc.z / cnt, acc.w / cnt));
-    if (count != nullptr && p == 0) *reinterpret_cast<float4*>(count + static_cast<size_t>(y) * w + x0) = make_float4(cnt, cnt, cnt, cnt);
+    const int n = max(0, gy_hi - gy_lo + 1) * max(0, gx_hi - gx_lo + 1) * pl.V;
+    const float cnt = static_cast<float>(n), inv = 1.f / cnt;
+    const bool pow2 = (n & (n - 1)) == 0;
+#pragma unroll
+    for (int i = 0; i < PC; ++i)
+      if (i < nk)
+        __stcs(reinterpret_cast<float4*>(dst + i * plane_out),
+               make_float4(div_count(acc[i].x, cnt, inv, pow2), div_count(acc[i].y, cnt, inv, pow2),
+                           div_count(acc[i].z, cnt, inv, pow2), div_count(acc[i].w, cnt, inv, pow2)));
+    if (count != nullptr && first_plane) *reinterpret_cast<float4*>(count + static_cast<size_t>(y) * w + x0) = make_float4(cnt, cnt, cnt, cnt);
   } else {
 #pragma unroll
     for (int jx = 0; jx < 4; ++jx) {
@@ -84,25 +103,32 @@ __global__ void __launch_bounds__(256) window_accumulate_kernel(
       if (x >= w) break;
       int gx_lo, gx_hi;
       cover_range(pl.ox, pl.nx, wc, x, gx_lo, gx_hi);
-      const int nxc = max(0, gx_hi - gx_lo + 1), nxv = nxc * pl.V, n = nyc * nxv;
-      float acc = 0.f;
-      for (int i0 = 0; i0 < n; i0 += NB) {
-        float t[NB];
+      float acc[PC];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const int i = min(i0 + j, n - 1);
-          const int iy = i / nxv, r = i - iy * nxv, ix = r / pl.V, v = r - ix * pl.V;
-          const int gy = gy_lo + iy, gx = gx_lo + ix, f = pl.flip[v];
-          const int ry = y - pl.oy[gy], rx = x - pl.ox[gx];
-          const int ys = (f & 2) ? hc - 1 - ry : ry, xs = (f & 1) ? wc - 1 - rx : rx;
-          t[j] = __ldg(plane + static_cast<size_t>((gy * pl.nx + gx) * pl.V + v) * stride_e + static_cast<size_t>(ys) * wc + xs);
+      for (int i = 0; i < PC; ++i) acc[i] = 0.f;
+      for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+        const int ry = y - pl.oy[gy];
+        for (int gx = gx_lo; gx <= gx_hi; ++gx) {
+          const int rx = x - pl.ox[gx];
+          const float* ent = img + static_cast<size_t>((gy * pl.nx + gx) * pl.V) * stride_e;
+          for (int v = 0; v < pl.V; ++v, ent += stride_e) {
+            const int f = pl.flip[v];
+            const int ys = (f & 2) ? hc - 1 - ry : ry, xs = (f & 1) ? wc - 1 - rx : rx;
+            const float* src = ent + ys * wc + xs;
+            float t[PC];
+#pragma unroll
+            for (int i = 0; i < PC; ++i) t[i] = __ldg(src + min(i, nk - 1) * chw);
+#pragma unroll
+            for (int i = 0; i < PC; ++i) acc[i] += t[i];
+          }
         }
-#pragma unroll
-        for (int j = 0; j < NB; ++j) if (i0 + j < n) acc += t[j];
       }
+      const int n = max(0, gy_hi - gy_lo + 1) * max(0, gx_hi - gx_lo + 1) * pl.V;
       const float cnt = static_cast<float>(n);
-      dst[jx] = acc / cnt;
-      if (count != nullptr && p == 0) count[static_cast<size_t>(y) * w + x] = cnt;
+#pragma unroll
+      for (int i = 0; i < PC; ++i)
+        if (i < nk) dst[i * plane_out + jx] = acc[i] / cnt;
+      if (count != nullptr && first_plane) count[static_cast<size_t>(y) * w + x] = cnt;
     }
   }
 }
@@ -136,9 +162,9 @@ extern "C" int sl_window_accumulate(const float* crops, long long stride_e, long
   }
   const long long quads = static_cast<long long>(h) * ((w + 3) / 4);
   SL_CHECK_ARG(quads < (1ll << 31));
-  const int planes = B * K;
-  SL_CHECK_ARG(planes <= 65535);
-  const dim3 grid(static_cast<unsigned>((quads + 255) / 256), static_cast<unsigned>(planes));
+  const long long groups = static_cast<long long>(B) * ((K + 3) / 4);       // (image, chunk of 4 class planes)
+  SL_CHECK_ARG(groups <= 65535 && static_cast<long long>(hc) * wc * K < (1ll << 31));
+  const dim3 grid(static_cast<unsigned>((quads + 255) / 256), static_cast<unsigned>(groups));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (vec) sl::window_accumulate_kernel<true><<<grid, 256, 0, st>>>(crops, stride_e, stride_b, K, hc, wc, pl, h, w, canvas, count);
   else sl::window_accumulate_kernel<false><<<grid, 256, 0, st>>>(crops, stride_e, stride_b, K, hc, wc, pl, h, w, canvas, count);

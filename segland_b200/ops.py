@@ -809,6 +809,31 @@ def fuse_logits(mats, n_lists=None, label=None, cm=None, ignore_label=IGNORE_LAB
     return (pred, fused) if want_fused else pred
 
 
+@_on_input_device
+def fuse_logits_sweep(stacks, n_lists=None, labels=None, cm=None, ignore_label=IGNORE_LABEL, want_fused=False):
+    """fusemat.py:37-48 for a whole sweep: stacks is the list of per-model tensors [T,K,H,W] fp32 (what each model's
+    eval sweep produced, in fusion-list order); every tile is fused exactly as `fuse_logits` fuses one -- sum in list
+    order, / n_lists, first-maximum argmax -- in one C-ABI call.  labels [T,H,W] uint8 + cm int64 [K,K] accumulate the
+    confusion matrix of the fused maps.  Returns pred uint8 [T,H,W] (and the fused stacks when want_fused)."""
+    stacks = [_cuda(m, torch.float32) for m in stacks]
+    if stacks[0].dim() != 4:
+        raise ValueError('stacks must be [T,K,H,W] tensors')
+    T, K, H, W = stacks[0].shape
+    for m in stacks:
+        if tuple(m.shape) != (T, K, H, W):
+            raise ValueError('all stacks must share one shape')
+    dev = stacks[0].device
+    pred = torch.empty(T, H, W, dtype=torch.uint8, device=dev)
+    fused = torch.empty(T, K, H, W, dtype=torch.float32, device=dev) if want_fused else None
+    if cm is not None:
+        labels = _cuda(labels, torch.uint8)
+        if tuple(labels.shape) != (T, H, W):
+            raise ValueError(f'labels must be [T,H,W]={T, H, W}')
+    call('sl_fuse_argmax_tiles', ptr_array(stacks), len(stacks), T, K, H * W, int(len(stacks) if n_lists is None else n_lists),
+         ptr(pred), ptr(fused), ptr(labels) if cm is not None else None, int(ignore_label), ptr(cm), _stream())
+    return (pred, fused) if want_fused else pred
+
+
 # ============================================================== decoder tails (SURVEY 8 f-4)
 def _tail_out(x, C_out, out):
     B, _, h, w = x.shape

@@ -336,6 +336,57 @@ def test_fuse_model_counts_and_divisor(ops, M):
     assert np.array_equal(cm.cpu().numpy().astype(np.float64), ref_ops.ref_confusion(labels.numpy(), ref_pred, 12))
 
 
+def test_fuse_sweep_matches_per_tile_fusion(ops):
+    """ops.fuse_logits_sweep (one C-ABI call for a sweep of tiles, BASELINE configs[4]) == fusemat.py:42-48 tile by tile."""
+    T, M, K, H, W = 5, 3, 12, 64, 48
+    g = torch.Generator().manual_seed(4)
+    stacks = [torch.randn(T, K, H, W, generator=g) for _ in range(M)]
+    labels = synth.make_labels(T, H, W, K, seed=4, coarse=8)
+    cm = torch.zeros(K, K, dtype=torch.int64, device='cuda')
+    pred, fused = ops.fuse_logits_sweep([m.cuda() for m in stacks], labels=labels, cm=cm, want_fused=True)
+    cm_ref = np.zeros((K, K))
+    for t in range(T):
+        ref_pred, ref_fused = ref_ops.ref_fuse([m[t].numpy() for m in stacks])
+        assert np.array_equal(pred[t].cpu().numpy(), ref_pred) and np.array_equal(fused[t].cpu().numpy(), ref_fused)
+        cm_ref += ref_ops.ref_confusion(labels[t].numpy(), ref_pred, K)
+    assert np.array_equal(cm.cpu().numpy().astype(np.float64), cm_ref)
+    assert ops.fuse_logits_sweep([m[:0].cuda() for m in stacks]).shape == (0, H, W)          # an empty shard is legal
+
+
+def test_get_orth_loss_matches_reference_formula(ops, golden):
+    """OrthLoss.get_orth_loss (loss/criterion.py:37-43) on the model-built proto_sim, forward and gradient."""
+    z = golden('orth_pseudo')
+    for key, want in (('sim_b', 'orth_b'), ('sim_f', 'orth_f')):      # proto_sim and loss the reference produced
+        sim = torch.from_numpy(z[key]).float()
+        assert abs(ops.get_orth_loss(sim.cuda()).item() - float(z[want])) <= 1e-6 * max(1.0, abs(float(z[want])))
+        a = sim.clone().cuda().requires_grad_(True)
+        loss = ops.get_orth_loss(a)
+        loss.backward()
+        b = sim.clone().requires_grad_(True)
+        ref = ref_ops.ref_orth_loss(b)
+        ref.backward()
+        assert abs(loss.item() - ref.item()) <= 1e-6 * max(1.0, abs(ref.item()))
+        assert torch.allclose(a.grad.cpu(), b.grad, rtol=0, atol=1e-7)
+    sim = torch.randn(7, 7, generator=torch.Generator().manual_seed(1))
+    assert abs(ops.get_orth_loss(sim.cuda()).item() - ref_ops.ref_orth_loss(sim).item()) <= 1e-6
+
+
+def test_ce_out_of_range_target_poisons_the_loss(ops):
+    """nn.CrossEntropyLoss raises a device assert for a target outside [0,K) that is not ignore_index; the fused
+    cross-entropy makes the loss and gradients NaN instead of silently dropping the pixel."""
+    lg = torch.randn(1, 5, 8, 8, device='cuda', requires_grad=True)
+    tgt = torch.randint(0, 5, (1, 32, 32), device='cuda')
+    good = ops.seg_cross_entropy(lg, tgt)
+    assert torch.isfinite(good)
+    tgt[0, 3, 3] = 255                                                    # ignore_index: fine
+    assert torch.isfinite(ops.seg_cross_entropy(lg, tgt))
+    tgt[0, 4, 4] = 7                                                      # outside [0,5), not ignored
+    bad = ops.seg_cross_entropy(lg, tgt)
+    assert torch.isnan(bad)
+    bad.backward()
+    assert torch.isnan(lg.grad).all()
+
+
 # ------------------------------------------------------- whole path, configs[0] and full size
 def test_eval_two_512_tiles_vs_oracle(ops):
     """BASELINE configs[0]: PSPNet-POP base eval on 2 synthetic 512x512 OEM-shaped tiles."""
