@@ -173,3 +173,18 @@ def test_tails_match_reference_decoders(golden):
     ref = t('ln_c96_out')
     exact, d = ref_ops.bf16_ulp_report(ref.to(torch.bfloat16), ref)
     assert exact == 1.0 and d.max().item() <= 0.5
+
+
+def test_full_size_head_matches_reference(golden):
+    """The oracle at configs[1] size against the reference's own full-tile logits / prediction / confusion matrix
+    (oracle/gen_golden_full.py); features come from the seeded generator and are checked by digest."""
+    import hashlib
+    from oracle import gen_golden_full
+    z = golden('head_base_c512_full')
+    kind, _, head_seed, data_seed = gen_golden_full.CASES[0]
+    st, labels, feats = gen_golden_full.make_case(kind, head_seed, data_seed)
+    assert hashlib.sha256(feats.view(torch.int16).numpy().tobytes()).hexdigest() == str(z[f'{kind}_feat_sha256'])
+    pred, cm, logits = ref_ops.ref_eval_tile(feats.float(), labels.numpy(), st.base_emb, None, st.cls, None, (1024, 1024),
+                                             st.n_classes)
+    assert np.array_equal(logits.numpy(), z[f'{kind}_logits'])
+    assert np.array_equal(pred, z[f'{kind}_pred']) and np.array_equal(cm, z[f'{kind}_cm'])
