@@ -67,7 +67,25 @@ def main():
                 (model.decoder(model.backbone.base_forward(torch.randn(2, 3, 256, 256, device='cuda'))))
         model.eval()
         g = torch.Generator().manual_seed(1)
-        images = [torch.randn(1, 3, 1024, 1024, generator=g) for _ in range(n_tiles)]
+        # smooth random images (random init + white noise gives spatially constant features: nothing to segment)
+        images = [F.interpolate(torch.randn(1, 3, 24, 24, generator=g), size=(1024, 1024), mode='bicubic', align_corners=False)
+                  + 0.1 * torch.randn(1, 3, 1024, 1024, generator=g) for _ in range(n_tiles)]
+        # a head whose arg-max varies over the tile: prototypes = centred decoder features of random pixels of tile 0,
+        # classifier(s) = the trained-like construction of segland_b200.synth on those prototypes
+        from segland_b200 import synth
+        with torch.no_grad():
+            f0 = model.decoder(model.backbone.base_forward(images[0].cuda()))[0].flatten(1).cpu()      # [512, N]
+        f0 = f0 - f0.mean(1, keepdim=True)
+        pick = torch.randperm(f0.shape[1], generator=g)[:11]
+        protos = torch.nn.functional.normalize(f0[:, pick].t().contiguous(), dim=-1)
+        st = synth.make_trained_like_state(512, 7, 4 if is_ft else 0, seed=3, base=protos[:7], novel=protos[7:] if is_ft else None)
+        with torch.no_grad():
+            model.base_emb.copy_(st.base_emb)
+            for seq, ws in ((model.classifier, st.cls),) + (((model.classifier_n, st.cls_n),) if is_ft else ()):
+                seq[0].weight.copy_(ws[0].view(512, 512, 1, 1)); seq[2].weight.copy_(ws[1].view(512, 512, 1, 1))
+                seq[4].weight.copy_(ws[2].view(1, 512, 1, 1))
+            if is_ft:
+                model.novel_emb.copy_(st.novel_emb)
         labels = [torch.randint(0, K, (1, 1024, 1024), generator=g).to(torch.uint8) for _ in range(n_tiles)]
         name = 'pspnet_pop/resnet50 ' + ('is_ft=True (forward_all, 12 classes)' if is_ft else 'is_ft=False (forward_base, 8 classes)')
         print(f'=== {name}, {n_tiles} tiles of 1024^2')
@@ -118,7 +136,9 @@ def main():
             print(f'--- {tag}')
             print(f'patched: {len(done)} names; head logits rel-to-max vs reference (fp32 features) {rel(O, R):.2e}, '
                   f'vs reference on bf16-rounded features {rel(O, Bf):.2e}; bf16 rounding alone moves the reference by {rel(Bf, R):.2e}')
-            print(f'arg-max agreement at 1024^2: vs reference {100 * agree_ref:.4f} %, vs reference on bf16 features {100 * agree_bf:.4f} %')
+            hist = torch.bincount(up(R).flatten(), minlength=K).float()
+            print(f'arg-max agreement at 1024^2: vs reference {100 * agree_ref:.4f} %, vs reference on bf16 features {100 * agree_bf:.4f} % '
+                  f'(reference class shares: {[round(v, 3) for v in (hist / hist.sum()).tolist()]})')
             print(f'mIoU (random labels, so ~chance): reference {miou(cm_ref):.6f}, reference/bf16 {miou(cm_bf):.6f}, patched {miou(cm_our):.6f}, '
                   f'fused path {miou(cm_fused):.6f}; |cm_patched - cm_bf16ref|_1 = {np.abs(cm_our - cm_bf).sum():.0f} of {cm_bf.sum():.0f} px')
             med = lambda v: 1e3 * float(np.median(v))

@@ -60,7 +60,7 @@ def make_head_state(C, Kb=KB_OEM, Kn=0, seed=1234, proto_scale=1.0):
     return HeadState(base, novel, cls, cls_n)
 
 
-def make_trained_like_state(C, Kb=KB_OEM, Kn=0, seed=1234, n_bg_units=64, bg_gain=5.0, noise=0.02):
+def make_trained_like_state(C, Kb=KB_OEM, Kn=0, seed=1234, n_bg_units=64, bg_gain=5.0, noise=0.02, base=None, novel=None):
     """A head whose argmax is meaningful on make_features() tiles, so a sweep has a non-trivial mIoU
     (random-init MLPs give alpha_k of random sign and mIoU ~ chance).  Construction: hidden units
     0..K-1 of layer 1 are the normalised prototypes, so a foreground vector p*s_k lights exactly unit
@@ -70,8 +70,8 @@ def make_trained_like_state(C, Kb=KB_OEM, Kn=0, seed=1234, n_bg_units=64, bg_gai
     jitter so no weight is exactly zero.  In ft mode classifier_n is built the same way (classes Kb..K-1
     and the background) and classifier handles the base classes."""
     gen = torch.Generator().manual_seed(seed)
-    base = _orthogonal(gen, Kb, C)
-    novel = _orthogonal(gen, Kn, C) if Kn else None
+    base = _orthogonal(gen, Kb, C) if base is None else base.clone()       # given prototypes: any [Kb,C] / [Kn,C] rows
+    novel = (_orthogonal(gen, Kn, C) if novel is None else novel.clone()) if Kn else None
     protos = base if novel is None else torch.cat([base, novel], 0)
     K = protos.shape[0]
     s_hat = F.normalize(protos, p=2, dim=-1)
