@@ -662,12 +662,12 @@ def run_config2(rank, world, dev, peaks, args):
     return {'workload': '20 support tiles [512,128,128] bf16 + fp32 masks [1,1024,1024], 4 novel classes x 5 shots, sharded '
                         f'by rank ({n_local} on rank 0); MAP -> per-class sums + counts all-reduce (NCCL) -> orthogonal loss',
             'updates_per_s': 1.0 / t_update, 'support_tiles_per_s': n_support / t_update, 'ms_per_update': 1e3 * t_update,
-            'scaling': 'strong (20 tiles shared by all ranks; the update is latency-bound: 3 MAP launches, 2 all-reduces, '
+            'scaling': 'strong (20 tiles shared by all ranks; the update is latency-bound: 3 MAP launches, one all-reduce, '
                        'index_add, orth loss)',
             'roofline': {'bound': 'hbm', 'kernel': 'sl_map_proto (3 launches)', 'achieved': gbs, 'peak': peaks['hbm_gbs'],
                          'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'ms': 1e3 * t_map,
                          'bytes_per_launch': map_bytes, 'note': 'rank 0 shard, features + fp32 mask per tile'},
-            'collective': 'torch.distributed all_reduce (NCCL), 8 KB + 16 B per update' if world > 1 else 'none (1 rank)'}
+            'collective': 'one torch.distributed all_reduce (NCCL) of 4 x 513 fp32 per update' if world > 1 else 'none (1 rank)'}
 
 
 def run_config3(rank, world, dev, peaks, args):
@@ -807,7 +807,7 @@ def main():
     ap.add_argument('--latency-tiles', type=int, default=1000, help='single-tile latency sample (0 = skip)')
     ap.add_argument('--cpu-tiles', type=int, default=8, help='tiles in the bounded CPU-baseline sample (0 = skip)')
     ap.add_argument('--eager-tiles', type=int, default=16, help='tiles in the eager-PyTorch-on-GPU baseline (0 = skip)')
-    ap.add_argument('--c3-tiles', type=int, default=8, help='tiles per step in configs[3]')
+    ap.add_argument('--c3-tiles', type=int, default=16, help='tiles per step in configs[3]')
     ap.add_argument('--c4-tiles', type=int, default=80, help='tiles in the configs[4] fusion sweep (all ranks together)')
     ap.add_argument('--skip-configs', action='store_true', help='only the headline workload (profiler runs)')
     ap.add_argument('--bg-mode', default='auto', choices=['auto', 'tc', 'simt'])

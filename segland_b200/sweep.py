@@ -103,20 +103,17 @@ def novel_prototypes_from_support(features, masks, class_of_tile, n_novel, group
     masked_average_pooling, networks/pspnet.py:7-15, but learns novel_emb by SGD).
     features [n,C,h,w] bf16 and masks [n,1,H,W] float are THIS rank's support tiles, class_of_tile [n] (int64, values
     in [0,n_novel)) their novel-class indices.  Every image lives wholly on one rank (MAP is a mean of per-image
-    ratios); ranks exchange per-class sums of per-image prototypes and shot counts in one all-reduce each.
+    ratios); ranks exchange per-class sums of per-image prototypes and shot counts in ONE all-reduce.
     Returns novel_emb [n_novel,C] fp32 (rows of classes without a shot anywhere are zero)."""
     dev = features.device
     C = features.shape[1]
-    sums = torch.zeros(n_novel, C, dtype=torch.float32, device=dev)
-    cnt = torch.zeros(n_novel, dtype=torch.float32, device=dev)
+    acc = torch.zeros(n_novel, C + 1, dtype=torch.float32, device=dev)      # [per-class prototype sums | shot counts]
     if features.shape[0] > 0:
         _, per_image = ops.masked_average_pooling(features, masks, return_per_image=True)
         idx = class_of_tile.to(dev, torch.int64)
-        sums.index_add_(0, idx, per_image)
-        cnt.index_add_(0, idx, torch.ones_like(idx, dtype=torch.float32))
-    all_reduce_sum_(sums, group)
-    all_reduce_sum_(cnt, group)
-    return sums / cnt.clamp_min(1.0).unsqueeze(1)
+        acc.index_add_(0, idx, torch.cat([per_image, torch.ones_like(per_image[:, :1])], dim=1))
+    all_reduce_sum_(acc, group)                                             # one collective: 4 x 513 fp32 = 8 KB
+    return acc[:, :C] / acc[:, C:].clamp_min(1.0)
 
 
 class GraphedTileStep:
