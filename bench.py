@@ -277,9 +277,9 @@ class LaunchCounter:
         def counted(name, *a):
             rc = counter._orig(name, *a)
             k = counter.PER_CALL.get(name, 0)
-            # sl_upsample_argmax: a second launch (confusion over label, pred) when a confusion matrix is requested
-            # and the counting is not fused into the interpolation kernel (argument 13 = cm)
-            if name == 'sl_upsample_argmax' and a[13] is not None and os.environ.get('SL_POST_PRUNE', '0') != '1':
+            # sl_upsample_argmax: a second launch (confusion over label, pred) only when SL_POST_FUSED_CM=0 asks for
+            # the counting outside the interpolation kernel (argument 13 = cm)
+            if name == 'sl_upsample_argmax' and a[13] is not None and os.environ.get('SL_POST_FUSED_CM', '') == '0':
                 k += 1
             counter.n += k
             counter.by_name[name] = counter.by_name.get(name, 0) + k

@@ -38,9 +38,10 @@ extern "C" {
  * They are read ONCE per process (no getenv on the launch path); sl_env_reload() re-reads them.
  *   SL_POST_PRUNE=1     sl_upsample_argmax's prediction-only path on the per-cell class-pruning kernel (post_prune.cu)
  *                       instead of the row-cached kernel: identical results; see profiles/ for when it pays
- *   SL_TC_PAIR=0        background MLP on the single-CTA tcgen05 kernel instead of the cta_group::2 pair kernel
- *   SL_TC_PAIR=1        pair kernel with one (A, B) operand pair per MMA pass and pipeline stage (the schedule before the
- *                       de-duplicated stages; 4-10 % slower)
+ *   SL_TC_PAIR=0        (builds with -DSL_AB_VARIANTS only) background MLP on the single-CTA tcgen05 kernel instead of
+ *                       the cta_group::2 pair kernel
+ *   SL_TC_PAIR=1        (builds with -DSL_AB_VARIANTS only) pair kernel with one (A, B) operand pair per MMA pass and
+ *                       pipeline stage (the schedule before the de-duplicated stages; 4-10 % slower)
  *   SL_TC_SMALL=0       C <= 128: streaming kernel instead of the weights-resident narrow-head kernel
  *   SL_PREP_SPLIT=1     sl_pop_prepare as five separate launches instead of three
  *   SL_POST_FUSED_CM=1/0 sl_upsample_argmax counts the confusion matrix inside the interpolation kernel (1) or in a

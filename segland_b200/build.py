@@ -40,15 +40,28 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, ab_variants=None):
+    """ab_variants (or SL_AB_VARIANTS=1 in the environment): also compile the superseded kernel generations kept for
+    A/B measurements (profiles/scripts/pair_probe.py, pair_dedup_probe.py); the product build leaves them out."""
     nvcc = os.environ.get('NVCC', 'nvcc')
+    if ab_variants is None:
+        ab_variants = os.environ.get('SL_AB_VARIANTS', '') == '1'
+    flags = NVCC_FLAGS + (['-DSL_AB_VARIANTS'] if ab_variants else [])
+    stamp = os.path.join(OBJ_DIR, 'ab_variants' if ab_variants else 'product')
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    if not os.path.exists(stamp):                 # switching flavour: rebuild everything
+        force = True
+        for f in ('ab_variants', 'product'):
+            if os.path.exists(os.path.join(OBJ_DIR, f)):
+                os.remove(os.path.join(OBJ_DIR, f))
+        open(stamp, 'w').close()
     os.makedirs(OBJ_DIR, exist_ok=True)
     hdrs = _deps()
     jobs = []
     for src in sources():
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + '.o')
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            cmd = [nvcc] + flags + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
             jobs.append(cmd)
 
     def run(cmd):
@@ -69,5 +82,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
+    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv,
+                 ab_variants=True if '--ab-variants' in sys.argv else None)
     print(path)

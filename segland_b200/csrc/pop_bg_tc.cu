@@ -964,7 +964,11 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
   }
   // cta_group::2 variant for the background-only launch: a CTA pair shares every weight tile
   {
+#ifdef SL_AB_VARIANTS
     const int pe = sl::env().tc_pair;
+#else
+    const int pe = -1;                                               // SL_TC_PAIR is honoured only by -DSL_AB_VARIANTS builds
+#endif
     const bool use_pair = KQ == 0 && p.m_tiles >= 2 && pe != 0;
     if (use_pair) {
       // each CTA loads half of B: box rows = NT/2
@@ -976,8 +980,12 @@ static int launch_head_tc(const uint16_t* feat, int B, int C, int N, const uint1
       if ((rc = make_map(&m.w2l, W2_lo, 2, wdims, wbox))) return rc;
       const int pair_tiles = (p.m_tiles + 1) / 2;
       int pgrid = 2 * (pair_tiles < sl::num_sms() / 2 ? pair_tiles : sl::num_sms() / 2);
+#ifdef SL_AB_VARIANTS
       const bool dedup = pe != 1;                                    // SL_TC_PAIR=1: the older one-(A, B)-pair-per-pass stages
       auto kern = dedup ? bg_pair_kernel<true> : bg_pair_kernel<false>;
+#else
+      auto kern = bg_pair_kernel<true>;                              // the product kernel; A/B variants need -DSL_AB_VARIANTS
+#endif
       cudaError_t pe2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
       if (pe2 != cudaSuccess) return static_cast<int>(pe2);
       kern<<<pgrid, THREADS, P_SMEM_BYTES, st>>>(m, p);

@@ -783,7 +783,10 @@ extern "C" int sl_upsample_argmax(const float* logits_lr, int B, int K, int h, i
         return SL_LAUNCH_RESULT();
       }
     }
-    const bool split_cm = cm != nullptr && pred != nullptr && fused_env != 1;
+    // Row-cached kernel: counting inside the interpolation kernel (per-thread vertical run lengths) is now the default:
+    // re-measured in round 2 on both coherent and random predictions it is 3-5 % cheaper than a second launch over
+    // (label, pred) (profiles/r2_post_probe.txt); SL_POST_FUSED_CM=0 restores the second launch.
+    const bool split_cm = cm != nullptr && pred != nullptr && fused_env == 0;
     const uint8_t* k_label = split_cm ? nullptr : label;
     unsigned long long* k_cm = split_cm ? nullptr : cmu;
     const int rc = big ? sl::launch_rows<256>(logits_lr, B, K, h, w, H, W, rows, sy, sx, k_label, ignore_label, pred, conf,

@@ -199,19 +199,115 @@ class LogitBank:
         return pred
 
 
+# --------------------------------------------------------------------------- GeoTIFF label maps (no rasterio needed)
+GEO_TAGS = (33550, 33922, 34264, 34735, 34736, 34737, 42113)   # ModelPixelScale, ModelTiepoint, ModelTransformation,
+#                                                                 GeoKeyDirectory, GeoDoubleParams, GeoAsciiParams, GDAL_NODATA
+_TIFF_TYPES = {1: ('B', 1), 2: ('c', 1), 3: ('H', 2), 4: ('I', 4), 5: ('II', 8), 12: ('d', 8), 16: ('Q', 8)}
+
+
+def read_geotiff_tags(path):
+    """The georeferencing tags of a (classic, non-Big) TIFF as {tag: (tiff_type, values)}: what eval_base.py:180-188
+    takes from `rasterio.open(input).profile` (CRS + affine transform + nodata), read straight from the image file
+    directory so a tile's georeferencing can be copied onto its label map without rasterio."""
+    import struct
+    with open(path, 'rb') as f:
+        data = f.read()
+    bo = {b'II': '<', b'MM': '>'}[data[:2]]
+    if struct.unpack(bo + 'H', data[2:4])[0] != 42:
+        raise ValueError('not a classic TIFF')
+    off = struct.unpack(bo + 'I', data[4:8])[0]
+    n = struct.unpack(bo + 'H', data[off:off + 2])[0]
+    out = {}
+    for i in range(n):
+        tag, typ, cnt, val = struct.unpack(bo + 'HHI4s', data[off + 2 + 12 * i: off + 14 + 12 * i])
+        if tag not in GEO_TAGS or typ not in _TIFF_TYPES:
+            continue
+        fmt, size = _TIFF_TYPES[typ]
+        raw = val[:size * cnt] if size * cnt <= 4 else data[struct.unpack(bo + 'I', val)[0]:][:size * cnt]
+        if typ == 2:
+            out[tag] = (typ, raw.decode('ascii', 'replace'))
+        else:
+            out[tag] = (typ, list(struct.unpack(bo + fmt[0] * (cnt * len(fmt)), raw)))
+    return out
+
+
+def write_geotiff(path, pred_u8, palette=None, geo_tags=None, nodata=0):
+    """A single-band uint8 GeoTIFF of a label map, as eval_base.py:180-188 / eval_ft.py:184-194 write with rasterio
+    (`driver GTiff, dtype uint8, count 1, nodata 0`, `write_colormap(1, colormap)`): baseline little-endian TIFF, one
+    uncompressed strip, palette colour when `palette` (flat [r,g,b]*256 list or {index: (r,g,b[,a])} as the scripts'
+    `colormap`) is given, the georeferencing tags of `read_geotiff_tags` copied through, GDAL_NODATA = nodata."""
+    import struct
+    import numpy as np
+    a = np.ascontiguousarray(pred_u8, dtype=np.uint8)
+    if a.ndim != 2:
+        raise ValueError('write_geotiff takes one [H,W] uint8 map')
+    H, W = a.shape
+    entries = []                                     # (tag, type, count, packed bytes)
+    add = lambda tag, typ, vals: entries.append((tag, typ, len(vals), struct.pack('<' + _TIFF_TYPES[typ][0][0] * len(vals), *vals)))
+    add(256, 4, [W]); add(257, 4, [H]); add(258, 3, [8]); add(259, 3, [1])
+    add(262, 3, [3 if palette is not None else 1])
+    add(277, 3, [1]); add(278, 4, [H]); add(279, 4, [H * W]); add(284, 3, [1]); add(339, 3, [1])
+    if palette is not None:
+        lut = np.zeros((3, 256), dtype=np.uint16)
+        if isinstance(palette, dict):
+            for k, rgb in palette.items():
+                lut[:, int(k)] = [int(c) * 257 for c in rgb[:3]]
+        else:
+            flat = list(palette) + [0] * (768 - len(palette))
+            lut[:] = (np.asarray(flat[:768], dtype=np.uint16).reshape(256, 3).T) * 257
+        add(320, 3, lut.reshape(-1).tolist())
+    tags = dict(geo_tags or {})
+    if nodata is not None and 42113 not in tags:
+        tags[42113] = (2, str(nodata) + '\0')
+    for tag, (typ, vals) in tags.items():
+        if typ == 2:
+            b = vals.encode('ascii') if isinstance(vals, str) else bytes(vals)
+            entries.append((tag, 2, len(b), b))
+        else:
+            add(tag, typ, vals)
+    entries.sort(key=lambda e: e[0])
+    n = len(entries) + 1                              # + StripOffsets
+    ifd_off = 8
+    extra_off = ifd_off + 2 + 12 * n + 4
+    extra = b''
+    packed = []
+    for tag, typ, cnt, b in entries:
+        if len(b) <= 4:
+            packed.append((tag, typ, cnt, b.ljust(4, b'\0')))
+        else:
+            if len(extra) % 2:
+                extra += b'\0'
+            packed.append((tag, typ, cnt, struct.pack('<I', extra_off + len(extra))))
+            extra += b
+    if len(extra) % 2:
+        extra += b'\0'
+    strip_off = extra_off + len(extra)
+    packed.append((273, 4, 1, struct.pack('<I', strip_off)))
+    packed.sort(key=lambda e: e[0])
+    with open(path, 'wb') as f:
+        f.write(b'II' + struct.pack('<HI', 42, ifd_off) + struct.pack('<H', n))
+        for tag, typ, cnt, v in packed:
+            f.write(struct.pack('<HHI', tag, typ, cnt) + v)
+        f.write(struct.pack('<I', 0) + extra)
+        f.write(a.tobytes())
+
+
 class AsyncMapWriter:
     """Asynchronous uint8 label-map writer (eval_base.py:180-188 writes one GeoTIFF per tile and
     fusemat.py:49-53 one palettised PNG per tile, both synchronously inside the eval loop).  `submit` copies the
     device map into a pinned staging slot on a side stream and returns at once; worker threads wait for the
-    copy's event, encode a 'P'-mode PNG with the class palette (as fusemat.py does) and recycle the slot.
-    rasterio/GeoTIFF is not available in this image; georeferencing stays with the caller."""
+    copy's event, encode a 'P'-mode PNG with the class palette (as fusemat.py does) or, with fmt='tif', the palettised
+    single-band GeoTIFF of eval_base.py:180-188 (`write_geotiff`; pass the input tile's `read_geotiff_tags(...)` to
+    `submit` to carry its georeferencing), and recycle the slot."""
 
-    def __init__(self, out_dir, shape, palette=None, slots=8, workers=2):
+    def __init__(self, out_dir, shape, palette=None, slots=8, workers=2, fmt='png'):
         import os
         import queue
         import threading
         os.makedirs(out_dir, exist_ok=True)
-        self.out_dir, self.palette = out_dir, palette
+        if fmt not in ('png', 'tif'):
+            raise ValueError("fmt must be 'png' or 'tif'")
+        self.out_dir, self.palette, self.fmt = out_dir, palette, fmt
         self._free, self._work = queue.Queue(), queue.Queue()
         self._stream = torch.cuda.Stream()
         for _ in range(slots):
@@ -228,19 +324,22 @@ class AsyncMapWriter:
             item = self._work.get()
             if item is None:
                 return
-            name, buf, event = item
+            name, buf, event, geo = item
             try:
                 event.synchronize()
-                img = Image.fromarray(buf.numpy(), 'P')
-                if self.palette is not None:
-                    img.putpalette(self.palette)
-                img.save(os.path.join(self.out_dir, name + '.png'))
+                if self.fmt == 'tif':
+                    write_geotiff(os.path.join(self.out_dir, name + '.tif'), buf.numpy(), self.palette, geo)
+                else:
+                    img = Image.fromarray(buf.numpy(), 'P')
+                    if self.palette is not None:
+                        img.putpalette(self.palette)
+                    img.save(os.path.join(self.out_dir, name + '.png'))
             except Exception as e:                                  # noqa: BLE001  (reported by close())
                 self._errors.append((name, e))
             finally:
                 self._free.put(buf)
 
-    def submit(self, name, pred_u8):
+    def submit(self, name, pred_u8, geo_tags=None):
         """pred_u8: uint8 [H,W] device tensor.  Blocks only when every staging slot is in flight."""
         buf = self._free.get()
         self._stream.wait_stream(torch.cuda.current_stream())
@@ -249,7 +348,7 @@ class AsyncMapWriter:
             event = torch.cuda.Event()
             event.record(self._stream)
         pred_u8.record_stream(self._stream)
-        self._work.put((name, buf, event))
+        self._work.put((name, buf, event, geo_tags))
 
     def close(self):
         for _ in self._threads:

@@ -1007,6 +1007,16 @@ def test_async_map_writer_roundtrip(ops, tmp_path):
         img = Image.open(tmp_path / f'tile_{i}.png')
         assert img.mode == 'P' and np.array_equal(np.array(img), maps[i].cpu().numpy())
         assert img.getpalette()[:36] == palette
+    # GeoTIFF form (eval_base.py:180-188), georeferencing tags copied through per tile
+    geo = {33550: (12, [0.5, 0.5, 0.0]), 33922: (12, [0, 0, 0, 1000.0, 2000.0, 0.0])}
+    wt = sweep.AsyncMapWriter(str(tmp_path), (64, 96), palette=palette, slots=2, workers=2, fmt='tif')
+    for i in range(6):
+        wt.submit(f'geo_{i}', maps[i], geo_tags=geo)
+    wt.close()
+    for i in range(6):
+        img = Image.open(tmp_path / f'geo_{i}.tif')
+        assert img.mode == 'P' and np.array_equal(np.array(img), maps[i].cpu().numpy())
+        assert tuple(img.tag_v2[33922])[3:5] == (1000.0, 2000.0) and img.getpalette()[:36] == palette
 
 
 @pytest.mark.parametrize('C,Kn,hw,B', [(512, 0, (15, 8), 2), (96, 4, (9, 8), 3), (192, 4, (30, 28), 1), (64, 0, (1, 8), 1),

@@ -227,3 +227,31 @@ def test_patch_installs_into_the_real_reference_when_present(monkeypatch):
         sys.path[:] = [p for p in sys.path if p != ref]
         for k in [k for k in sys.modules if k.split('.')[0] in ('networks', 'loss', 'utils', 'timm', 'engine', 'dataset')]:
             sys.modules.pop(k, None)
+
+
+def test_geotiff_writer_roundtrip(tmp_path):
+    """sweep.write_geotiff / read_geotiff_tags (eval_base.py:180-188's rasterio GTiff write, without rasterio): pixels,
+    palette, georeferencing tags and nodata survive a round trip through an independent TIFF reader (PIL)."""
+    from PIL import Image
+    a = (np.arange(100 * 72) % 12).astype(np.uint8).reshape(100, 72)
+    geo = {33550: (12, [0.5, 0.5, 0.0]), 33922: (12, [0, 0, 0, 500000.0, 4100000.0, 0.0]),
+           34735: (3, [1, 1, 0, 3, 1024, 0, 1, 1, 1025, 0, 1, 1, 3072, 0, 1, 32633]), 34737: (2, 'WGS 84 / UTM zone 33N|\0')}
+    colormap = {i: (i * 20, 255 - i * 20, i * 3, 255) for i in range(12)}        # the scripts' `colormap` dict form
+    path = str(tmp_path / 'tile.tif')
+    sweep.write_geotiff(path, a, colormap, geo)
+    im = Image.open(path)
+    assert im.mode == 'P' and im.size == (72, 100) and np.array_equal(np.array(im), a)
+    pal = im.getpalette()
+    assert pal[3:6] == [20, 235, 3] and pal[33:36] == [220, 35, 33]
+    assert tuple(im.tag_v2[33550]) == (0.5, 0.5, 0.0) and im.tag_v2[33922][3:5] == (500000.0, 4100000.0)
+    assert im.tag_v2[34735][-1] == 32633 and im.tag_v2[42113].rstrip('\0') == '0'
+    back = sweep.read_geotiff_tags(path)
+    for tag, (typ, vals) in geo.items():
+        assert back[tag][0] == typ and (list(back[tag][1]) == list(vals) if typ != 2 else back[tag][1] == vals)
+    # a second generation written from the tags read back is identical byte for byte
+    sweep.write_geotiff(str(tmp_path / 'again.tif'), a, colormap, {k: v for k, v in back.items() if k != 42113})
+    assert open(path, 'rb').read() == open(str(tmp_path / 'again.tif'), 'rb').read()
+    # grey-scale (no palette) and odd sizes
+    sweep.write_geotiff(str(tmp_path / 'g.tif'), a[:33, :17], None, None, nodata=None)
+    g = Image.open(str(tmp_path / 'g.tif'))
+    assert g.mode == 'L' and np.array_equal(np.array(g), a[:33, :17])
