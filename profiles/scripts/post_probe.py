@@ -35,13 +35,15 @@ def main():
         T = 32
         st = synth.make_trained_like_state(C, Kb, Kn, seed=1234)
         K = st.n_classes
-        labels_h = synth.make_labels(8, 1024, 1024, K, seed=1234)
-        feats = synth.make_features(labels_h, st, stride, seed=1234).to(dev).repeat(4, 1, 1, 1)
-        labels = labels_h.to(dev).repeat(4, 1, 1)
         head = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n)
-        lg = head(feats)
-        rnd = torch.randn_like(lg)
-        for data_name, x in (('trained-like logits', lg), ('pure randn logits', rnd)):
+        data = []
+        for coarse in (32, 8):                       # 32-pixel label regions (the bench workload) and 128-pixel regions
+            labels_h = synth.make_labels(8, 1024, 1024, K, seed=1234, coarse=coarse)
+            feats = synth.make_features(labels_h, st, stride, seed=1234).to(dev).repeat(4, 1, 1, 1)
+            data.append((f'trained-like, {1024 // coarse}-px regions', head(feats), labels_h.to(dev).repeat(4, 1, 1)))
+            del feats
+        data.append(('pure randn logits', torch.randn_like(data[0][1]), data[0][2]))
+        for data_name, x, labels in data:
             for prune in (1, 0):
                 for fused in (None, 0, 1):
                     _cabi.set_env(SL_POST_PRUNE=prune, SL_POST_FUSED_CM=fused)
@@ -49,7 +51,7 @@ def main():
                     t = timeit(lambda: ops.upsample_argmax(x, (1024, 1024), label=labels, cm=cm))
                     t2 = timeit(lambda: ops.upsample_argmax(x, (1024, 1024)))
                     byts = T * (K * hw * hw * 4 + 2 * 1024 * 1024)
-                    print(f'{name:32s} {data_name:20s} prune={prune} fused_cm={fused}: pred+cm {t * 1e3:7.3f} ms '
+                    print(f'{name:32s} {data_name:32s} prune={prune} fused_cm={fused}: pred+cm {t * 1e3:7.3f} ms '
                           f'({byts / t / 1e9:6.0f} GB/s = {100 * byts / t / 1e9 / PEAK:4.1f}% HBM)  pred only {t2 * 1e3:7.3f} ms')
         _cabi.set_env(SL_POST_PRUNE=None, SL_POST_FUSED_CM=None)
     # ---- sliding-window aggregation: 1024^2 tile, stride-4 model (canvas 256^2), 512-px crops at stride 256 (3x3),

@@ -32,6 +32,7 @@ constexpr int PR_THREADS = 256;
 constexpr int PR_ROWS = 5;            // output rows per work item
 constexpr int PR_MAX_BAND = 10;       // rows per band (up-sampling factors below 10)
 constexpr uint32_t PR_NF = 0x80000000u;
+constexpr int PR_BUCKETS = 6;         // survivor counts 2, 3, 4, 5-6, >= 7, and non-finite cells
 
 __device__ __forceinline__ float2 pr_mul2(const float2 a, const float2 b) {
   float2 d;
@@ -64,16 +65,27 @@ struct CmRun {
   unsigned int cnt;
   __device__ __forceinline__ void flush(unsigned int* hist) { if (cnt) atomicAdd(&hist[bin], cnt); cnt = 0; }
   __device__ __forceinline__ void add_word(unsigned int* hist, uint32_t lw, uint32_t pw, int K, int ignore_label) {
-    const uint32_t l0 = lw & 0xffu, p0 = pw & 0xffu;
-    if (lw == l0 * 0x01010101u && pw == p0 * 0x01010101u) {
-      if (static_cast<int>(l0) == ignore_label || static_cast<int>(l0) >= K) return;
-      const int b = static_cast<int>(l0) * K + static_cast<int>(p0);
-      if (b == bin) { cnt += 4u; return; }
-      flush(hist);
-      bin = b; cnt = 4u;
-      return;
+    // common cases without a per-byte loop: the four predictions are equal and the labels are one class, possibly with
+    // ignore_label bytes sprinkled in (OEM tiles: ~1 % ignore pixels)
+    const uint32_t p0 = pw & 0xffu;
+    if (pw == p0 * 0x01010101u) {
+      const uint32_t ign = __vcmpeq4(lw, static_cast<uint32_t>(ignore_label & 0xff) * 0x01010101u);   // 0xff per ignored byte
+      if (ign == 0xffffffffu) return;
+      const uint32_t l0 = (lw >> ((__ffs(~ign) - 1) & 24)) & 0xffu;        // first non-ignored label
+      if ((((lw ^ (l0 * 0x01010101u)) & ~ign) == 0u)) {
+        if (static_cast<int>(l0) >= K) return;
+        const unsigned int n = 4u - (__popc(ign) >> 3);
+        const int b = static_cast<int>(l0) * K + static_cast<int>(p0);
+        if (b == bin) { cnt += n; return; }
+        flush(hist);
+        bin = b; cnt = n;
+        return;
+      }
     }
-#pragma unroll
+    slow(hist, lw, pw, K, ignore_label);
+  }
+  // mixed word: per byte, kept out of line so that the (many, unrolled) call sites stay small
+  __device__ __noinline__ void slow(unsigned int* hist, uint32_t lw, uint32_t pw, int K, int ignore_label) {
     for (int j = 0; j < 4; ++j) {
       const int l = static_cast<int>((lw >> (8 * j)) & 0xffu), p = static_cast<int>((pw >> (8 * j)) & 0xffu);
       if (l == ignore_label || l >= K) continue;
@@ -132,6 +144,62 @@ __device__ __forceinline__ uint32_t survivor_mask(int K, Get get) {
   return S;
 }
 
+// One work item of the queued-strip phase: 4 output columns x nr <= PR_ROWS rows, the surviving classes of `todo` evaluated in
+// ascending index order with the same arithmetic as the row-cached kernel: top = fma(l0x, a, l1x*b) per source row,
+// value = fma(l1y, bot, l0y*top).  NF: a non-finite value is around -> NaN-aware compare (np.argmax: first maximum,
+// NaN counts as maximal).  Returns the four class indices of every row, one byte each.
+template <bool NF>
+__device__ __forceinline__ void eval_item(int nr, const float* __restrict__ raw, int K, int ncols_alloc, uint32_t todo,
+                                          const int (&xi)[4], const int (&xn)[4], const float (&xl0)[4],
+                                          const float (&xl1)[4], const float* __restrict__ rl0,
+                                          const float* __restrict__ rl1, uint32_t (&idx)[PR_ROWS]) {
+  constexpr int NR = PR_ROWS;                    // rows >= nr are computed on the (valid) weights of row nr-1 and never stored
+  float best[NR][4];
+  int ro[NR];                                    // row weight index (shared-memory broadcast loads in the loops)
+#pragma unroll
+  for (int r = 0; r < NR; ++r) { ro[r] = min(r, nr - 1); idx[r] = 0u; }
+  auto L0 = [&](int r) { return rl0[ro[r]]; };
+  auto L1 = [&](int r) { return rl1[ro[r]]; };
+  bool first = !NF;
+  if (NF) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) best[r][j] = -INFINITY;
+  }
+  while (todo) {
+    const int k = __ffs(todo) - 1;
+    todo &= todo - 1u;
+    const uint32_t kk = static_cast<uint32_t>(k) * 0x01010101u;
+    const float* t = raw + k * ncols_alloc;
+    const float* u = t + K * ncols_alloc;
+    float top[4], bot[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      top[j] = __fmaf_rn(xl0[j], t[xi[j]], __fmul_rn(xl1[j], t[xn[j]]));
+      bot[j] = __fmaf_rn(xl0[j], u[xi[j]], __fmul_rn(xl1[j], u[xn[j]]));
+    }
+    if (first) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        idx[r] = kk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) best[r][j] = __fmaf_rn(L1(r), bot[j], __fmul_rn(L0(r), top[j]));
+      }
+      first = false;
+    } else {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v = __fmaf_rn(L1(r), bot[j], __fmul_rn(L0(r), top[j]));
+          const bool take = NF ? (v > best[r][j] || (v != v && best[r][j] == best[r][j])) : (v > best[r][j]);
+          if (take) { best[r][j] = v; idx[r] = (idx[r] & ~(0xffu << (8 * j))) | (kk & (0xffu << (8 * j))); }
+        }
+    }
+  }
+}
+
 // Persistent kernel: a CTA walks work units u = blockIdx.x, blockIdx.x + gridDim.x, ...; unit = (image, band, column
 // chunk of 1024 pixels).  The source rows of unit i+1 are copied global -> shared (cp.async) while unit i is processed;
 // the confusion histogram lives in shared memory for the whole kernel and is flushed once per CTA.
@@ -143,13 +211,13 @@ __global__ void __launch_bounds__(PR_THREADS, 3) upsample_prune_kernel(
     unsigned long long* __restrict__ cm, int ncols_alloc, int n_chunks, int n_units) {
   const int K = KT > 0 ? KT : K_rt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: raw [2 buffers][2 rows][K][ncols_alloc] fp32 | mask [ncols_alloc] u32 | lists [4][2*PR_THREADS] u16 | hist [K*K] u32
+  // layout: raw [2 buffers][2 rows][K][ncols_alloc] fp32 | mask [ncols_alloc] u32 | lists [PR_BUCKETS][2*PR_THREADS] u16 | hist [K*K] u32
   float* raw_all = reinterpret_cast<float*>(smem_raw);
   const int raw_stride = 2 * K * ncols_alloc;
   uint32_t* cmask = reinterpret_cast<uint32_t*>(raw_all + 2 * raw_stride);
   uint16_t* lists = reinterpret_cast<uint16_t*>(cmask + ncols_alloc);
-  unsigned int* hist = reinterpret_cast<unsigned int*>(lists + 4 * 2 * PR_THREADS);
-  __shared__ int list_n[4];
+  unsigned int* hist = reinterpret_cast<unsigned int*>(lists + PR_BUCKETS * 2 * PR_THREADS);
+  __shared__ int list_n[PR_BUCKETS];
   __shared__ int band_rows[2];                                  // y_lo, y_hi of the current unit
   __shared__ float row_l0[PR_MAX_BAND], row_l1[PR_MAX_BAND];
 
@@ -203,7 +271,7 @@ __global__ void __launch_bounds__(PR_THREADS, 3) upsample_prune_kernel(
         const SrcCoord cy = src_coord(sy, yl + ln, h);
         row_l0[ln] = cy.l0; row_l1[ln] = cy.l1;
       }
-      if (ln < 4) list_n[ln] = 0;
+      if (ln < PR_BUCKETS) list_n[ln] = 0;
     }
     // ---- survivor mask per cell (cell c = source columns c, min(c + 1, ncols - 1))
     for (int c = tid; c < q.ncols; c += PR_THREADS) {
@@ -216,6 +284,7 @@ __global__ void __launch_bounds__(PR_THREADS, 3) upsample_prune_kernel(
     __syncthreads();
     const int y_lo = band_rows[0], R = band_rows[1] - band_rows[0];
     const int nchunks = (R + PR_ROWS - 1) / PR_ROWS;
+    const int chunk_rows = (R + nchunks - 1) / nchunks;          // balanced: 8 rows -> 4 + 4, 9 -> 5 + 4
     if (R > 0) {
       // ---- one strip (4 output columns x the band's rows) per thread
       const int x0 = q.X0 + tid * 4;
@@ -242,7 +311,9 @@ __global__ void __launch_bounds__(PR_THREADS, 3) upsample_prune_kernel(
               if (r < R) run.add_word(hist, lw[r], pw, K, ignore_label);
           }
         } else {
-          const int bucket = (m & PR_NF) ? 3 : nc <= 2 ? 0 : nc <= 4 ? 1 : 2;
+          // one list per survivor-count class and one for non-finite cells: a warp only ever works on items of one
+          // list, so its lanes run about the same number of candidate iterations
+          const int bucket = (m & PR_NF) ? PR_BUCKETS - 1 : nc <= 4 ? nc - 2 : nc <= 6 ? 3 : 4;
           const int slot = atomicAdd(&list_n[bucket], nchunks);
           for (int qq = 0; qq < nchunks; ++qq)
             lists[bucket * 2 * PR_THREADS + slot + qq] = static_cast<uint16_t>(tid | (qq << 8));
@@ -253,12 +324,19 @@ __global__ void __launch_bounds__(PR_THREADS, 3) upsample_prune_kernel(
     if (R <= 0) continue;
 
     // ---- queued strips, one (strip, row chunk) item per thread and turn; items of one bucket run together
-    for (int bucket = 0; bucket < 4; ++bucket) {
+    // the lists are cut into rounds of 32 items and the rounds dealt to the warps in turn, across list boundaries, so every
+    // warp gets the same number of rounds (+-1) whatever the list sizes: nobody waits at the next barrier for a warp
+    // that happened to own the long lists
+    int round = 0;
+    for (int bucket = 0; bucket < PR_BUCKETS; ++bucket) {
       const int n_items = list_n[bucket];
-      for (int it = tid; it < n_items; it += PR_THREADS) {
+      const int n_rounds = (n_items + 31) >> 5;
+      for (int rr = ((tid >> 5) - round) & (PR_THREADS / 32 - 1); rr < n_rounds; rr += PR_THREADS / 32) {
+        const int it = rr * 32 + (tid & 31);
+        if (it >= n_items) continue;
         const int item = lists[bucket * 2 * PR_THREADS + it];
-        const int st = item & 0xff, r0 = (item >> 8) * PR_ROWS;
-        const int nr = min(PR_ROWS, R - r0);
+        const int st = item & 0xff, r0 = (item >> 8) * chunk_rows;
+        const int nr = min(chunk_rows, R - r0);
         const int xs0 = q.X0 + st * 4;
         int xi[4], xn[4];
         float xl0[4], xl1[4];
@@ -269,60 +347,11 @@ __global__ void __launch_bounds__(PR_THREADS, 3) upsample_prune_kernel(
           xi[j] = c.i0 - q.c_lo; xn[j] = xi[j] + c.step; xl0[j] = c.l0; xl1[j] = c.l1;
         }
         for (int c = xi[0]; c <= xi[3]; ++c) m |= cmask[c];
-        float best[PR_ROWS][4];
         uint32_t idx[PR_ROWS];                                  // four class indices per row, one byte each
-#pragma unroll
-        for (int r = 0; r < PR_ROWS; ++r) {
-          idx[r] = 0u;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) best[r][j] = -INFINITY;
-        }
-        const bool nf = (m & PR_NF) != 0u;
-        uint32_t todo = nf ? ((1u << K) - 1u) : m;
-        bool first = !nf;
-        while (todo) {
-          const int k = __ffs(todo) - 1;
-          todo &= todo - 1u;
-          const uint32_t kk = static_cast<uint32_t>(k) * 0x01010101u;
-          const float* t = raw + (0 * K + k) * ncols_alloc;
-          const float* v1 = raw + (1 * K + k) * ncols_alloc;
-          float top[4], bot[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            // l0x*a + l1x*b as nvcc contracts it in the row-cached kernel: fma(l0x, a, l1x*b)
-            top[j] = __fmaf_rn(xl0[j], t[xi[j]], __fmul_rn(xl1[j], t[xn[j]]));
-            bot[j] = __fmaf_rn(xl0[j], v1[xi[j]], __fmul_rn(xl1[j], v1[xn[j]]));
-          }
-#pragma unroll
-          for (int r = 0; r < PR_ROWS; ++r) {
-            if (r < nr) {
-              const float l0 = row_l0[r0 + r], l1 = row_l1[r0 + r];
-              // l0y*top + l1y*bot on packed pairs: mul then fma, the same products and sums as the row-cached kernel
-              float2 v01 = pr_mul2(make_float2(l0, l0), make_float2(top[0], top[1]));
-              float2 v23 = pr_mul2(make_float2(l0, l0), make_float2(top[2], top[3]));
-              v01 = pr_fma2(make_float2(l1, l1), make_float2(bot[0], bot[1]), v01);
-              v23 = pr_fma2(make_float2(l1, l1), make_float2(bot[2], bot[3]), v23);
-              const float v[4] = {v01.x, v01.y, v23.x, v23.y};
-              if (first) {
-                idx[r] = kk;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) best[r][j] = v[j];
-              } else if (!nf) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (v[j] > best[r][j]) { best[r][j] = v[j]; idx[r] = (idx[r] & ~(0xffu << (8 * j))) | (kk & (0xffu << (8 * j))); }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)                    // np.argmax: first maximum, NaN counts as maximal
-                  if (v[j] > best[r][j] || (v[j] != v[j] && best[r][j] == best[r][j])) {
-                    best[r][j] = v[j];
-                    idx[r] = (idx[r] & ~(0xffu << (8 * j))) | (kk & (0xffu << (8 * j)));
-                  }
-              }
-            }
-          }
-          first = false;
-        }
+        const float* rl0 = row_l0 + r0;
+        const float* rl1 = row_l1 + r0;
+        if (m & PR_NF) eval_item<true>(nr, raw, K, ncols_alloc, (1u << K) - 1u, xi, xn, xl0, xl1, rl0, rl1, idx);
+        else eval_item<false>(nr, raw, K, ncols_alloc, m, xi, xn, xl0, xl1, rl0, rl1, idx);
         const size_t pix = (static_cast<size_t>(q.b) * H + y_lo + r0) * W + xs0;
 #pragma unroll
         for (int r = 0; r < PR_ROWS; ++r) {
@@ -335,6 +364,7 @@ __global__ void __launch_bounds__(PR_THREADS, 3) upsample_prune_kernel(
           }
         }
       }
+      round += n_rounds;
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -357,7 +387,7 @@ int launch_upsample_prune(const float* logits_lr, int B, int K, int h, int w, in
   if (static_cast<int>(1.f / sy) + 2 > sl::PR_MAX_BAND) return -100;
   const int ncols_alloc = static_cast<int>(PR_THREADS * 4 * sx) + 4;
   const size_t smem = static_cast<size_t>(4) * K * ncols_alloc * 4 + static_cast<size_t>(ncols_alloc) * 4 +
-                      4 * 2 * PR_THREADS * 2 + static_cast<size_t>(K) * K * 4;
+                      PR_BUCKETS * 2 * PR_THREADS * 2 + static_cast<size_t>(K) * K * 4;
   if (smem > 160 * 1024) return -100;
   const int n_chunks = (W / 4 + PR_THREADS - 1) / PR_THREADS;
   const long long units = static_cast<long long>(B) * h * n_chunks;
