@@ -263,7 +263,7 @@ class LaunchCounter:
     launches at the benchmarked shapes, from the sources; checked against the ncu launch list under profiles/)."""
     PER_CALL = {'sl_pop_prepare': 3, 'sl_pop_fg_lowres': 1, 'sl_pop_bg_tc': 1, 'sl_pop_bg_simt': 1, 'sl_pop_head_tc': 2,
                 'sl_upsample_argmax': 1, 'sl_confusion': 1, 'sl_views_reduce': 1, 'sl_window_accumulate': 1,
-                'sl_map_proto': 3, 'sl_orth_loss': 1, 'sl_orth_from_sim': 1, 'sl_fuse_argmax': 1, 'sl_fuse_argmax_tiles': 0, 'sl_pseudo_label': 1,
+                'sl_map_proto': 3, 'sl_orth_loss': 1, 'sl_orth_from_sim': 1, 'sl_fuse_argmax': 1, 'sl_fuse_argmax_tiles': 1, 'sl_pseudo_label': 1,
                 'sl_inter_union': 3}
 
     def __init__(self):

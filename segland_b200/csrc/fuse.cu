@@ -12,10 +12,10 @@ namespace sl {
 struct FusePtrs { const float* m[SL_MAX_FUSE]; };
 
 template <int M>  // 0 = runtime count
-__global__ void __launch_bounds__(256) fuse_argmax_kernel(FusePtrs ptrs, int Mrt, int K, long long HW4, float divisor,
-                                                          uint8_t* __restrict__ pred, float* __restrict__ fused,
-                                                          const uint8_t* __restrict__ label, int ignore_label,
-                                                          unsigned long long* __restrict__ cm) {
+__global__ void __launch_bounds__(256) fuse_argmax_kernel(FusePtrs ptrs0, int Mrt, int K, long long HW4, float divisor,
+                                                          uint8_t* __restrict__ pred0, float* __restrict__ fused0,
+                                                          const uint8_t* __restrict__ label0, int ignore_label,
+                                                          unsigned long long* __restrict__ cm, int T) {
   __shared__ unsigned int hist[SL_MAX_CLASSES * SL_MAX_CLASSES];
   const bool do_cm = cm != nullptr;
   if (do_cm) {
@@ -27,6 +27,16 @@ __global__ void __launch_bounds__(256) fuse_argmax_kernel(FusePtrs ptrs, int Mrt
   const long long start = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   const long long iters = (HW4 + stride - 1) / stride;
   const size_t HW = static_cast<size_t>(HW4) * 4;
+  // T tiles, tile-major stacks [T][K][HW]: every CTA takes its slice of every tile, so the per-CTA histogram is
+  // flushed once per sweep instead of once per tile (the K*K global atomics per CTA were the limit of per-tile launches)
+  for (int tile = 0; tile < T; ++tile) {
+  FusePtrs ptrs;
+#pragma unroll
+  for (int m = 0; m < (M > 0 ? M : SL_MAX_FUSE); ++m)
+    ptrs.m[m] = (m < Mn) ? ptrs0.m[m] + static_cast<size_t>(tile) * K * HW : nullptr;
+  uint8_t* pred = pred0 + static_cast<size_t>(tile) * HW;
+  float* fused = fused0 ? fused0 + static_cast<size_t>(tile) * K * HW : nullptr;
+  const uint8_t* label = label0 ? label0 + static_cast<size_t>(tile) * HW : nullptr;
   for (long long it = 0; it < iters; ++it) {
     const long long g = start + it * stride;
     const bool active = g < HW4;
@@ -66,6 +76,7 @@ __global__ void __launch_bounds__(256) fuse_argmax_kernel(FusePtrs ptrs, int Mrt
       }
     }
   }
+  }
   if (do_cm) {
     __syncthreads();
     for (int i = threadIdx.x; i < K * K; i += 256)
@@ -75,9 +86,10 @@ __global__ void __launch_bounds__(256) fuse_argmax_kernel(FusePtrs ptrs, int Mrt
 
 }  // namespace sl
 
-extern "C" int sl_fuse_argmax(const float* const* mats_host, int M, int K, long long HW, int divisor, uint8_t* pred,
-                              float* fused, const uint8_t* label, int ignore_label, long long* cm, void* stream) {
+static int fuse_launch(const float* const* mats_host, int M, int T, int K, long long HW, int divisor, uint8_t* pred,
+                       float* fused, const uint8_t* label, int ignore_label, long long* cm, void* stream) {
   SL_CHECK_PTR(mats_host); SL_CHECK_PTR(pred);
+  SL_CHECK_ARG(T >= 1);
   SL_CHECK_ARG(M >= 1 && M <= SL_MAX_FUSE && K >= 1 && K <= SL_MAX_CLASSES && HW >= 4 && HW % 4 == 0 && divisor >= 1);
   if (cm) SL_CHECK_PTR(label);
   sl::FusePtrs p;
@@ -98,7 +110,7 @@ extern "C" int sl_fuse_argmax(const float* const* mats_host, int M, int K, long 
   auto* cmu = reinterpret_cast<unsigned long long*>(cm);
   const float d = static_cast<float>(divisor);
 #define SL_FUSE_LAUNCH(MM) sl::fuse_argmax_kernel<MM><<<static_cast<int>(blocks), 256, 0, st>>>( \
-      p, M, K, HW4, d, pred, fused, label, ignore_label, cmu)
+      p, M, K, HW4, d, pred, fused, label, ignore_label, cmu, T)
   switch (M) {
     case 1: SL_FUSE_LAUNCH(1); break;
     case 2: SL_FUSE_LAUNCH(2); break;
@@ -110,24 +122,17 @@ extern "C" int sl_fuse_argmax(const float* const* mats_host, int M, int K, long 
   return SL_LAUNCH_RESULT();
 }
 
-// A sweep of T tiles in one call: mats_host[m] is model m's stack for all tiles, [T,K,HW] (tile-major, as an eval sweep
-// writes it); tile t is fused exactly as sl_fuse_argmax fuses one tile (one launch per tile, queued back to back from C,
-// so the host cost per tile is a kernel launch, not a Python call).
+extern "C" int sl_fuse_argmax(const float* const* mats_host, int M, int K, long long HW, int divisor, uint8_t* pred,
+                              float* fused, const uint8_t* label, int ignore_label, long long* cm, void* stream) {
+  return fuse_launch(mats_host, M, 1, K, HW, divisor, pred, fused, label, ignore_label, cm, stream);
+}
+
+// A sweep of T tiles in ONE launch: mats_host[m] is model m's stack for all tiles, [T,K,HW] (tile-major, as an eval sweep
+// writes it); every tile is fused exactly as sl_fuse_argmax fuses one tile (same operations in the same order per pixel).
 extern "C" int sl_fuse_argmax_tiles(const float* const* mats_host, int M, int T, int K, long long HW, int divisor,
                                     uint8_t* pred, float* fused, const uint8_t* label, int ignore_label, long long* cm,
                                     void* stream) {
-  SL_CHECK_PTR(mats_host);
-  SL_CHECK_ARG(T >= 0 && M >= 1 && M <= SL_MAX_FUSE);
-  const float* tile_ptrs[SL_MAX_FUSE];
-  for (int t = 0; t < T; ++t) {
-    for (int m = 0; m < M; ++m) {
-      SL_CHECK_PTR(mats_host[m]);
-      tile_ptrs[m] = mats_host[m] + static_cast<size_t>(t) * K * HW;
-    }
-    const int rc = sl_fuse_argmax(tile_ptrs, M, K, HW, divisor, pred + static_cast<size_t>(t) * HW,
-                                  fused ? fused + static_cast<size_t>(t) * K * HW : nullptr,
-                                  label ? label + static_cast<size_t>(t) * HW : nullptr, ignore_label, cm, stream);
-    if (rc != 0) return rc;
-  }
-  return SL_OK;
+  SL_CHECK_ARG(T >= 0);
+  if (T == 0) return SL_OK;
+  return fuse_launch(mats_host, M, T, K, HW, divisor, pred, fused, label, ignore_label, cm, stream);
 }
