@@ -48,6 +48,7 @@ extern "C" {
  *                       second launch over (label, pred) (0); default: inside for the pruning kernel, second launch for
  *                       the row-cached kernel
  *   SL_TC_DEBUG=<bits>  knock-outs inside the single-CTA kernel (timing experiments, results INVALID)
+ *   SL_FG_MMA=0         sl_pop_fg_lowres on the FFMA2 CUDA-core kernel instead of the mma.sync kernel
  *   SL_TAIL_FUSED=0     sl_tail_bn_relu_conv as two kernels (bf16 hi/lo planes in the workspace + generic GEMM)
  *   SL_SMALL_DBG=<ptr>  device pointer (decimal) of a 64x16 int64 buffer receiving per-tile cycle stamps of CTA 0
  */
@@ -114,7 +115,9 @@ SL_API int sl_pop_prepare(const float *protos, int K, int Kb, int C,
                    uint16_t *W1p_hi, uint16_t *W1p_lo, uint16_t *W2_hi, uint16_t *W2_lo,
                    uint16_t *W1p_f16, uint16_t *W2_f16, float *ws, void *stream);
 
-/* K foreground logits at feature resolution (HBM-bound, CUDA cores).
+/* K foreground logits at feature resolution (HBM-bound; the projections run on the legacy tensor path -- mma.sync
+ * m16n8k16 with the fp32 prototypes split into three bf16 terms, fp32 accumulation -- so that the K FMAs per feature
+ * element do not bind before HBM does).
  *   feat   [B,C,N] bf16 (features.flatten(2), pspnet_pop.py:148); C % 8 == 0, C <= 512,
  *          N % 8 == 0, 16-byte aligned.
  *   logits [B,Ktot,N] fp32; channel ch_map[k] (host array of K ints) receives class

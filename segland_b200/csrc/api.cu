@@ -17,6 +17,7 @@ static void load_env() {
   e.post_fused_cm = geti("SL_POST_FUSED_CM", -1);
   e.post_prune = geti("SL_POST_PRUNE", 0);
   e.tail_fused = geti("SL_TAIL_FUSED", 1);
+  e.fg_mma = geti("SL_FG_MMA", 1);
   const char* d = getenv("SL_SMALL_DBG");
   e.small_dbg = d != nullptr ? static_cast<long long>(strtoull(d, nullptr, 10)) : 0;
   g_env = e;

@@ -38,6 +38,7 @@ struct Env {
   int post_fused_cm;    // SL_POST_FUSED_CM (-1 = unset)
   int post_prune;       // SL_POST_PRUNE    (0)
   int tail_fused;       // SL_TAIL_FUSED    (1)
+  int fg_mma;           // SL_FG_MMA        (1: mma.sync projections; 0: the FFMA2 kernel)
   long long small_dbg;  // SL_SMALL_DBG     (0)
 };
 const Env& env();       // api.cu

@@ -178,6 +178,9 @@ static int launch_fg(const CUtensorMap& map_x, int B, int C, int N, const float*
   return SL_LAUNCH_RESULT();
 }
 
+int launch_fg_mma(const uint16_t* feat, int B, int C, int N, const float* s_hat, const float* alpha, const float* beta,
+                  int K, int k_base, float* logits, int Ktot, const int* ch_map_host, cudaStream_t st);   // pop_fg_mma.cu
+
 }  // namespace sl
 
 extern "C" int sl_pop_fg_lowres(const uint16_t* feat, int B, int C, int N, const float* s_hat, const float* alpha,
@@ -195,6 +198,17 @@ extern "C" int sl_pop_fg_lowres(const uint16_t* feat, int B, int C, int N, const
     map.ch[k] = ch_map_host[k];
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // Default: the projections run on the legacy tensor path, 16 classes per pass (pop_fg_mma.cu): 88-102 % of the HBM
+  // copy peak at K = 7 and K = 11 against 92 % / 66-70 % for the FFMA2 kernel below (profiles/r2_fg_mma_probe.txt),
+  // which stays as the SL_FG_MMA=0 comparison.
+  const int mma_env = sl::env().fg_mma;
+  if (mma_env != 0) {
+    for (int k_base = 0; k_base < K; k_base += 16) {
+      const int rc = sl::launch_fg_mma(feat, B, C, N, s_hat, alpha, beta, K, k_base, logits, Ktot, ch_map_host, st);
+      if (rc != 0) return rc;
+    }
+    return SL_OK;
+  }
   // Up to 12 classes per pass keep the accumulators in registers; more classes take extra passes.
   for (int k_base = 0; k_base < K; k_base += 12) {
     const int kc = (K - k_base) < 12 ? (K - k_base) : 12;
