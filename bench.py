@@ -263,7 +263,7 @@ class LaunchCounter:
     launches at the benchmarked shapes, from the sources; checked against the ncu launch list under profiles/)."""
     PER_CALL = {'sl_pop_prepare': 3, 'sl_pop_fg_lowres': 1, 'sl_pop_bg_tc': 1, 'sl_pop_bg_simt': 1, 'sl_pop_head_tc': 2,
                 'sl_upsample_argmax': 1, 'sl_confusion': 1, 'sl_views_reduce': 1, 'sl_window_accumulate': 1,
-                'sl_map_proto': 3, 'sl_orth_loss': 1, 'sl_orth_from_sim': 1, 'sl_fuse_argmax': 1, 'sl_fuse_argmax_tiles': 1, 'sl_pseudo_label': 1,
+                'sl_map_proto': 4, 'sl_orth_loss': 1, 'sl_orth_from_sim': 1, 'sl_fuse_argmax': 1, 'sl_fuse_argmax_tiles': 1, 'sl_pseudo_label': 1,
                 'sl_inter_union': 3}
 
     def __init__(self):
@@ -662,9 +662,9 @@ def run_config2(rank, world, dev, peaks, args):
     return {'workload': '20 support tiles [512,128,128] bf16 + fp32 masks [1,1024,1024], 4 novel classes x 5 shots, sharded '
                         f'by rank ({n_local} on rank 0); MAP -> per-class sums + counts all-reduce (NCCL) -> orthogonal loss',
             'updates_per_s': 1.0 / t_update, 'support_tiles_per_s': n_support / t_update, 'ms_per_update': 1e3 * t_update,
-            'scaling': 'strong (20 tiles shared by all ranks; the update is latency-bound: 3 MAP launches, one all-reduce, '
+            'scaling': 'strong (20 tiles shared by all ranks; the update is latency-bound: 4 MAP launches, one all-reduce, '
                        'index_add, orth loss)',
-            'roofline': {'bound': 'hbm', 'kernel': 'sl_map_proto (3 launches)', 'achieved': gbs, 'peak': peaks['hbm_gbs'],
+            'roofline': {'bound': 'hbm', 'kernel': 'sl_map_proto (4 launches)', 'achieved': gbs, 'peak': peaks['hbm_gbs'],
                          'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'ms': 1e3 * t_map,
                          'bytes_per_launch': map_bytes, 'note': 'rank 0 shard, features + fp32 mask per tile'},
             'collective': 'one torch.distributed all_reduce (NCCL) of 4 x 513 fp32 per update' if world > 1 else 'none (1 rank)'}
