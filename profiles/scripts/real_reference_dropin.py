@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""patch() on the REAL reference on a B200: networks.pspnet_pop.GFSS_Model with its ResNet-50
-backbone and PSP decoder (seeded random init, BatchNorm statistics calibrated on random images), driven through the
-body of eval_base.py:162-178 -- model(image) -> F.interpolate -> .cpu() -> np.argmax -> get_confusion_matrix --
+"""patch() on the REAL reference on a B200: the reference's own GFSS_Model classes with their real
+backbones and decoders -- pspnet_pop/resnet50 (base and ft), convnext_pop/convnext-t, swin_pop/swin-t, lsk_pop/lsk-t,
+deeplab_pop/resnet50, seghr_pop/hr-w32 and hr-w18 (C = 270: outside the kernels' range, must stay on the reference) --
+seeded random init, BatchNorm statistics calibrated on random images, a trained-like head on prototypes taken from the
+model's own decoder features, driven through the body of eval_base.py:162-178 -- model(image) -> F.interpolate -> .cpu() -> np.argmax -> get_confusion_matrix --
 unpatched vs patched on the same GPU, plus the fused path (sweep.TileEvaluator, the three-line edit of INTEGRATION.md).
 
-    SEGLAND_REFERENCE=/path/to/SegLand python profiles/scripts/real_reference_dropin.py [n_tiles]
+    SEGLAND_REFERENCE=/path/to/SegLand python profiles/scripts/real_reference_dropin.py [n_tiles] [model,model,...]
 
 The reference tree is not part of this repository; for this run a scratch copy travels under baseline/_ref/ (git-ignored).
 """
@@ -51,10 +53,18 @@ def main():
     pspnet_pop, convnext_pop, _, _, pyt_utils = gen_golden.import_reference()
     from segland_b200 import ops, patch as slp, sweep
     torch.backends.cudnn.benchmark = False
-    for is_ft in (False, True):
+    import importlib
+    specs = [('pspnet_pop', 'resnet50', False), ('pspnet_pop', 'resnet50', True), ('convnext_pop', 'convnext-t', True),
+             ('swin_pop', 'swin-t', True), ('lsk_pop', 'lsk-t', True), ('deeplab_pop', 'resnet50', True),
+             ('seghr_pop', 'hr-w32', True), ('seghr_pop', 'hr-w18', True)]
+    if len(sys.argv) > 2:
+        specs = [sp for sp in specs if sp[0] in sys.argv[2].split(',')]
+    for mod_name, backbone, is_ft in specs:
         torch.manual_seed(0)
         K = 8 + (4 if is_ft else 0)
-        model = pspnet_pop.GFSS_Model(n_base=7, backbone='resnet50', dilated=True, os=8, n_novel=4, is_ft=is_ft)
+        net_mod = importlib.import_module('networks.' + mod_name)
+        model = net_mod.GFSS_Model(n_base=7, backbone=backbone, dilated=True, os=8, n_novel=4, is_ft=is_ft)
+        Cm = model.base_emb.shape[1]
         if is_ft:
             with torch.no_grad():
                 torch.nn.init.orthogonal_(model.base_emb)
@@ -64,7 +74,7 @@ def main():
         model.train()                                            # calibrate BatchNorm running statistics
         with torch.no_grad():
             for _ in range(30):
-                (model.decoder(model.backbone.base_forward(torch.randn(2, 3, 256, 256, device='cuda'))))
+                slp._features(model, torch.randn(2, 3, 256, 256, device='cuda'))
         model.eval()
         g = torch.Generator().manual_seed(1)
         # smooth random images (random init + white noise gives spatially constant features: nothing to segment)
@@ -74,21 +84,23 @@ def main():
         # classifier(s) = the trained-like construction of segland_b200.synth on those prototypes
         from segland_b200 import synth
         with torch.no_grad():
-            f0 = model.decoder(model.backbone.base_forward(images[0].cuda()))[0].flatten(1).cpu()      # [512, N]
+            f0 = slp._features(model, images[0].cuda())[0].flatten(1).float().cpu()                   # [C, N]
         f0 = f0 - f0.mean(1, keepdim=True)
         pick = torch.randperm(f0.shape[1], generator=g)[:11]
         protos = torch.nn.functional.normalize(f0[:, pick].t().contiguous(), dim=-1)
-        st = synth.make_trained_like_state(512, 7, 4 if is_ft else 0, seed=3, base=protos[:7], novel=protos[7:] if is_ft else None)
+        st = synth.make_trained_like_state(Cm, 7, 4 if is_ft else 0, seed=3, n_bg_units=min(64, Cm // 4), base=protos[:7],
+                                           novel=protos[7:] if is_ft else None)
         with torch.no_grad():
             model.base_emb.copy_(st.base_emb)
             for seq, ws in ((model.classifier, st.cls),) + (((model.classifier_n, st.cls_n),) if is_ft else ()):
-                seq[0].weight.copy_(ws[0].view(512, 512, 1, 1)); seq[2].weight.copy_(ws[1].view(512, 512, 1, 1))
-                seq[4].weight.copy_(ws[2].view(1, 512, 1, 1))
+                seq[0].weight.copy_(ws[0].view(Cm, Cm, 1, 1)); seq[2].weight.copy_(ws[1].view(Cm, Cm, 1, 1))
+                seq[4].weight.copy_(ws[2].view(1, Cm, 1, 1))
             if is_ft:
                 model.novel_emb.copy_(st.novel_emb)
         labels = [torch.randint(0, K, (1, 1024, 1024), generator=g).to(torch.uint8) for _ in range(n_tiles)]
-        name = 'pspnet_pop/resnet50 ' + ('is_ft=True (forward_all, 12 classes)' if is_ft else 'is_ft=False (forward_base, 8 classes)')
-        print(f'=== {name}, {n_tiles} tiles of 1024^2')
+        name = f'{mod_name}/{backbone} C={Cm} ' + ('is_ft=True (forward_all, 12 classes)' if is_ft else 'is_ft=False (forward_base, 8 classes)')
+        print(f'=== {name}, {n_tiles} tiles of 1024^2' + ('' if ops.PopHead.supports(Cm) else
+              '  [C outside the kernels\' range: patch() leaves this model on the reference forward]'))
         res = {}
         for tf32 in (False, True):
             torch.backends.cudnn.allow_tf32 = tf32
@@ -110,6 +122,12 @@ def main():
             our_logits = []
             cm_our, lat_our = eval_loop(model, images, labels, K, pyt_utils, our_logits)
             # fused path: decoder features -> TileEvaluator (head + up-sample + argmax + confusion on the device)
+            if not ops.PopHead.supports(Cm):
+                slp.unpatch()
+                R, O = torch.cat(ref_logits), torch.cat(our_logits)
+                print(f'--- {tag}: patched == unpatched (reference forward kept): {torch.equal(R, O)}; per tile '
+                      f'{1e3 * float(np.median(lat_ref)):.1f} ms')
+                continue
             ev = sweep.TileEvaluator(slp.head_for(model), (1024, 1024))
             lat_fused, preds = [], []
             for it, (image, label) in enumerate(zip(images[:1] + images, labels[:1] + labels)):
@@ -150,11 +168,11 @@ def main():
         with torch.no_grad():
             x = images[0].cuda()
             for _ in range(2):
-                model.decoder(model.backbone.base_forward(x))
+                slp._features(model, x)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(5):
-                model.decoder(model.backbone.base_forward(x))
+                slp._features(model, x)
             torch.cuda.synchronize()
             print(f'backbone + decoder alone (tf32): {1e3 * (time.perf_counter() - t0) / 5:.1f} ms per tile')
 
