@@ -391,6 +391,25 @@ def run_ours(args, rank, world, local_rank):
         ops.upsample_argmax(lg, (TILE, TILE), label=labels, cm=ev.cm)
     stage_s_ms = 1e3 * time_loop(stage_s, max(args.steps, 20))
 
+    # ---- the opt-in tensor modes on the same pass (informational; not parity-grade on near-tie data)
+    alt_modes = {}
+    if use_tc and not args.skip_configs:
+        for mode in ('mid', 'balanced'):
+            if mode == args.tc_precision:
+                continue
+            alt = ops.PopHead(st.base_emb, st.cls, None, None, device=dev, bg_mode=args.bg_mode, tc_precision=mode)
+
+            def alt_pass():
+                alt(feats, out=lg, fg_only=True)
+                alt.bg_tc(feats, lg)
+                ops.upsample_argmax(lg, (TILE, TILE), label=labels, cm=ev.cm)
+            t_pass = max_over_ranks(time_loop(alt_pass, 4 * P, warm=P), world, dev)
+            t_bg = time_loop(lambda: alt.bg_tc(feats, lg), 20)
+            alt_modes[mode] = {'tiles_per_s': world * T / t_pass, 'ms_per_pass': 1e3 * t_pass, 'bg_ms': 1e3 * t_bg,
+                               'mma_passes': {'mid': 4, 'balanced': 3}[mode]}
+            del alt
+        ev.reset()
+
     # ---- end to end through the public API with HOST buffers (double-buffered H2D, D2H of preds)
     Te = min(T, args.e2e_tiles)
     # --e2e-tiles 0 (profiler runs only) skips the host-buffer leg; the driver's default run always measures it
@@ -477,6 +496,7 @@ def run_ours(args, rank, world, local_rank):
         'timed_region_s': timed_s,
         'kernel_ms_per_pass': kern_ms,
         'prepare_ms_per_weight_update': prepare_ms,
+        'opt_in_tensor_modes': alt_modes,
         'roofline': roofline,
         'stage_s': stage_s,
         'e2e': e2e,
