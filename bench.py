@@ -325,14 +325,27 @@ def run_ours(args, rank, world, local_rank):
     ev = sweep.TileEvaluator(head, (TILE, TILE))
     use_tc = head._use_tc(N_PIX)
     fused = use_tc and args.fuse and head.fused_ok(N_PIX)
+    # default: the sweep is software-pipelined over two streams (post-processing of pass p-1 underneath the background
+    # MLP of pass p, sweep.PipelinedTileEvaluator); --no-pipeline runs the three kernels back to back on one stream
+    pipelined = not args.no_pipeline and not fused
+    pev = sweep.PipelinedTileEvaluator(head, (TILE, TILE)) if pipelined else None
 
     stream = torch.cuda.current_stream()
     ev_k = {k: [] for k in ('fg', 'bg', 'post')}
     lg = torch.empty(T, K, HW_LR, HW_LR, dtype=torch.float32, device=dev)
     ev._logits = lg
 
-    def one_pass(record):
+    def one_pass(record, seq=False, sink=None):
         """One pass of the hot path over the T resident tiles; per-kernel events on the recorded passes."""
+        sink = ev_k if sink is None else sink
+        if pipelined and not seq:
+            pev.trace = [] if record else None
+            out = pev.step(feats, labels)
+            if record:                       # fg(p), bg(p) and the post of pass p-1 that ran underneath bg(p)
+                for name, a, b in pev.trace:
+                    sink[name].append((a, b))
+                pev.trace = None
+            return out
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
         if record: marks[0].record(stream)
         if not fused:
@@ -349,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
         if record:
             marks[3].record(stream)
             for name, a, b in (('fg', 0, 1), ('bg', 1, 2), ('post', 2, 3)):
-                ev_k[name].append((marks[a], marks[b]))
+                sink[name].append((marks[a], marks[b]))
         return out
 
     def barrier():
@@ -362,8 +375,8 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         for _ in range(min(P, 4)):
             one_pass(False)
-    ev.finalize(base_classes=KB)                             # warm the (lazy) NCCL communicator as well
-    ev.reset()
+    (pev or ev).finalize(base_classes=KB)                    # warm the (lazy) NCCL communicator as well
+    (pev or ev).reset()
     sampler.start()
     barrier()
     counter = LaunchCounter()
@@ -374,7 +387,7 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(args.steps):
             for p in range(P):
                 one_pass(p == P // 2)                        # per-kernel events on one pass per step
-        cm, mious = ev.finalize(base_classes=KB)             # the one all-reduce of the sweep
+        cm, mious = (pev or ev).finalize(base_classes=KB)    # flushes the pipeline; the one all-reduce of the sweep
         t_end.record(stream)
     barrier()
     clocks = sampler.finish()
@@ -382,6 +395,21 @@ def run_ours(args, rank, world, local_rank):
     kern_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in ev_k.items()}
     value = world * T * P * args.steps / (elapsed_ms * 1e-3)
     gpu_launches = counter.n
+
+    # ---- the same passes back to back on one stream (no overlap): per-kernel times of each kernel running alone
+    seq_k = {k: [] for k in ('fg', 'bg', 'post')}
+    ev.reset()
+    n_seq = 4 * P
+    for p in range(8):
+        one_pass(False, seq=True)
+    s0, s1 = ev_pair()
+    s0.record(stream)
+    for p in range(n_seq):
+        one_pass(p % 8 == 4, seq=True, sink=seq_k)
+    s1.record(stream)
+    torch.cuda.synchronize()
+    seq_pass_ms = max_over_ranks(s0.elapsed_time(s1), world, dev) / n_seq
+    seq_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in seq_k.items()}
 
     # ---- stage S (everything but the background MLP): fg + post, timed on its own
     ev.reset()
@@ -456,14 +484,18 @@ def run_ours(args, rank, world, local_rank):
                     'frac_executed_of_burst': bg_exec_flops / (kern_ms['bg'] * 1e-3) / 1e12 / peaks['tflops_burst'],
                     'peak_source': peaks['source'] + (' bf16 sustained (timed region %.2f s)' % timed_s if sustained
                                                       else ' bf16 burst (timed region %.2f s)' % timed_s),
-                    'flops_per_launch': bg_flops}
+                    'flops_per_launch': bg_flops,
+                    'frac_kernel_alone': bg_flops / (seq_ms['bg'] * 1e-3) / 1e12 / peak,
+                    'note': ('kernel duration measured inside the pipelined timed region, where the up-sampling kernel of the '
+                             'previous pass shares the SMs (and the 1 kW power cap) with it; frac_kernel_alone is the same '
+                             'kernel in the sequential leg') if pipelined else 'sequential passes'}
     else:
         byts = fg_bytes if dominant == 'fg' else post_bytes
         ach = byts / (kern_ms[dominant] * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                     'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'kernel': dominant,
                     'peak_source': peaks['source'], 'bytes_per_launch': byts}
-    fg_gbs = fg_bytes / (kern_ms['fg'] * 1e-3) / 1e9
+    fg_gbs = fg_bytes / (seq_ms['fg'] * 1e-3) / 1e9
     s_bytes_tile = C * N_PIX * 2 + 2 * TILE * TILE
     stage_s = {'value': T / (stage_s_ms * 1e-3), 'unit': '1024x1024 tiles/s (fg logits + upsample/argmax/confusion; '
                'no background MLP)', 'ms_per_pass': stage_s_ms,
@@ -473,10 +505,11 @@ def run_ours(args, rank, world, local_rank):
                'roofline_hbm': {'kernel': 'pop_fg_kernel (sl_pop_fg_lowres)', 'achieved': fg_gbs, 'peak': peaks['hbm_gbs'],
                                 'unit': 'GB/s', 'frac': fg_gbs / peaks['hbm_gbs'], 'bytes_per_launch': fg_bytes,
                                 'traffic': traffic.get('pop_fg_kernel', {}).get('base')},
-               'post_roofline_hbm': {'kernel': 'sl_upsample_argmax (+ confusion)', 'achieved': post_bytes / (kern_ms['post'] * 1e-3) / 1e9,
+               'post_roofline_hbm': {'kernel': 'sl_upsample_argmax (+ confusion)', 'achieved': post_bytes / (seq_ms['post'] * 1e-3) / 1e9,
                                      'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                                     'frac': post_bytes / (kern_ms['post'] * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                                     'bound_note': 'instruction-issue bound, not HBM (ncu: profiles/r1_ncu_post.txt)'},
+                                     'frac': post_bytes / (seq_ms['post'] * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                                     'ms_alone': seq_ms['post'],
+                                     'bound_note': 'instruction-issue bound, not HBM (ncu: profiles/r2b_ncu_post_regs.txt)'},
                'algorithmic_bytes_per_tile': s_bytes_tile}
     cpu_tps, cores = cpu_reference_tiles_per_s(args.cpu_tiles) if world == 1 and args.cpu_tiles > 0 else (None, None)
     eager = gpu_eager_reference(args.eager_tiles, dev) if world == 1 and args.eager_tiles > 0 else None
@@ -491,10 +524,17 @@ def run_ours(args, rank, world, local_rank):
                                              'balanced': 'balanced (split-bf16 L1, fp16 L2, 2+1 passes)'}[args.tc_precision])
                    if use_tc else 'fp32 CUDA cores',
                    'head_launches': 'one (fg logits fused into the tcgen05 kernel)' if fused else 'two (fg kernel + bg kernel)',
+                   'schedule': 'pipelined (post of pass p-1 under bg of pass p)' if pipelined else 'sequential',
                    'l2_policy': f'inputs larger than L2 ({T * C * N_PIX * 2 / 1e6:.0f} MB features per pass)',
                    'parallelism': f'dp{world}'},
         'timed_region_s': timed_s,
         'kernel_ms_per_pass': kern_ms,
+        'schedule': ('pipelined over two streams: fg(p), bg(p) on a high-priority stream, post(p-1) underneath bg(p) on a second '
+                     'stream (sweep.PipelinedTileEvaluator); kernel_ms_per_pass are durations while co-running'
+                     if pipelined else 'sequential: fg -> bg -> post on one stream'),
+        'sequential': {'tiles_per_s': world * T / (seq_pass_ms * 1e-3), 'ms_per_pass': seq_pass_ms,
+                       'kernel_ms_per_pass': seq_ms, 'passes': n_seq,
+                       'note': 'the same passes back to back on one stream, each kernel alone on the GPU'},
         'prepare_ms_per_weight_update': prepare_ms,
         'opt_in_tensor_modes': alt_modes,
         'roofline': roofline,
@@ -820,6 +860,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--tiles', type=int, default=32, help='distinct resident 1024^2 tiles per pass per GPU')
+    ap.add_argument('--no-pipeline', action='store_true', help='run fg -> bg -> post back to back on one stream')
     ap.add_argument('--passes', type=int, default=48, help='passes over the resident tiles per step (48 x 32 tiles: '
                                                            '~55 ms per step, so 20 steps time > 1 s)')
     ap.add_argument('--e2e-tiles', type=int, default=8)

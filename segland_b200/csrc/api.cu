@@ -16,6 +16,7 @@ static void load_env() {
   e.prep_split = geti("SL_PREP_SPLIT", 0);
   e.post_fused_cm = geti("SL_POST_FUSED_CM", -1);
   e.post_prune = geti("SL_POST_PRUNE", 0);
+  e.post_regs = geti("SL_POST_REGS", 1);
   e.tail_fused = geti("SL_TAIL_FUSED", 1);
   e.fg_mma = geti("SL_FG_MMA", 1);
   const char* d = getenv("SL_SMALL_DBG");

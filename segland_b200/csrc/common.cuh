@@ -37,6 +37,7 @@ struct Env {
   int prep_split;       // SL_PREP_SPLIT    (0)
   int post_fused_cm;    // SL_POST_FUSED_CM (-1 = unset)
   int post_prune;       // SL_POST_PRUNE    (0)
+  int post_regs;        // SL_POST_REGS     (1: register-resident source-row intervals for the prediction-only path)
   int tail_fused;       // SL_TAIL_FUSED    (1)
   int fg_mma;           // SL_FG_MMA        (1: mma.sync projections; 0: the FFMA2 kernel)
   long long small_dbg;  // SL_SMALL_DBG     (0)

@@ -491,7 +491,9 @@ bg_fused_kernel(const __grid_constant__ Maps maps, Params p) {
 constexpr int P_STAGES = 6;                          // 32 KB stages: 16 KB A + 16 KB half-B
 constexpr int P_STAGE_BYTES = A_BYTES + B_BYTES_MAX / 2;
 constexpr int P_BAR_BYTES = 8 * (2 * P_STAGES + 4 + 2 * MAX_N_TILES) + 16;   // barriers + the TMEM base word
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + STAGING_BYTES + W3_BYTES + P_BAR_BYTES;
+// (no W3 region: the pair kernel reads w3 through L1.  Keeping the CTA under 225 KB leaves room for one small CTA of
+// another kernel -- the register-resident up-sampling kernel needs 256 B -- next to it on the SM.)
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + STAGING_BYTES + P_BAR_BYTES;
 static_assert(P_SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;          // clears the CTA-pair peer bit of a shared::cluster address
 
@@ -537,7 +539,7 @@ constexpr int D_STAGE_BYTES = 2 * A_BYTES + B_BYTES_MAX;     // [A0 16 KB][A1 16
 static_assert(D_STAGES * D_STAGE_BYTES == P_STAGES * P_STAGE_BYTES, "both pair layouts use the same 192 KB ring");
 
 template <bool DEDUP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)   // 512, not THREADS: caps the kernel at 128 registers, see below
 bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
@@ -545,7 +547,7 @@ bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
   constexpr int NSTG = DEDUP ? D_STAGES : P_STAGES;
   constexpr int STG_BYTES = DEDUP ? D_STAGE_BYTES : P_STAGE_BYTES;
   const uint32_t stage_out = base + P_STAGES * P_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES + STAGING_BYTES + W3_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES + STAGING_BYTES);
   // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then h1_ready[slot][n-tile]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P_STAGES + 4 + 2 * MAX_N_TILES);
   const uint32_t bar0 = smem_u32(bars);

@@ -730,6 +730,9 @@ __global__ void __launch_bounds__(256) views_reduce_vec4_kernel(const float* __r
 int launch_upsample_prune(const float* logits_lr, int B, int K, int h, int w, int H, int W, float sy, float sx,
                           const uint8_t* label, int ignore_label, uint8_t* pred, unsigned long long* cm,
                           cudaStream_t st);                      // post_prune.cu
+int launch_upsample_regs(const float* logits_lr, int B, int K, int h, int w, int H, int W, float sy, float sx,
+                         const uint8_t* label, int ignore_label, uint8_t* pred, unsigned long long* cm,
+                         cudaStream_t st);                       // post_regs.cu
 
 static inline int grid_for(long long work_items, int per_sm) {
   long long blocks = (work_items + 255) / 256;
@@ -777,6 +780,17 @@ extern "C" int sl_upsample_argmax(const float* logits_lr, int B, int K, int h, i
       const bool fused = cm != nullptr && fused_env != 0;
       const int rc = sl::launch_upsample_prune(logits_lr, B, K, h, w, H, W, sy, sx, fused ? label : nullptr, ignore_label,
                                                pred, fused ? cmu : nullptr, st);
+      if (rc != -100) {
+        if (rc != 0 || cm == nullptr || fused) return rc;
+        sl::confusion_kernel<<<sl::grid_for((px + 15) / 16, 8), 256, 0, st>>>(label, pred, px, K, ignore_label, cmu, nullptr);
+        return SL_LAUNCH_RESULT();
+      }
+    }
+    if (((big && sl::env().post_regs != 0) || sl::env().post_regs == 2) && !conf && !probs && !logits_hr) {   // 2: any size (tests)
+      // prediction-only path at K = 8 / 12, up-sampling by >= 2x: source-row intervals in registers (post_regs.cu)
+      const bool fused = cm != nullptr && (pred == nullptr || fused_env != 0);
+      const int rc = sl::launch_upsample_regs(logits_lr, B, K, h, w, H, W, sy, sx, fused ? label : nullptr, ignore_label,
+                                              pred, fused ? cmu : nullptr, st);
       if (rc != -100) {
         if (rc != 0 || cm == nullptr || fused) return rc;
         sl::confusion_kernel<<<sl::grid_for((px + 15) / 16, 8), 256, 0, st>>>(label, pred, px, K, ignore_label, cmu, nullptr);

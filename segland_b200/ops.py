@@ -245,6 +245,14 @@ class PopHead:
     def fused_ok(self, N):
         return self.K <= 12 and self._use_tc(N)
 
+    def bg(self, feats, out):
+        """Background logit into out[:,0] by whichever kernel the head's mode and the shape select."""
+        N = feats.shape[2] * feats.shape[3]
+        if self._use_tc(N):
+            self.bg_tc(feats, out)
+        else:
+            self.bg_simt(feats, out)
+
     def bg_simt(self, feats, out):
         B, C, h, w = feats.shape
         p = self._plan
@@ -538,7 +546,7 @@ def window_accumulate(crop_logits, plan, flips=(0,), layout='bekhw', want_count=
 # ================================================================== dense post-processing
 @_on_input_device
 def upsample_argmax(logits, size, label=None, cm=None, ignore_label=IGNORE_LABEL, want_pred=True,
-                    want_conf=False, want_probs=False, want_logits=False):
+                    want_conf=False, want_probs=False, want_logits=False, pred_out=None):
     """F.interpolate(logits, size, mode='bilinear', align_corners=True) -> argmax(dim=1) -> uint8
     (eval_base.py:168-170, eval_ft.py:168-172), optionally fused with the confusion-matrix update
     (eval_base.py:172-178).  logits [B,K,h,w] fp32 CUDA.
@@ -546,13 +554,20 @@ def upsample_argmax(logits, size, label=None, cm=None, ignore_label=IGNORE_LABEL
     cm: int64 [K,K] CUDA accumulator (row = gt, col = pred), updated in place; needs label
         [B,H,W] uint8.  Returns a dict with the requested outputs: 'pred' uint8 [B,H,W],
         'conf' fp32 [B,H,W] and 'probs' fp32 [B,K,H,W] (softmax; spec: this repo), 'logits'
-        fp32 [B,K,H,W] (the up-sampled logits eval_base.py:190-191 dumps for fusemat)."""
+        fp32 [B,K,H,W] (the up-sampled logits eval_base.py:190-191 dumps for fusemat).
+    pred_out: optional caller-owned uint8 [B,H,W] buffer for 'pred'."""
     logits = _cuda(logits, torch.float32)
     B, K, h, w = logits.shape
     H, W = int(size[0]), int(size[1])
     dev = logits.device
     out = {}
-    pred = torch.empty(B, H, W, dtype=torch.uint8, device=dev) if want_pred else None
+    if want_pred and pred_out is not None:                    # caller-owned prediction buffer (no allocation on this call)
+        if pred_out.dtype != torch.uint8 or tuple(pred_out.shape) != (B, H, W) or pred_out.device != dev or \
+                not pred_out.is_contiguous():
+            raise ValueError(f'pred_out must be a contiguous uint8 [B,H,W]={B, H, W} tensor on {dev}')
+        pred = pred_out
+    else:
+        pred = torch.empty(B, H, W, dtype=torch.uint8, device=dev) if want_pred else None
     conf = torch.empty(B, H, W, dtype=torch.float32, device=dev) if want_conf else None
     probs = torch.empty(B, K, H, W, dtype=torch.float32, device=dev) if want_probs else None
     hr = torch.empty(B, K, H, W, dtype=torch.float32, device=dev) if want_logits else None

@@ -88,6 +88,127 @@ class TileEvaluator:
         return self.cm, ops.miou_from_confusion(self.cm, base_classes)
 
 
+class PipelinedTileEvaluator(TileEvaluator):
+    """TileEvaluator with the sweep software-pipelined over two streams: the head of batch t (foreground kernel, then
+    the tensor-bound background MLP) runs on a high-priority stream while the up-sample / arg-max / confusion kernel of
+    batch t-1 runs on a second stream UNDER the background MLP.  The two kernels are complementary -- the MLP keeps the
+    tensor pipe busy and leaves most issue slots idle, the post-processing kernel is bound by instruction issue and
+    touches neither tensor cores nor shared memory -- and they are sized to share an SM (pair kernel: 12 warp slots x
+    128 registers, 225 KB; post-processing: 128-thread CTAs of 128 registers, 256 B), so a pass costs
+    fg + max(bg, post) instead of fg + bg + post.  Results are identical to TileEvaluator (same kernels, integer
+    accumulation); low-res logits are double-buffered.
+
+    `step` returns the result dict of the PREVIOUS batch (None on the first call); `flush()` returns the last one.
+    Returned tensors are safe to use on the caller's current stream.  The prediction map lives in one of two buffers
+    owned by the evaluator (allocating a fresh map per batch on the second stream costs a cudaMalloc per step once two
+    streams share the caching allocator): it stays valid until the next-but-one `step`.  `finalize` flushes."""
+
+    def __init__(self, head: ops.PopHead, out_size, ignore_label=ops.IGNORE_LABEL):
+        super().__init__(head, out_size, ignore_label)
+        dev = head.device
+        self._hi = torch.cuda.Stream(device=dev, priority=-1)    # head kernels: placed first when both have CTAs pending
+        self._lo = torch.cuda.Stream(device=dev, priority=0)
+        self._lg = [None, None]
+        self._pred = [None, None]
+        self._ev_fg = [torch.cuda.Event() for _ in range(2)]
+        self._ev_bg = [torch.cuda.Event() for _ in range(2)]
+        self._ev_post = [torch.cuda.Event() for _ in range(2)]
+        self._n = 0
+        self._pending = None                                     # (buffer, labels, want_pred, kw) of the batch awaiting its post
+        self.last = None
+        self.trace = None                                        # set to a list to collect (name, start, end) CUDA events
+
+    def _mark(self, stream):
+        if self.trace is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    def _post(self, gate, cur):
+        if self._pending is None:
+            return None
+        b, labels, want_pred, kw = self._pending
+        self._pending = None
+        lo = self._lo
+        lo.wait_event(self._ev_bg[b])
+        if gate is not None:
+            lo.wait_event(gate)                                  # start together with the NEXT batch's background MLP
+        pred = None
+        if want_pred:
+            pred = self._pred[b]
+            want = (self._lg[b].shape[0], *self.out_size)
+            if pred is None or tuple(pred.shape) != want:
+                pred = self._pred[b] = torch.empty(want, dtype=torch.uint8, device=self._lg[b].device)
+        with torch.cuda.stream(lo):
+            t0 = self._mark(lo)
+            out = ops.upsample_argmax(self._lg[b], self.out_size, label=labels, cm=self.cm if labels is not None else None,
+                                      ignore_label=self.ignore_label, want_pred=want_pred, pred_out=pred, **kw)
+            t1 = self._mark(lo)
+            self._ev_post[b].record(lo)
+        if t0 is not None:
+            self.trace.append(('post', t0, t1))
+        cur.wait_event(self._ev_post[b])
+        for k, v in out.items():
+            if k != 'pred':
+                v.record_stream(cur)
+        if labels is not None:
+            labels.record_stream(lo)
+        self.last = out
+        return out
+
+    def step(self, features, labels=None, want_pred=True, **kw):
+        dev = self.head.device
+        cur = torch.cuda.current_stream(dev)
+        feats = ops._cuda(features, torch.bfloat16)
+        if labels is not None:
+            labels = ops._cuda(labels, torch.uint8)
+        B, _, h, w = feats.shape
+        b = self._n & 1
+        lg = self._lg[b]
+        if lg is None or lg.shape[0] != B or lg.shape[-2:] != (h, w):
+            lg = self._lg[b] = torch.empty(B, self.head.n_classes, h, w, dtype=torch.float32, device=feats.device)
+        hi = self._hi
+        hi.wait_stream(cur)                                      # inputs (and any H2D copy) are ready
+        if self._n >= 2:
+            hi.wait_event(self._ev_post[b])                      # logits buffer b has been consumed
+        with torch.cuda.stream(hi):
+            t0 = self._mark(hi)
+            if (h * w) % 8 == 0 and not self.head.fuse:
+                self.head(feats, out=lg, fg_only=True)
+                t1 = self._mark(hi)
+                self._ev_fg[b].record(hi)
+                self.head.bg(feats, lg)
+            else:                                                # padded / single-launch heads: no split point
+                t1 = self._mark(hi)
+                self._ev_fg[b].record(hi)
+                self.head(feats, out=lg)
+            t2 = self._mark(hi)
+            self._ev_bg[b].record(hi)
+        if t0 is not None:
+            self.trace += [('fg', t0, t1), ('bg', t1, t2)]
+        feats.record_stream(hi)
+        prev = self._post(self._ev_fg[b], cur)
+        self._pending = (b, labels, want_pred, kw)
+        self._n += 1
+        return prev
+
+    def flush(self):
+        """Run the post-processing of the last batch; returns its result dict (None when nothing is pending)."""
+        cur = torch.cuda.current_stream(self.head.device)
+        out = self._post(None, cur)
+        cur.wait_stream(self._hi)
+        return out
+
+    def reset(self):
+        self.flush()
+        super().reset()
+
+    def finalize(self, base_classes, group=None):
+        self.flush()
+        return super().finalize(base_classes, group)
+
+
 def prototype_mean_all_reduce_(per_image_sum, count, group=None):
     """Multi-GPU masked-average-pool prototypes: MAP is a mean of PER-IMAGE ratios
     (networks/pspnet.py:14-15), so every support image lives wholly on one rank; ranks sum
