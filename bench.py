@@ -328,7 +328,7 @@ def run_ours(args, rank, world, local_rank):
     # default: the sweep is software-pipelined over two streams (post-processing of pass p-1 underneath the background
     # MLP of pass p, sweep.PipelinedTileEvaluator); --no-pipeline runs the three kernels back to back on one stream
     pipelined = not args.no_pipeline and not fused
-    pev = sweep.PipelinedTileEvaluator(head, (TILE, TILE), fg_under_bg=not args.fg_on_main) if pipelined else None
+    pev = sweep.PipelinedTileEvaluator(head, (TILE, TILE)) if pipelined else None
 
     stream = torch.cuda.current_stream()
     ev_k = {k: [] for k in ('fg', 'bg', 'post')}
@@ -860,8 +860,6 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--tiles', type=int, default=32, help='distinct resident 1024^2 tiles per pass per GPU')
-    ap.add_argument('--fg-on-main', action='store_true', help='pipelined schedule with the stand-alone foreground kernel in '
-                    'front of the background MLP instead of sl_pop_fg_lite underneath it')
     ap.add_argument('--no-pipeline', action='store_true', help='run fg -> bg -> post back to back on one stream')
     ap.add_argument('--passes', type=int, default=48, help='passes over the resident tiles per step (48 x 32 tiles: '
                                                            '~55 ms per step, so 20 steps time > 1 s)')

@@ -130,23 +130,6 @@ SL_API int sl_pop_fg_lowres(const uint16_t *feat, int B, int C, int N,
                      const float *s_hat, const float *alpha, const float *beta, int K,
                      float *logits, int Ktot, const int *ch_map_host, void *stream);
 
-/* The same K foreground logits from a kernel that can SHARE an SM with sl_pop_bg_tc: 128-thread CTAs, <= 128
- * registers, no shared memory, CUDA cores only (features loaded straight into a register ring, prototypes read from
- * the kernel-parameter constant bank).  Slower on its own -- one CTA per SM next to the background MLP streams a few
- * hundred GB/s -- which is all it takes to hide the foreground pass underneath the tensor-bound background MLP on a
- * second stream (sweep.PipelinedTileEvaluator).  Packed fp32 FMAs over the channels in ascending order: bit-identical
- * to sl_pop_fg_lowres's FFMA2 kernel (SL_FG_MMA=0) and within ~1e-7 of its default mma.sync kernel.  Same reference
- * lines as sl_pop_fg_lowres (pspnet_pop.py:108-109,114-115,150-157,178-182); C % 8 == 0, C <= 512, N % 8 == 0.
- *   ws_host: sl_pop_fg_lite_ws_bytes(K, C) bytes of HOST memory (pinned for a truly asynchronous copy) that
- *       sl_pop_fg_lite_prepare fills with s_hat by a stream-ordered device-to-host copy, once per weight update; the
- *       caller synchronises with that stream before the first sl_pop_fg_lite call, which reads it on the host to build
- *       its 16 KB parameter table (8 classes per launch). */
-SL_API size_t sl_pop_fg_lite_ws_bytes(int K, int C);
-SL_API int sl_pop_fg_lite_prepare(const float *s_hat, int K, int C, void *ws_host, void *stream);
-SL_API int sl_pop_fg_lite(const uint16_t *feat, int B, int C, int N, const void *ws_host,
-                   const float *alpha, const float *beta, int K,
-                   float *logits, int Ktot, const int *ch_map_host, void *stream);
-
 /* Background logit (class 0), exact fp32 CUDA-core path:
  *   logit_0 = w3 . relu(W2 relu(W1' q))   written to channel `ch` of logits.
  */

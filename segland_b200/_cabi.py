@@ -19,8 +19,6 @@ _SIGNATURES = {
     'sl_env_reload': [],
     'sl_pop_prepare': [_P, c_int, c_int, c_int] + [_P] * 19,
     'sl_pop_fg_lowres': [_P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int, POINTER(c_int), _P],
-    'sl_pop_fg_lite_prepare': [_P, c_int, c_int, _P, _P],
-    'sl_pop_fg_lite': [_P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int, POINTER(c_int), _P],
     'sl_pop_bg_simt': [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P],
     'sl_pop_bg_tc': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, _P],
     'sl_pop_head_tc': [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_int, POINTER(c_int), _P, _P,
@@ -82,8 +80,6 @@ def lib():
         handle.sl_pop_prepare_bwd_ws_bytes.restype = c_size_t
         handle.sl_pop_prepare_ws_bytes.argtypes = [c_int, c_int]
         handle.sl_pop_prepare_ws_bytes.restype = c_size_t
-        handle.sl_pop_fg_lite_ws_bytes.argtypes = [c_int, c_int]
-        handle.sl_pop_fg_lite_ws_bytes.restype = c_size_t
         handle.sl_upsample_ce_ws_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
         handle.sl_upsample_ce_ws_bytes.restype = c_size_t
         handle.sl_tail_bn_relu_conv_ws_bytes.argtypes = [c_int, c_int, c_int]
@@ -106,7 +102,7 @@ def set_env(**switches):
 
 
 def exported_names():
-    return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes', 'sl_pop_prepare_ws_bytes', 'sl_pop_fg_lite_ws_bytes', 'sl_upsample_ce_ws_bytes',
+    return list(_SIGNATURES) + ['sl_error_string', 'sl_pop_bg_tc_ws_bytes', 'sl_pop_prepare_ws_bytes', 'sl_upsample_ce_ws_bytes',
                                      'sl_pop_head_bwd_ws_bytes', 'sl_pop_prepare_bwd_ws_bytes', 'sl_tail_bn_relu_conv_ws_bytes']
 
 

@@ -207,11 +207,6 @@ class PopHead:
                  ptr(bg[0]), ptr(bg[1]), ptr(bg[2]), ptr(plan.s_hat), ptr(plan.alpha), ptr(plan.beta),
                  ptr(plan.W1p_t), ptr(plan.W2_t), ptr(sp[0]), ptr(sp[1]), ptr(sp[2]), ptr(sp[3]), ptr(hf[0]), ptr(hf[1]),
                  ptr(ws), _stream())
-            # host copy of s_hat for the co-resident foreground kernel (sl_pop_fg_lite passes it as a kernel parameter)
-            self._fg_lite_ws = torch.empty(_cabi.lib().sl_pop_fg_lite_ws_bytes(K, C) // 4, dtype=torch.float32).pin_memory()
-            call('sl_pop_fg_lite_prepare', ptr(plan.s_hat), K, C, self._fg_lite_ws.data_ptr(), _stream())
-            self._fg_lite_ready = torch.cuda.Event()
-            self._fg_lite_ready.record(torch.cuda.current_stream(dev))
         self._plan = plan
         self._ch_map = int_array([1 + k for k in range(K)])
         return self
@@ -249,18 +244,6 @@ class PopHead:
 
     def fused_ok(self, N):
         return self.K <= 12 and self._use_tc(N)
-
-    def fg_lite(self, feats, out):
-        """The K foreground logits into out[:,1:] by the kernel that can share an SM with the background MLP
-        (sl_pop_fg_lite): packed fp32 FMAs, within ~1e-7 of the default kernel of __call__(fg_only=True)."""
-        B, C, h, w = feats.shape
-        p = self._plan
-        if self._fg_lite_ready is not None:                      # the host copy of s_hat (refresh) has landed
-            self._fg_lite_ready.synchronize()
-            self._fg_lite_ready = None
-        with torch.cuda.device(feats.device):
-            call('sl_pop_fg_lite', ptr(feats), B, C, h * w, self._fg_lite_ws.data_ptr(), ptr(p.alpha), ptr(p.beta), self.K,
-                 ptr(out), out.shape[1], self._ch_map, _stream())
 
     def bg(self, feats, out):
         """Background logit into out[:,0] by whichever kernel the head's mode and the shape select."""

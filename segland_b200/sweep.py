@@ -95,28 +95,23 @@ class PipelinedTileEvaluator(TileEvaluator):
     tensor pipe busy and leaves most issue slots idle, the post-processing kernel is bound by instruction issue and
     touches neither tensor cores nor shared memory -- and they are sized to share an SM (pair kernel: 12 warp slots x
     128 registers, 225 KB; post-processing: 128-thread CTAs of 128 registers, 256 B), so a pass costs
-    fg + max(bg, post) instead of fg + bg + post (max(bg, post + fg) with fg_under_bg).  Low-res logits are
-    double-buffered; the confusion matrix is accumulated in integers as in TileEvaluator.
+    fg + max(bg, post) instead of fg + bg + post.  Results are identical to TileEvaluator (same kernels, integer
+    accumulation); low-res logits are double-buffered.  (The foreground kernel stays in front of the MLP: it is
+    HBM-bound and cheap, and moving it underneath as well was measured to gain nothing under the power cap,
+    profiles/r2b_overlap_probe.txt.)
 
     `step` returns the result dict of the PREVIOUS batch (None on the first call); `flush()` returns the last one.
     Returned tensors are safe to use on the caller's current stream.  The prediction map lives in one of two buffers
     owned by the evaluator (allocating a fresh map per batch on the second stream costs a cudaMalloc per step once two
     streams share the caching allocator): it stays valid until the next-but-one `step`.  `finalize` flushes."""
 
-    def __init__(self, head: ops.PopHead, out_size, ignore_label=ops.IGNORE_LABEL, fg_under_bg=True):
+    def __init__(self, head: ops.PopHead, out_size, ignore_label=ops.IGNORE_LABEL):
         super().__init__(head, out_size, ignore_label)
         dev = head.device
         self._hi = torch.cuda.Stream(device=dev, priority=-1)    # head kernels: placed first when both have CTAs pending
         self._lo = torch.cuda.Stream(device=dev, priority=0)
-        # fg_under_bg: the foreground logits of batch t are computed by sl_pop_fg_lite on the second stream as well,
-        # after the post-processing of batch t-1, both underneath the background MLP of batch t (a pass then costs
-        # max(bg, post + fg) instead of fg + max(bg, post)); False keeps the stand-alone foreground kernel in front of
-        # the background MLP on the first stream (then every number is bit-identical to TileEvaluator's; with
-        # sl_pop_fg_lite the foreground logits agree to ~1e-7: fp32 FMAs instead of mma.sync, another summation order).
-        self.fg_under_bg = bool(fg_under_bg)
         self._lg = [None, None]
         self._pred = [None, None]
-        self._ev_in = [torch.cuda.Event() for _ in range(2)]
         self._ev_fg = [torch.cuda.Event() for _ in range(2)]
         self._ev_bg = [torch.cuda.Event() for _ in range(2)]
         self._ev_post = [torch.cuda.Event() for _ in range(2)]
@@ -175,20 +170,17 @@ class PipelinedTileEvaluator(TileEvaluator):
         lg = self._lg[b]
         if lg is None or lg.shape[0] != B or lg.shape[-2:] != (h, w):
             lg = self._lg[b] = torch.empty(B, self.head.n_classes, h, w, dtype=torch.float32, device=feats.device)
-        hi, lo = self._hi, self._lo
+        hi = self._hi
         split = (h * w) % 8 == 0 and not self.head.fuse           # padded / single-launch heads have no split point
-        under = split and self.fg_under_bg
-        self._ev_in[b].record(cur)                               # inputs (and any H2D copy) are ready
-        hi.wait_event(self._ev_in[b])
+        hi.wait_stream(cur)                                      # inputs (and any H2D copy) are ready
         if self._n >= 2:
             hi.wait_event(self._ev_post[b])                      # logits buffer b has been consumed
         with torch.cuda.stream(hi):
             t0 = self._mark(hi)
-            if split and not under:
+            if split:
                 self.head(feats, out=lg, fg_only=True)
             t1 = self._mark(hi)
-            if not under:
-                self._ev_fg[b].record(hi)
+            self._ev_fg[b].record(hi)
             if split:
                 self.head.bg(feats, lg)
             else:
@@ -196,20 +188,11 @@ class PipelinedTileEvaluator(TileEvaluator):
             t2 = self._mark(hi)
             self._ev_bg[b].record(hi)
         if t0 is not None:
-            self.trace += [('bg', t1, t2)] + ([] if under else [('fg', t0, t1)])
+            self.trace += [('fg', t0, t1), ('bg', t1, t2)]
         feats.record_stream(hi)
-        # second stream: post-processing of the previous batch (it starts when that batch's background MLP ends, i.e.
-        # together with this batch's), then this batch's foreground logits
-        prev = self._post(None if under else self._ev_fg[b], cur)
-        if under:
-            lo.wait_event(self._ev_in[b])
-            with torch.cuda.stream(lo):
-                f0 = self._mark(lo)
-                self.head.fg_lite(feats, lg)
-                f1 = self._mark(lo)
-            if f0 is not None:
-                self.trace.append(('fg', f0, f1))
-            feats.record_stream(lo)
+        # second stream: the post-processing of the previous batch, gated on this batch's foreground kernel so that it
+        # starts together with this batch's background MLP
+        prev = self._post(self._ev_fg[b], cur)
         self._pending = (b, labels, want_pred, kw)
         self._n += 1
         return prev
