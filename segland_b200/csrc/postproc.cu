@@ -767,7 +767,20 @@ extern "C" int sl_upsample_argmax(const float* logits_lr, int B, int K, int h, i
     // shared memory per CTA = 2*K*THREADS*16 B (K=12, 256 threads: 96 KB -> 2 CTAs/SM).
     const long long px = static_cast<long long>(B) * H * W;
     const bool big = px >= (8ll << 20) && W >= 1024 && K <= 12;
-    const int rows = big ? 32 : 16;
+    int rows = big ? 32 : 16;
+    if (big && (conf || probs || logits_hr)) {
+      // Soft outputs: 128 registers and 96 KB of row cache allow two 256-thread CTAs per SM, so 16 tiles x 32 bands =
+      // 512 CTAs run as 1.7 waves of 296.  Pick the band height that fills whole waves (28 rows: 37 bands x 16 tiles =
+      // 592 CTAs = 2.0 waves); cost = waves x (rows + the band's source-row refills at ~1.5 rows each).
+      const long long slots = 2ll * sl::num_sms();
+      const long long gx = (W / 4 + 255) / 256;
+      double best = 1e30;
+      for (int r = 16; r <= 64; r += 2) {
+        const long long ctas = gx * ((H + r - 1) / r) * B;
+        const double cost = static_cast<double>((ctas + slots - 1) / slots) * (r + 1.5 * (r * static_cast<double>(sy) + 2.0));
+        if (cost < best) { best = cost; rows = r; }
+      }
+    }
     // When the prediction map is written anyway, the confusion matrix is accumulated by a second launch over
     // (label, pred) -- the map is still in L2 -- instead of inside the interpolation kernel: that kernel is bound by
     // instruction issue, and on noisy predictions (runs of equal (label, pred) pairs broken every few pixels) the
