@@ -38,7 +38,7 @@ extern "C" {
  * They are read ONCE per process (no getenv on the launch path); sl_env_reload() re-reads them.
  *   SL_POST_PRUNE=1     sl_upsample_argmax's prediction-only path on the per-cell class-pruning kernel (post_prune.cu)
  *                       instead of the row-cached kernel: identical results; see profiles/ for when it pays
- *   SL_POST_REGS=0      sl_upsample_argmax's prediction-only path (K = 8 / 12, up-sampling by >= 2x, >= 8 tiles) on the
+ *   SL_POST_REGS=0      sl_upsample_argmax's prediction-only path (K = 8 / 12, up-sampling by >= 2x) on the
  *                       row-cached shared-memory kernel instead of the register-resident one (post_regs.cu): identical results
  *   SL_TC_PAIR=0        (builds with -DSL_AB_VARIANTS only) background MLP on the single-CTA tcgen05 kernel instead of
  *                       the cta_group::2 pair kernel
