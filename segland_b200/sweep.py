@@ -120,6 +120,13 @@ class PipelinedTileEvaluator(TileEvaluator):
         self.last = None
         self.trace = None                                        # set to a list to collect (name, start, end) CUDA events
 
+    def _retire(self, t):
+        """A buffer replaced because the batch shape changed (the ragged last batch of a sweep) may still be read or
+        written by kernels queued on the two streams: tell the caching allocator before the reference is dropped."""
+        if t is not None:
+            t.record_stream(self._hi)
+            t.record_stream(self._lo)
+
     def _mark(self, stream):
         if self.trace is None:
             return None
@@ -141,6 +148,7 @@ class PipelinedTileEvaluator(TileEvaluator):
             pred = self._pred[b]
             want = (self._lg[b].shape[0], *self.out_size)
             if pred is None or tuple(pred.shape) != want:
+                self._retire(pred)
                 pred = self._pred[b] = torch.empty(want, dtype=torch.uint8, device=self._lg[b].device)
         with torch.cuda.stream(lo):
             t0 = self._mark(lo)
@@ -169,6 +177,7 @@ class PipelinedTileEvaluator(TileEvaluator):
         b = self._n & 1
         lg = self._lg[b]
         if lg is None or lg.shape[0] != B or lg.shape[-2:] != (h, w):
+            self._retire(lg)
             lg = self._lg[b] = torch.empty(B, self.head.n_classes, h, w, dtype=torch.float32, device=feats.device)
         hi = self._hi
         split = (h * w) % 8 == 0 and not self.head.fuse           # padded / single-launch heads have no split point

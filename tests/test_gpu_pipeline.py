@@ -79,3 +79,29 @@ def test_pipelined_reset_and_unlabelled_batches(mods):
     assert torch.equal(r2['pred'], s2['pred']) and torch.equal(r2['probs'], s2['probs'])
     assert torch.equal(pipe.cm, seq.cm)
 
+
+
+def test_pipelined_ragged_last_batch(mods):
+    """80 tiles in batches of 32 end with a batch of 16: buffers are re-allocated mid-sweep while both streams are busy."""
+    ops, sweep = mods
+    st = synth.make_trained_like_state(512, 7, 0, seed=13)
+    head = ops.PopHead(st.base_emb, st.cls, None, None)
+    labels = synth.make_labels(10, 1024, 1024, st.n_classes, seed=60)
+    feats = synth.make_features(labels, st, 8, seed=60).cuda()
+    labels = labels.cuda()
+    seq = sweep.TileEvaluator(head, (1024, 1024))
+    pipe = sweep.PipelinedTileEvaluator(head, (1024, 1024))
+    ref, got = [], []
+    for rep in range(3):                                         # 4 + 4 + 2, three times over
+        for lo, hi in ((0, 4), (4, 8), (8, 10)):
+            ref.append(seq.step(feats[lo:hi], labels[lo:hi])['pred'].clone())
+            r = pipe.step(feats[lo:hi], labels[lo:hi])
+            if r is not None:
+                got.append(r['pred'].clone())
+            junk = torch.full((4, 8, 128, 128), float(rep), device='cuda')      # churn the allocator on the caller's stream
+            del junk
+    got.append(pipe.flush()['pred'].clone())
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    assert torch.equal(pipe.finalize(7)[0], seq.finalize(7)[0])
