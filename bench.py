@@ -128,15 +128,20 @@ def ev_pair():
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
-def time_loop(fn, iters, warm=3):
-    """Average device time of fn() in seconds (CUDA events on the current stream, synchronised both sides)."""
+def time_loop(fn, iters, warm=3, finish=None):
+    """Average device time of fn() in seconds (CUDA events on the current stream, synchronised both sides); `finish`
+    (e.g. the flush of a pipelined evaluator) runs once inside the timed region after the last fn()."""
     for _ in range(warm):
         fn()
+    if finish is not None:
+        finish()
     torch.cuda.synchronize()
     a, b = ev_pair()
     a.record()
     for _ in range(iters):
         fn()
+    if finish is not None:
+        finish()
     b.record()
     torch.cuda.synchronize()
     return a.elapsed_time(b) / iters * 1e-3
@@ -735,9 +740,17 @@ def run_config3(rank, world, dev, peaks, args):
     probability-map output: (a) whole 1024^2 tile, original + h-flip views averaged at feature resolution
     (sl_views_reduce); (b) sliding window -- 512-px crops at stride 384 (3 x 3 windows, the last pulled back to the
     border), original + h-flip per crop, stitched with sl_window_accumulate -- then the fused up-sample + softmax."""
-    from segland_b200 import ops, synth
+    from segland_b200 import ops, sweep, synth
     out = {}
     Tt = args.c3_tiles
+    n_it = max(10, args.steps)
+
+    def pipelined_time(head, reduce, feats):
+        """The same step through sweep.PipelinedTileEvaluator (up-sampling + soft-max of step t-1 on a second stream
+        underneath the head of step t; the register-resident kernel shares an SM with the pair kernel)."""
+        pev = sweep.PipelinedTileEvaluator(head, (TILE, TILE), reduce=reduce)
+        t = time_loop(lambda: pev.step(feats, want_probs=True), n_it, finish=pev.flush)
+        return max_over_ranks(t, world, dev)
     for name, Cm in (('ConvNeXt-T C=192', 192), ('Swin-T/S C=96', 96)):
         stc = synth.make_head_state(Cm, KB, 4, seed=2)
         head = ops.PopHead(stc.base_emb, stc.cls, stc.novel_emb, stc.cls_n, device=dev)
@@ -760,7 +773,12 @@ def run_config3(rank, world, dev, peaks, args):
                 e[3].record()
                 marks['whole'] = e
             return r
-        t_whole = max_over_ranks(time_loop(whole, max(10, args.steps)), world, dev)
+        t_whole_seq = max_over_ranks(time_loop(whole, n_it), world, dev)
+        # narrow heads (C <= 128) run on the weights-resident kernel, whose 14 warps x 128 registers fill the register
+        # file: nothing can share its SMs, so those models keep the back-to-back schedule
+        use_pipe = not args.no_pipeline and Cm > 128
+        t_whole = t_whole_seq if not use_pipe else pipelined_time(
+            head, lambda x: ops.aggregate_views(x.view(2, Tt, K, hw, hw), [0, 1]), feats)
         whole(True)
         torch.cuda.synchronize()
         e = marks['whole']
@@ -790,7 +808,9 @@ def run_config3(rank, world, dev, peaks, args):
                 e[3].record()
                 marks['sliding'] = e
             return r
-        t_slide = max_over_ranks(time_loop(sliding, max(10, args.steps)), world, dev)
+        t_slide_seq = max_over_ranks(time_loop(sliding, n_it), world, dev)
+        t_slide = t_slide_seq if not use_pipe else pipelined_time(
+            head, lambda x: ops.window_accumulate(x.view(Tt, E, K, hc, wc), plan, flips), cf)
         sliding(True)
         torch.cuda.synchronize()
         e = marks['sliding']
@@ -801,9 +821,13 @@ def run_config3(rank, world, dev, peaks, args):
         bg_flops = (4.0 * Cm * Cm + 2.0 * Cm) * hw * hw * 2 * Tt
         out[name] = {
             'tiles_per_step_per_gpu': Tt,
-            'whole_tile_2_views': {'tiles_per_s': world * Tt / t_whole, 'ms_per_step': 1e3 * t_whole, 'kernels': k_whole,
+            'schedule': ('pipelined (views / window reduction + up-sampling + soft-max of step t-1 underneath the head of step t)'
+                         if use_pipe else 'sequential (the narrow-head kernel leaves no room on the SM)'),
+            'whole_tile_2_views': {'tiles_per_s': world * Tt / t_whole, 'ms_per_step': 1e3 * t_whole,
+                                   'sequential_tiles_per_s': world * Tt / t_whole_seq, 'kernels_sequential': k_whole, 'kernels': k_whole,
                                    'head_tflops_algorithmic': bg_flops / (k_whole['head_ms'] * 1e-3) / 1e12},
-            'sliding_window_3x3_2_views': {'tiles_per_s': world * Tt / t_slide, 'ms_per_step': 1e3 * t_slide, 'kernels': k_slide,
+            'sliding_window_3x3_2_views': {'tiles_per_s': world * Tt / t_slide, 'ms_per_step': 1e3 * t_slide,
+                                           'sequential_tiles_per_s': world * Tt / t_slide_seq, 'kernels': k_slide,
                                            'crops_per_tile': E,
                                            'window_accumulate_roofline': {'bound': 'hbm', 'achieved': win_gbs, 'peak': peaks['hbm_gbs'],
                                                                           'unit': 'GB/s', 'frac': win_gbs / peaks['hbm_gbs'],

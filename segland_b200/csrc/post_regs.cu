@@ -53,10 +53,13 @@ __device__ __forceinline__ void tour(const float (&v)[K], float& best, int& idx)
 
 // A thread owns COLS consecutive output columns (COLS = 4: uchar4 label / pred accesses; 2 for K = 12 to stay under
 // 128 registers) of one image and walks down a band of output rows.  grid (ceil(W / (COLS*THREADS)), bands, B).
-template <int K, int COLS, int THREADS>
+// SOFT: also the soft-max outputs of the row-cached kernel's soft path (conf = max probability, probs = [B,K,H,W]), with
+// its formulas -- e = ex2.approx(v*log2e - best*log2e), sums in class order, rcp.approx -- so the bits are the same.
+template <int K, int COLS, int THREADS, bool SOFT>
 __global__ void __launch_bounds__(THREADS, 512 / THREADS) upsample_regs_kernel(
     const float* __restrict__ logits_lr, int h, int w, int H, int W, int ivals_per_band, float sy, float sx,
-    const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred, unsigned long long* __restrict__ cm) {
+    const uint8_t* __restrict__ label, int ignore_label, uint8_t* __restrict__ pred, float* __restrict__ conf,
+    float* __restrict__ probs, unsigned long long* __restrict__ cm) {
   static_assert(COLS == 4 || COLS == 2, "COLS");
   constexpr int NP = COLS / 2;                                   // packed pairs per class
   __shared__ unsigned int hist[K * K];
@@ -203,6 +206,33 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) upsample_regs_kernel(
           if (y + 4 < y_end) lq3 = load_label(label + pix + 4 * static_cast<size_t>(W));
         }
         int idx[COLS];
+        // soft-max of one packed pair of pixels from its K values and their maximum (row-cached kernel's formulas)
+        auto soft_pair = [&](float (&va)[K], float (&vb)[K], float best_a, float best_b, int q) {
+          constexpr float kLog2e = 1.4426950408889634f;
+          const float nba = -best_a * kLog2e, nbb = -best_b * kLog2e;
+          float sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            float ea, eb;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(fmaf(va[k], kLog2e, nba)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(fmaf(vb[k], kLog2e, nbb)));
+            va[k] = ea; vb[k] = eb;
+            sa += ea; sb += eb;
+          }
+          float ia, ib;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ia) : "f"(sa));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ib) : "f"(sb));
+          if (conf) *reinterpret_cast<float2*>(conf + pix + 2 * q) = make_float2(ia, ib);
+          if (probs) {
+            float* dst = probs + (static_cast<size_t>(b) * K) * (static_cast<size_t>(H) * W) + (pix - static_cast<size_t>(b) * H * W) + 2 * q;
+            const float2 inv = make_float2(ia, ib);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              __stcs(reinterpret_cast<float2*>(dst), pr_mul2(make_float2(va[k], vb[k]), inv));   // streaming: written once
+              dst += static_cast<size_t>(H) * W;
+            }
+          }
+        };
         if (!bad) {
 #pragma unroll
           for (int q = 0; q < NP; ++q) {
@@ -213,23 +243,26 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) upsample_regs_kernel(
               va[k] = t.x;
               vb[k] = t.y;
             }
-            float best;
-            tour<0, K, K>(va, best, idx[2 * q]);
-            tour<0, K, K>(vb, best, idx[2 * q + 1]);
+            float best_a, best_b;
+            tour<0, K, K>(va, best_a, idx[2 * q]);
+            tour<0, K, K>(vb, best_b, idx[2 * q + 1]);
+            if constexpr (SOFT) soft_pair(va, vb, best_a, best_b, q);
           }
         } else {
-          float best[COLS];
 #pragma unroll
-          for (int j = 0; j < COLS; ++j) { best[j] = -INFINITY; idx[j] = 0; }
+          for (int q = 0; q < NP; ++q) {
+            float va[K], vb[K];
+            float best_a = -INFINITY, best_b = -INFINITY;
+            idx[2 * q] = 0; idx[2 * q + 1] = 0;
 #pragma unroll
-          for (int k = 0; k < K; ++k)
-#pragma unroll
-            for (int q = 0; q < NP; ++q) {
-              const float va = __fmaf_rn(cy.l1, bot[k][q].x, __fmul_rn(cy.l0, top[k][q].x));
-              const float vb = __fmaf_rn(cy.l1, bot[k][q].y, __fmul_rn(cy.l0, top[k][q].y));
-              if (va > best[2 * q] || (va != va && best[2 * q] == best[2 * q])) { best[2 * q] = va; idx[2 * q] = k; }
-              if (vb > best[2 * q + 1] || (vb != vb && best[2 * q + 1] == best[2 * q + 1])) { best[2 * q + 1] = vb; idx[2 * q + 1] = k; }
+            for (int k = 0; k < K; ++k) {
+              va[k] = __fmaf_rn(cy.l1, bot[k][q].x, __fmul_rn(cy.l0, top[k][q].x));
+              vb[k] = __fmaf_rn(cy.l1, bot[k][q].y, __fmul_rn(cy.l0, top[k][q].y));
+              if (va[k] > best_a || (va[k] != va[k] && best_a == best_a)) { best_a = va[k]; idx[2 * q] = k; }
+              if (vb[k] > best_b || (vb[k] != vb[k] && best_b == best_b)) { best_b = vb[k]; idx[2 * q + 1] = k; }
             }
+            if constexpr (SOFT) soft_pair(va, vb, best_a, best_b, q);
+          }
         }
         uint32_t p4 = static_cast<uint32_t>(idx[0]) | (static_cast<uint32_t>(idx[1]) << 8);
         if constexpr (COLS == 4) p4 |= (static_cast<uint32_t>(idx[2]) << 16) | (static_cast<uint32_t>(idx[3]) << 24);
@@ -318,7 +351,9 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) upsample_regs_kernel(
 
 // Returns -100 when the shape is outside this kernel's range (the caller falls back to the row-cached kernel).
 int launch_upsample_regs(const float* logits_lr, int B, int K, int h, int w, int H, int W, float sy, float sx,
-                         const uint8_t* label, int ignore_label, uint8_t* pred, unsigned long long* cm, cudaStream_t st) {
+                         const uint8_t* label, int ignore_label, uint8_t* pred, float* conf, float* probs,
+                         unsigned long long* cm, cudaStream_t st) {
+  if ((conf != nullptr || probs != nullptr) && K != 12) return -100;   // K = 8 soft outputs: four columns per thread spill; row-cached kernel
   if (!(K == 8 || K == 12) || W % 4 != 0 || B > 65535 ||
       !(sy > 0.f && sy <= 0.5f && sx > 0.f && sx <= (K == 8 ? 0.3f : 0.5f)) || h < 2) return -100;
   // 128-thread CTAs: 16 K registers and 256 B of shared memory, so that one CTA fits on an SM NEXT TO a CTA of the
@@ -344,10 +379,11 @@ int launch_upsample_regs(const float* logits_lr, int B, int K, int h, int w, int
   }
   if (best_n == 0) return -100;
   const dim3 grid(gx, (intervals + best_n - 1) / best_n, B);
-#define SL_REGS_LAUNCH(KK, CC, TT) upsample_regs_kernel<KK, CC, TT><<<grid, TT, 0, st>>>( \
-      logits_lr, h, w, H, W, best_n, sy, sx, label, ignore_label, pred, cm)
-  if (K == 8) SL_REGS_LAUNCH(8, 4, threads);
-  else SL_REGS_LAUNCH(12, 2, threads);
+#define SL_REGS_LAUNCH(KK, CC, TT, SOFT) upsample_regs_kernel<KK, CC, TT, SOFT><<<grid, TT, 0, st>>>( \
+      logits_lr, h, w, H, W, best_n, sy, sx, label, ignore_label, pred, conf, probs, cm)
+  const bool soft = conf != nullptr || probs != nullptr;
+  if (K == 8) { if (soft) SL_REGS_LAUNCH(8, 4, threads, true); else SL_REGS_LAUNCH(8, 4, threads, false); }
+  else { if (soft) SL_REGS_LAUNCH(12, 2, threads, true); else SL_REGS_LAUNCH(12, 2, threads, false); }
 #undef SL_REGS_LAUNCH
   return SL_LAUNCH_RESULT();
 }

@@ -546,7 +546,7 @@ def window_accumulate(crop_logits, plan, flips=(0,), layout='bekhw', want_count=
 # ================================================================== dense post-processing
 @_on_input_device
 def upsample_argmax(logits, size, label=None, cm=None, ignore_label=IGNORE_LABEL, want_pred=True,
-                    want_conf=False, want_probs=False, want_logits=False, pred_out=None):
+                    want_conf=False, want_probs=False, want_logits=False, pred_out=None, out_bufs=None):
     """F.interpolate(logits, size, mode='bilinear', align_corners=True) -> argmax(dim=1) -> uint8
     (eval_base.py:168-170, eval_ft.py:168-172), optionally fused with the confusion-matrix update
     (eval_base.py:172-178).  logits [B,K,h,w] fp32 CUDA.
@@ -555,21 +555,27 @@ def upsample_argmax(logits, size, label=None, cm=None, ignore_label=IGNORE_LABEL
         [B,H,W] uint8.  Returns a dict with the requested outputs: 'pred' uint8 [B,H,W],
         'conf' fp32 [B,H,W] and 'probs' fp32 [B,K,H,W] (softmax; spec: this repo), 'logits'
         fp32 [B,K,H,W] (the up-sampled logits eval_base.py:190-191 dumps for fusemat).
-    pred_out: optional caller-owned uint8 [B,H,W] buffer for 'pred'."""
+    pred_out: optional caller-owned uint8 [B,H,W] buffer for 'pred'; out_bufs: optional dict of caller-owned buffers
+    for 'pred' / 'conf' / 'probs' (no allocation for those outputs)."""
     logits = _cuda(logits, torch.float32)
     B, K, h, w = logits.shape
     H, W = int(size[0]), int(size[1])
     dev = logits.device
     out = {}
-    if want_pred and pred_out is not None:                    # caller-owned prediction buffer (no allocation on this call)
-        if pred_out.dtype != torch.uint8 or tuple(pred_out.shape) != (B, H, W) or pred_out.device != dev or \
-                not pred_out.is_contiguous():
-            raise ValueError(f'pred_out must be a contiguous uint8 [B,H,W]={B, H, W} tensor on {dev}')
-        pred = pred_out
-    else:
-        pred = torch.empty(B, H, W, dtype=torch.uint8, device=dev) if want_pred else None
-    conf = torch.empty(B, H, W, dtype=torch.float32, device=dev) if want_conf else None
-    probs = torch.empty(B, K, H, W, dtype=torch.float32, device=dev) if want_probs else None
+    def buf(name, want, shape, dtype):                       # caller-owned output buffer (no allocation) or a fresh one
+        if not want:
+            return None
+        given = (out_bufs or {}).get(name)
+        if name == 'pred' and given is None:
+            given = pred_out
+        if given is None:
+            return torch.empty(shape, dtype=dtype, device=dev)
+        if given.dtype != dtype or tuple(given.shape) != tuple(shape) or given.device != dev or not given.is_contiguous():
+            raise ValueError(f'{name} buffer must be a contiguous {dtype} {tuple(shape)} tensor on {dev}')
+        return given
+    pred = buf('pred', want_pred, (B, H, W), torch.uint8)
+    conf = buf('conf', want_conf, (B, H, W), torch.float32)
+    probs = buf('probs', want_probs, (B, K, H, W), torch.float32)
     hr = torch.empty(B, K, H, W, dtype=torch.float32, device=dev) if want_logits else None
     if cm is not None:
         if label is None:

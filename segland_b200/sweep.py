@@ -59,10 +59,15 @@ class TileEvaluator:
     """eval_base.py:162-199 / eval_ft.py:162-202 after the decoder, for a stream of tile batches:
     head -> align-corners upsample -> argmax -> confusion accumulation, all on the device."""
 
-    def __init__(self, head: ops.PopHead, out_size, ignore_label=ops.IGNORE_LABEL):
+    def __init__(self, head: ops.PopHead, out_size, ignore_label=ops.IGNORE_LABEL, reduce=None):
+        """reduce: optional callable applied to the head's low-res logits before the up-sampling, on the stream the
+        post-processing runs on -- test-time view averaging (`lambda lg: ops.aggregate_views(lg.view(V, -1, *lg.shape[1:]),
+        flips)`) or sliding-window stitching (`lambda lg: ops.window_accumulate(lg.view(B, E, ...), plan, flips)`); the
+        features of a step then hold all views / crops of its tiles and labels stay per tile."""
         self.head = head
         self.out_size = (int(out_size[0]), int(out_size[1]))
         self.ignore_label = ignore_label
+        self.reduce = reduce
         K = head.n_classes
         self.cm = torch.zeros(K, K, dtype=torch.int64, device=head.device)
         self._logits = None
@@ -78,6 +83,8 @@ class TileEvaluator:
         if self._logits is None or self._logits.shape[0] != B or self._logits.shape[-2:] != (h, w):
             self._logits = torch.empty(B, self.head.n_classes, h, w, dtype=torch.float32, device=feats.device)
         logits = self.head(feats, out=self._logits)
+        if self.reduce is not None:
+            logits = self.reduce(logits)
         return ops.upsample_argmax(logits, self.out_size, label=labels, cm=self.cm if labels is not None else None,
                                    ignore_label=self.ignore_label, want_pred=want_pred, **kw)
 
@@ -101,12 +108,14 @@ class PipelinedTileEvaluator(TileEvaluator):
     profiles/r2b_overlap_probe.txt.)
 
     `step` returns the result dict of the PREVIOUS batch (None on the first call); `flush()` returns the last one.
-    Returned tensors are safe to use on the caller's current stream.  The prediction map lives in one of two buffers
-    owned by the evaluator (allocating a fresh map per batch on the second stream costs a cudaMalloc per step once two
-    streams share the caching allocator): it stays valid until the next-but-one `step`.  `finalize` flushes."""
+    Returned tensors are safe to use on the caller's current stream.  The map-sized outputs (pred, conf, probs) live in
+    one of two buffer sets owned by the evaluator -- a fresh map per batch on the second stream would have to be handed
+    back to the caller's stream with record_stream, and with the host running ahead of the GPU the caching allocator then
+    cannot recycle it and falls back to one cudaMalloc per step (2 ms) -- so they stay valid until the next-but-one
+    `step`.  `finalize` flushes."""
 
-    def __init__(self, head: ops.PopHead, out_size, ignore_label=ops.IGNORE_LABEL):
-        super().__init__(head, out_size, ignore_label)
+    def __init__(self, head: ops.PopHead, out_size, ignore_label=ops.IGNORE_LABEL, reduce=None):
+        super().__init__(head, out_size, ignore_label, reduce)
         dev = head.device
         self._hi = torch.cuda.Stream(device=dev, priority=-1)    # head kernels: placed first when both have CTAs pending
         self._lo = torch.cuda.Stream(device=dev, priority=0)
@@ -126,6 +135,7 @@ class PipelinedTileEvaluator(TileEvaluator):
         if t is not None:
             t.record_stream(self._hi)
             t.record_stream(self._lo)
+            t.record_stream(torch.cuda.current_stream(t.device))  # the caller may still be reading a returned map
 
     def _mark(self, stream):
         if self.trace is None:
@@ -143,24 +153,30 @@ class PipelinedTileEvaluator(TileEvaluator):
         lo.wait_event(self._ev_bg[b])
         if gate is not None:
             lo.wait_event(gate)                                  # start together with the NEXT batch's background MLP
-        pred = None
-        if want_pred:
-            pred = self._pred[b]
-            want = (self._lg[b].shape[0], *self.out_size)
-            if pred is None or tuple(pred.shape) != want:
-                self._retire(pred)
-                pred = self._pred[b] = torch.empty(want, dtype=torch.uint8, device=self._lg[b].device)
         with torch.cuda.stream(lo):
             t0 = self._mark(lo)
-            out = ops.upsample_argmax(self._lg[b], self.out_size, label=labels, cm=self.cm if labels is not None else None,
-                                      ignore_label=self.ignore_label, want_pred=want_pred, pred_out=pred, **kw)
+            lg = self._lg[b] if self.reduce is None else self.reduce(self._lg[b])
+            # every map-sized output lives in one of two evaluator-owned buffers (see the class docstring)
+            Bt, Kt = lg.shape[0], lg.shape[1]
+            wants = {'pred': (want_pred, (Bt, *self.out_size), torch.uint8),
+                     'conf': (kw.get('want_conf', False), (Bt, *self.out_size), torch.float32),
+                     'probs': (kw.get('want_probs', False), (Bt, Kt, *self.out_size), torch.float32)}
+            bufs = self._pred[b] if self._pred[b] is not None else {}
+            self._pred[b] = bufs
+            for name, (want, shape, dtype) in wants.items():
+                if want and (name not in bufs or tuple(bufs[name].shape) != shape):
+                    self._retire(bufs.get(name))
+                    bufs[name] = torch.empty(shape, dtype=dtype, device=lg.device)
+            out = ops.upsample_argmax(lg, self.out_size, label=labels, cm=self.cm if labels is not None else None,
+                                      ignore_label=self.ignore_label, want_pred=want_pred,
+                                      out_bufs={k: v for k, v in bufs.items() if wants[k][0]}, **kw)
             t1 = self._mark(lo)
             self._ev_post[b].record(lo)
         if t0 is not None:
             self.trace.append(('post', t0, t1))
         cur.wait_event(self._ev_post[b])
         for k, v in out.items():
-            if k != 'pred':
+            if k not in ('pred', 'conf', 'probs'):               # the up-sampled logits are allocated per call
                 v.record_stream(cur)
         if labels is not None:
             labels.record_stream(lo)

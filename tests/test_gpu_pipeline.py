@@ -105,3 +105,46 @@ def test_pipelined_ragged_last_batch(mods):
     for a, b in zip(got, ref):
         assert torch.equal(a, b)
     assert torch.equal(pipe.finalize(7)[0], seq.finalize(7)[0])
+
+
+def test_evaluators_with_view_and_window_reduction(mods):
+    """reduce= hook: flip-TTA averaging and sliding-window stitching run between the head and the up-sampling (on the
+    post-processing stream of the pipelined evaluator); probability maps included.  Both evaluators == the manual
+    composition of the same operators."""
+    ops, sweep = mods
+    st = synth.make_head_state(192, 7, 4, seed=3)
+    head = ops.PopHead(st.base_emb, st.cls, st.novel_emb, st.cls_n)
+    K, T, hw = head.n_classes, 2, 64
+    g = torch.Generator().manual_seed(9)
+    labels = torch.randint(0, K, (T, 256, 256), generator=g).to(torch.uint8).cuda()
+    # (a) two views per tile, view-major
+    feats = [torch.randn(2 * T, 192, hw, hw, generator=g).to(torch.bfloat16).cuda() for _ in range(3)]
+    red = lambda lg: ops.aggregate_views(lg.view(2, T, K, hw, hw), [0, 1])
+    manual = [ops.upsample_argmax(red(head(f)), (256, 256), want_probs=True) for f in feats]
+    for cls in (sweep.TileEvaluator, sweep.PipelinedTileEvaluator):
+        ev = cls(head, (256, 256), reduce=red)
+        outs = []
+        for f in feats:
+            r = ev.step(f, labels, want_probs=True)
+            if r is not None:
+                outs.append({k: v.clone() for k, v in r.items()})
+        if cls is sweep.PipelinedTileEvaluator:
+            outs.append({k: v.clone() for k, v in ev.flush().items()})
+        assert len(outs) == 3
+        for o, m in zip(outs, manual):
+            assert torch.equal(o['pred'], m['pred']) and torch.equal(o['probs'], m['probs'])
+        cm, _ = ev.finalize(7)
+        assert int(cm.sum()) == 3 * T * 256 * 256
+    # (b) sliding windows + flips
+    plan = ops.WindowPlan((256, 256), (128, 128), (96, 96), 4)
+    flips = (0, 1)
+    E = plan.n_windows * len(flips)
+    hc, wc = plan.crop_lr_hw
+    crops = [torch.randn(T * E, 192, hc, wc, generator=g).to(torch.bfloat16).cuda() for _ in range(2)]
+    redw = lambda lg: ops.window_accumulate(lg.view(T, E, K, hc, wc), plan, flips)
+    manual = [ops.upsample_argmax(redw(head(c)), (256, 256)) for c in crops]
+    pev = sweep.PipelinedTileEvaluator(head, (256, 256), reduce=redw)
+    assert pev.step(crops[0]) is None
+    a = pev.step(crops[1])['pred'].clone()
+    b = pev.flush()['pred'].clone()
+    assert torch.equal(a, manual[0]['pred']) and torch.equal(b, manual[1]['pred'])

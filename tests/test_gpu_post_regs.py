@@ -151,3 +151,55 @@ def test_regs_is_the_default_at_the_bench_shape_and_matches_oracle(ops):
     up = F.interpolate(lg.cpu(), size=(1024, 1024), mode='bilinear', align_corners=True)
     ref = np.argmax(up.numpy(), axis=1)
     assert (p1.cpu().numpy() == ref).mean() >= 0.9999
+
+
+def soft_both(ops, lg, size, label=None):
+    K = lg.shape[1]
+    res = []
+    try:
+        for regs in (1, 0):                                      # register kernel (K = 12) / row-cached kernel
+            _cabi.set_env(SL_POST_REGS=regs)
+            cm = torch.zeros(K, K, dtype=torch.int64, device='cuda') if label is not None else None
+            out = ops.upsample_argmax(lg, size, label=label, cm=cm, want_conf=True, want_probs=True)
+            res.append({k: v.clone() for k, v in out.items()} | ({'cm': cm.clone()} if cm is not None else {}))
+    finally:
+        _cabi.set_env(SL_POST_REGS=None)
+    return res
+
+
+@pytest.mark.parametrize('K,h,w,H,W', [
+    (12, 256, 256, 1024, 1024),     # configs[3]: ConvNeXt / Swin ft, x4, probability maps
+    (8, 128, 128, 1024, 1024),
+    (12, 60, 33, 300, 132),
+    (8, 125, 120, 1000, 960),
+    (12, 9, 7, 18, 16),
+])
+def test_regs_soft_outputs_equal_row_cached(ops, K, h, w, H, W):
+    """Probability maps and confidences of the register kernel == the row-cached soft path bit for bit (same ex2 / rcp
+    formulas, same order), and == torch softmax of F.interpolate within the approximation error (spec: this repo)."""
+    for seed, lg in ((1, smooth_logits(2, K, h, w, 1)), (2, torch.randn(2, K, h, w, generator=torch.Generator().manual_seed(2)) * 3)):
+        g = torch.Generator().manual_seed(seed)
+        label = torch.randint(0, K, (2, H, W), generator=g).to(torch.uint8)
+        a, b = soft_both(ops, lg.cuda(), (H, W), label.cuda())
+        for k in ('pred', 'conf', 'probs', 'cm'):
+            assert torch.equal(a[k], b[k]), k
+        up = F.interpolate(lg, size=(H, W), mode='bilinear', align_corners=True)
+        ref = torch.softmax(up, dim=1)
+        assert (a['probs'].cpu() - ref).abs().max().item() <= 2e-6
+        assert (a['conf'].cpu() - ref.max(dim=1).values).abs().max().item() <= 2e-6
+
+
+def test_regs_soft_non_finite(ops):
+    K, h, w, H, W = 12, 32, 32, 128, 128
+    g = torch.Generator().manual_seed(7)
+    lg = smooth_logits(2, K, h, w, 7)
+    idx = torch.randint(0, lg.numel(), (100,), generator=g)
+    lg.view(-1)[idx[:50]] = float('nan')
+    lg.view(-1)[idx[50:]] = float('inf')
+    a, b = soft_both(ops, lg.cuda(), (H, W))
+    assert torch.equal(a['pred'], b['pred'])
+    fin = torch.isfinite(b['probs']).all(dim=1) & torch.isfinite(a['probs']).all(dim=1)
+    assert fin.float().mean().item() > 0.5
+    pa, pb = a['probs'].permute(0, 2, 3, 1)[fin], b['probs'].permute(0, 2, 3, 1)[fin]
+    assert (pa - pb).abs().max().item() <= 1e-6
+    assert torch.equal(torch.isfinite(a['probs']), torch.isfinite(b['probs']))
