@@ -27,8 +27,9 @@ constexpr int FM_THREADS = FM_WARPS * 32;
 constexpr int FM_PX = 128;                      // pixels per item
 constexpr int FM_KS = 16;                       // channels per k-step
 constexpr int FM_STAGE_BYTES = FM_KS * FM_PX * 2;   // 4 KB: two [16][64] blocks of 2 KB
-constexpr int FM_STAGES = 2;
+constexpr int FM_STAGES = 2;                    // per warp when all 16 warps of a CTA have items
 constexpr int FM_RING_BYTES = FM_STAGES * FM_STAGE_BYTES;
+constexpr int FM_MAX_STAGES = 32;               // one warp with items (a single tile: 128 items on 148 SMs) takes the whole ring
 constexpr int FM_SPLITS = 3;
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
@@ -94,17 +95,24 @@ pop_fg_mma_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N
     for (int s = 0; s < FM_SPLITS; ++s)
       afrag[(static_cast<size_t>(ks) * FM_SPLITS + s) * 32 + l] = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
   }
-  const uint32_t my_ring = tc::smem_u32(ring) + static_cast<uint32_t>(warp * FM_RING_BYTES);
-  const uint32_t my_bars = tc::smem_u32(bars) + static_cast<uint32_t>(warp * 8 * FM_STAGES);
-  if (lane == 0) {
-    for (int s = 0; s < FM_STAGES; ++s) tc::mbar_init(my_bars + 8u * s, 1);
+  // Small batches: only the first `active` warps of a CTA have items (item i belongs to warp (i / gridDim.x) of CTA
+  // i % gridDim.x), and one warp streaming its 131 KB through two 4 KB stages is latency-bound (18 us for one tile).
+  // The 128 KB of ring space are therefore divided among the warps that have work: `stages` = 2 x 16 / active (a power of
+  // two, up to 32), same loads, same order, same arithmetic -- only more of them in flight.
+  const int items_per_image = (N + FM_PX - 1) / FM_PX;
+  const long long n_items = static_cast<long long>(B) * items_per_image;
+  int active = static_cast<int>((n_items + gridDim.x - 1) / gridDim.x);
+  active = active >= 16 ? 16 : active > 8 ? 16 : active > 4 ? 8 : active > 2 ? 4 : active > 1 ? 2 : 1;
+  const int stages = FM_STAGES * (FM_WARPS / active);
+  const uint32_t my_ring = tc::smem_u32(ring) + static_cast<uint32_t>(warp * stages * FM_STAGE_BYTES);
+  const uint32_t my_bars = tc::smem_u32(bars) + static_cast<uint32_t>(warp * 8 * stages);
+  if (lane == 0 && warp < active) {
+    for (int s = 0; s < stages; ++s) tc::mbar_init(my_bars + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (warp == 0) tc::tma_prefetch_desc(&map_x);
   }
   __syncthreads();
 
-  const int items_per_image = (N + FM_PX - 1) / FM_PX;
-  const long long n_items = static_cast<long long>(B) * items_per_image;
   const long long first = static_cast<long long>(blockIdx.x) + static_cast<long long>(warp) * gridDim.x;
   const long long stride = static_cast<long long>(gridDim.x) * FM_WARPS;
   uint32_t phase_bits = 0;
@@ -116,14 +124,14 @@ pop_fg_mma_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N
     const int b = static_cast<int>(item / items_per_image);
     const int n0 = static_cast<int>(item - static_cast<long long>(b) * items_per_image) * FM_PX;
     auto issue = [&](int ks) {                                   // lane 0 only
-      const int s = ks % FM_STAGES;
+      const int s = ks & (stages - 1);
       const uint32_t dst = my_ring + static_cast<uint32_t>(s * FM_STAGE_BYTES);
       tc::mbar_expect_tx(my_bars + 8u * s, FM_STAGE_BYTES);
       tc::tma_load_3d(dst, &map_x, my_bars + 8u * s, n0, ks * FM_KS, b, tc::L2_EVICT_FIRST);
       tc::tma_load_3d(dst + FM_STAGE_BYTES / 2, &map_x, my_bars + 8u * s, n0 + 64, ks * FM_KS, b, tc::L2_EVICT_FIRST);
     };
     if (lane == 0)
-      for (int ks = 0; ks < FM_STAGES - 1 && ks < ksteps; ++ks) issue(ks);
+      for (int ks = 0; ks < stages - 1 && ks < ksteps; ++ks) issue(ks);
 
     float acc[FM_PX / 8][4];
 #pragma unroll
@@ -132,8 +140,8 @@ pop_fg_mma_kernel(const __grid_constant__ CUtensorMap map_x, int B, int C, int N
       for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
 
     for (int ks = 0; ks < ksteps; ++ks) {
-      const int s = ks % FM_STAGES;
-      if (lane == 0 && ks + FM_STAGES - 1 < ksteps) issue(ks + FM_STAGES - 1);
+      const int s = ks & (stages - 1);
+      if (lane == 0 && ks + stages - 1 < ksteps) issue(ks + stages - 1);
       tc::mbar_wait(my_bars + 8u * s, (phase_bits >> s) & 1u);
       phase_bits ^= 1u << s;
       const uint4 a0 = afrag[(static_cast<size_t>(ks) * FM_SPLITS + 0) * 32 + lane];
