@@ -52,7 +52,7 @@ def load_peaks():
 
 
 def load_traffic():
-    for name in ('r2_traffic.json', 'r1_traffic.json'):
+    for name in ('r2b_traffic.json', 'r2_traffic.json', 'r1_traffic.json'):
         p = os.path.join(ROOT, 'profiles', name)
         if os.path.exists(p):
             return json.load(open(p)), name
@@ -507,7 +507,7 @@ def run_ours(args, rank, world, local_rank):
                'roofline_hbm_stage': {'achieved': s_bytes_tile * T / (stage_s_ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
                                       'unit': 'GB/s', 'frac': s_bytes_tile * T / (stage_s_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
                                       'note': 'whole stage: algorithmic bytes per tile x tiles / stage time'},
-               'roofline_hbm': {'kernel': 'pop_fg_kernel (sl_pop_fg_lowres)', 'achieved': fg_gbs, 'peak': peaks['hbm_gbs'],
+               'roofline_hbm': {'kernel': 'pop_fg_mma_kernel (sl_pop_fg_lowres)', 'achieved': fg_gbs, 'peak': peaks['hbm_gbs'],
                                 'unit': 'GB/s', 'frac': fg_gbs / peaks['hbm_gbs'], 'bytes_per_launch': fg_bytes,
                                 'traffic': traffic.get('pop_fg_kernel', {}).get('base')},
                'post_roofline_hbm': {'kernel': 'sl_upsample_argmax (+ confusion)', 'achieved': post_bytes / (seq_ms['post'] * 1e-3) / 1e9,
