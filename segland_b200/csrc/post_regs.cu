@@ -1,5 +1,6 @@
-// sl_upsample_argmax, prediction-only path for up-sampling by >= 2x with K = 8 or 12 classes (the eval hot path:
-// eval_base.py:168-178, eval_ft.py:168-183): F.interpolate(bilinear, align_corners=True) -> argmax -> confusion counts.
+// sl_upsample_argmax for up-sampling by >= 2x with K = 8 or 12 classes (the eval hot path: eval_base.py:168-178,
+// eval_ft.py:168-183): F.interpolate(bilinear, align_corners=True) -> argmax -> confusion counts, and at K = 12 also the
+// soft-max outputs (confidence, probability maps; spec: this repo).
 //
 // The row-cached kernel (postproc.cu) keeps the horizontal lerps of the two live source rows in shared memory and
 // re-reads them for every output row: at K = 8 its row loop is 258 instructions per warp and output row, 144 of them
@@ -9,7 +10,7 @@
 // them, and the arg-max is a tournament (contiguous index groups, right side wins only when strictly greater = first
 // maximum) instead of a K-long dependent chain.  No shared memory in the row loop, no per-row "is this row staged"
 // bookkeeping.  Same expression tree as the row-cached kernel (v = fma(l1y, H1, l0y*H0), H = fma(l0x, a, l1x*b)), so
-// the predictions are bit-identical to it (tests/test_gpu_parity.py, tests/test_gpu_post_regs.py).  Non-finite inputs
+// every output is bit-identical to it (tests/test_gpu_parity.py, tests/test_gpu_post_regs.py).  Non-finite inputs
 // are detected when a source row is loaded and routed to the np.argmax-compatible compare (first maximum, NaN wins).
 #include "common.cuh"
 
@@ -382,7 +383,7 @@ int launch_upsample_regs(const float* logits_lr, int B, int K, int h, int w, int
 #define SL_REGS_LAUNCH(KK, CC, TT, SOFT) upsample_regs_kernel<KK, CC, TT, SOFT><<<grid, TT, 0, st>>>( \
       logits_lr, h, w, H, W, best_n, sy, sx, label, ignore_label, pred, conf, probs, cm)
   const bool soft = conf != nullptr || probs != nullptr;
-  if (K == 8) { if (soft) SL_REGS_LAUNCH(8, 4, threads, true); else SL_REGS_LAUNCH(8, 4, threads, false); }
+  if (K == 8) SL_REGS_LAUNCH(8, 4, threads, false);            // (soft outputs at K = 8 were turned away above)
   else { if (soft) SL_REGS_LAUNCH(12, 2, threads, true); else SL_REGS_LAUNCH(12, 2, threads, false); }
 #undef SL_REGS_LAUNCH
   return SL_LAUNCH_RESULT();
