@@ -11,6 +11,10 @@ One "pass" = the whole path over T = 32 distinct resident tiles per GPU,
     sl_pop_fg_lowres -> sl_pop_bg_tc -> sl_upsample_argmax (+ confusion)
 (sl_pop_prepare runs once per weight update, outside the sweep, as in PopHead); one "step" = --passes passes
 (default 48: 1,536 tiles, ~55 ms), so K = 20 steps time > 1 s and the SM clocks are sampled > 50 times under load.
+The sweep runs through sweep.PipelinedTileEvaluator: fg(p), bg(p) on one stream, the up-sampling / arg-max / confusion
+kernel of pass p-1 on a second stream underneath bg(p) (the two kernels are sized to share an SM), flushed inside the
+timed region; --no-pipeline runs the three kernels back to back, and a short second leg always does, so that the line
+carries every kernel's duration alone as well (`sequential`, `roofline.frac_kernel_alone`).
 T*16.8 MB of features is larger than the 126 MB L2, so every pass streams from HBM.  Weak scaling: every rank owns
 its own T tiles; the only collective is one int64 all-reduce of the confusion matrix at the end of the sweep
 (inside the timed region).
