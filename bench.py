@@ -520,6 +520,14 @@ def run_ours(args, rank, world, local_rank):
                                      'ms_alone': seq_ms['post'],
                                      'bound_note': 'instruction-issue bound, not HBM (ncu: profiles/r2b_ncu_post_regs.txt)'},
                'algorithmic_bytes_per_tile': s_bytes_tile}
+    if pipelined:
+        # what the HBM-bound stage costs once it is pipelined: the pass minus the background MLP running alone
+        marg_ms = elapsed_ms / (args.steps * P) - seq_ms['bg']
+        stage_s['marginal_in_pipelined_pass'] = {
+            'ms_per_pass': marg_ms, 'achieved': s_bytes_tile * T / (marg_ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+            'frac': s_bytes_tile * T / (marg_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+            'note': 'pipelined pass time minus the background MLP alone (sequential leg): foreground kernel + what hiding the '
+                    'post-processing underneath the MLP costs it'}
     cpu_tps, cores = cpu_reference_tiles_per_s(args.cpu_tiles) if world == 1 and args.cpu_tiles > 0 else (None, None)
     eager = gpu_eager_reference(args.eager_tiles, dev) if world == 1 and args.eager_tiles > 0 else None
     line = {
