@@ -538,8 +538,11 @@ constexpr int D_STAGES = 3;
 constexpr int D_STAGE_BYTES = 2 * A_BYTES + B_BYTES_MAX;     // [A0 16 KB][A1 16 KB][B0 16 KB][B1 16 KB]
 static_assert(D_STAGES * D_STAGE_BYTES == P_STAGES * P_STAGE_BYTES, "both pair layouts use the same 192 KB ring");
 
+// __launch_bounds__(512, 1), not (THREADS = 320, 1): caps the kernel at 128 registers (4 bytes of spill).  Its 10 warps
+// take 12 register-allocation slots = 49,152 registers, which leaves 16,384 -- one 128-thread, 128-register CTA of the
+// up-sampling kernel (post_regs.cu) -- next to it on the SM; at 146 registers nothing else fitted.
 template <bool DEDUP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)   // 512, not THREADS: caps the kernel at 128 registers, see below
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
 bg_pair_kernel(const __grid_constant__ Maps maps, Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
