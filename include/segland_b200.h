@@ -46,9 +46,8 @@ extern "C" {
  *                       pipeline stage (the schedule before the de-duplicated stages; 4-10 % slower)
  *   SL_TC_SMALL=0       C <= 128: streaming kernel instead of the weights-resident narrow-head kernel
  *   SL_PREP_SPLIT=1     sl_pop_prepare as five separate launches instead of three
- *   SL_POST_FUSED_CM=1/0 sl_upsample_argmax counts the confusion matrix inside the interpolation kernel (1) or in a
- *                       second launch over (label, pred) (0); default: inside for the pruning kernel, second launch for
- *                       the row-cached kernel
+ *   SL_POST_FUSED_CM=1/0 sl_upsample_argmax counts the confusion matrix inside the interpolation kernel (1, the default
+ *                       for every kernel) or in a second launch over (label, pred) (0)
  *   SL_TC_DEBUG=<bits>  knock-outs inside the single-CTA kernel (timing experiments, results INVALID)
  *   SL_FG_MMA=0         sl_pop_fg_lowres on the FFMA2 CUDA-core kernel instead of the mma.sync kernel
  *   SL_TAIL_FUSED=0     sl_tail_bn_relu_conv as two kernels (bf16 hi/lo planes in the workspace + generic GEMM)
